@@ -1,0 +1,207 @@
+/* mgbx.h -- C ABI of libmgbx.so: the B200-native (sm_100a) barrier-Newton engine.
+ *
+ * This is the drop-in boundary for the hot path of sloisel/MultiGridBarrier.jl.  The reference
+ * selects a backend with a `Device` marker and moves a pure-data `MGBProblem` across with
+ * `native_to_device(device, prob)` (src/device.jl:18-60, src/mgb.jl:798-842); the solve then runs
+ * `mgb_driver -> mgb_core -> mgb_step -> newton -> barrier f0/f1/f2` on backend arrays.  A Julia
+ * `B200Device` shim or the Python host mirror (multigridbarrier.jl_b200/) binds
+ * exactly the entry points below by `ccall` / `ctypes`:
+ *
+ *   mgbx_create        <- native_to_device(::Type{CUDADevice}, prob)   ext/MultiGridBarrierCUDAExt/conversion.jl:152-159
+ *   mgbx_step          <- mgb_step (+ newton, line search, f0/f1/f2, R'HR, solve)   src/mgb.jl:16-82, src/newton.jl:227-287
+ *   mgbx_scalars       <- the scalars mgb_core / mgb_driver read between t-steps   src/mgb.jl:135-136,454,526-527
+ *   mgbx_phase1_init   <- feasibility probe + slack initialisation    src/mgb.jl:417-448
+ *   mgbx_set_feasibility_box <- _feasibility_convex(Q, b, R, ...)     src/mgb.jl:217-287,504
+ *   mgbx_handoff       <- z2 = SOL_feas.z[1:len]                      src/mgb.jl:566
+ *   mgbx_matched_t     <- _matched_t                                  src/mgb.jl:307-330
+ *   mgbx_get_z / mgbx_set_z <- device_to_native / warm starts         src/mgb.jl:841
+ *   mgbx_destroy       <- mgb_cleanup                                 src/mgb.jl:840
+ *   mgbx_barrier_eval, mgbx_hessian_pattern, mgbx_hessian_values, mgbx_solve_newton_system,
+ *   mgbx_plan_pattern  <- fine-grained parity hooks for barrier(Q).f0/f1/f2 (src/convex.jl:155-202),
+ *                         _make_block_assembly_plan (src/BlockMatrices.jl:322-491) and solve (src/utils.jl:142-145)
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every array argument is HOST memory owned by the caller, the
+ *     library copies what it needs at mgbx_create and owns all device memory behind the handle;
+ *   - all matrices are column-major exactly as the Julia arrays are (an n x k grid is k contiguous
+ *     columns of length n; BlockDiag.data is p x p x N, src/BlockMatrices.jl:17-27);
+ *   - indices are 0-based int64 (Julia's Int minus one);
+ *   - every call returns an int status: 0 ok, >0 numerical outcome (MGBX_NOT_CONVERGED ...),
+ *     <0 error (argument / CUDA / allocation); no exceptions cross the ABI; the text of the last
+ *     error is available from mgbx_last_error();
+ *   - one handle <-> one CUDA stream <-> one host thread at a time (re-entrant across handles);
+ *   - there is NO CPU fallback: without a CUDA device mgbx_create fails with MGBX_ERR_CUDA.
+ */
+#ifndef MGBX_H
+#define MGBX_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGBX_ABI_VERSION 1
+#define MGBX_MAX_LEVELS 32
+#define MGBX_MAX_ND 12      /* rows of D seen by one node functor (incl. phase-I extras) */
+#define MGBX_MAX_PIECES 6
+#define MGBX_MAX_NI 6       /* inputs of one piece */
+#define MGBX_MAX_NC 8       /* rows of one piece (EP: nz) */
+
+enum {
+  MGBX_OK = 0,
+  MGBX_NOT_CONVERGED = 1,   /* Newton / step did not converge (caller applies kappa -> sqrt(kappa)) */
+  MGBX_NON_FINITE = 2,      /* the starting point of a Newton run is outside the barrier's domain */
+  MGBX_ERR_ARG = -1,
+  MGBX_ERR_CUDA = -2,
+  MGBX_ERR_ALLOC = -3,
+  MGBX_ERR_UNSUPPORTED = -4,
+  MGBX_ERR_INTERNAL = -5
+};
+
+enum { MGBX_PIECE_EP = 0, MGBX_PIECE_LINEAR = 1 };
+enum { MGBX_MAIN = 0, MGBX_FEAS = 1 };
+
+/* sparse matrix, CSR, 0-based, column indices sorted within a row */
+typedef struct {
+  int64_t rows, cols;
+  const int64_t *rowptr;   /* rows + 1 */
+  const int64_t *colind;   /* nnz */
+  const double *val;       /* nnz */
+} mgbx_csr;
+
+/* one convex piece: y -> A*y[idx] + b; EP: [q; s] in the power cone s >= |q|^p
+ * (src/convex_euclidian_power.jl:446-452); LINEAR: every row > 0 (src/convex_linear.jl:216-222) */
+typedef struct {
+  int32_t kind;            /* MGBX_PIECE_EP | MGBX_PIECE_LINEAR */
+  int32_t ni, nc;          /* inputs, rows (EP: nc == ni == nz) */
+  const int32_t *idx;      /* ni D-row indices, 0-based; NULL = 0..ni-1 (Colon) */
+  const double *A;         /* n x (nc*ni): row i holds vec(A_i) column-major */
+  const double *b;         /* n x nc */
+  const double *p;         /* n, EP only */
+  const double *mu;        /* n, EP only */
+} mgbx_piece;
+
+/* Convex set = pieces + optional select grid (src/convex_piecewise.jl:158-160) */
+typedef struct {
+  int32_t npieces;
+  const mgbx_piece *pieces;
+  const double *select;    /* n x npieces or NULL (all pieces active everywhere) */
+} mgbx_convex;
+
+/* one AMG (src/multigrid.jl:278-288): geometry-level data + level->fine prolongations */
+typedef struct {
+  int64_t n, N;            /* broken nodes, elements; n = p*N */
+  int32_t p, nu, nD, L;    /* nodes/element, state variables, rows of D, levels */
+  const double *w;         /* n quadrature weights */
+  int32_t nops;            /* distinct non-identity operators */
+  const double *const *op_data;  /* nops arrays p x p x N (BlockDiag.data) */
+  const int32_t *D_var;    /* nD: state variable of D row k */
+  const int32_t *D_op;     /* nD: operator id, -1 = identity */
+  const mgbx_csr *R_fine;  /* L matrices (nu*n) x m_l */
+  const mgbx_csr *T;       /* L-1 level transfers m_{l+1} x m_l with R_fine[l] = R_fine[l+1]*T[l] */
+  const int64_t *var_offsets;    /* L x (nu+1): first column of variable k at level l */
+} mgbx_amg;
+
+/* MGBProblem (src/mgb.jl:666-674) */
+typedef struct {
+  mgbx_amg amg[2];         /* [MGBX_MAIN], [MGBX_FEAS] (amg[1].n == 0: no phase-I data) */
+  const double *f_grid;    /* n x nD(main) */
+  const double *g_grid;    /* n x nu(main) */
+  mgbx_convex Q;
+  const double *barrier_weights; /* n (already normalised, 0 = node dropped) or NULL = 1/n */
+} mgbx_problem;
+
+typedef struct {
+  int32_t dense_direct_max;  /* Newton systems with <= this many unknowns: dense Cholesky (default 2048) */
+  int32_t coarse_max;        /* V-cycle is cut at the first level with <= this many unknowns (default 512) */
+  int32_t pcg_maxit;         /* default 400 */
+  double pcg_rtol;           /* relative residual, default 1e-11 */
+  int32_t smoother_sweeps;   /* l1-Jacobi / Chebyshev pre+post sweeps, default 2 */
+  int32_t condense;          /* 1 (default): eliminate node-local :full variables exactly before PCG */
+  int32_t device;            /* CUDA device ordinal, -1 = current */
+  int32_t verbose;
+} mgbx_config;
+
+/* options of one mgb_step (src/mgb.jl:16-30; defaults src/mgb.jl:360-363) */
+typedef struct {
+  int32_t maxit;             /* 10000 */
+  int32_t max_newton;        /* ceil(log2(-log2(eps)))+2 = 8 */
+  int32_t initial_step;
+  int32_t stop_kind;         /* 0 stopping_exact(theta), 1 stopping_inexact(lambda_tol, theta) */
+  double stop_lambda_tol;
+  double stop_theta;
+  int32_t finalize;          /* 0 none, 1 stopping_exact(finalize_theta) */
+  double finalize_theta;
+  int32_t line_search;       /* 0 backtracking(beta, c1), 1 illinois(beta) */
+  double ls_beta, ls_c1;
+} mgbx_step_opts;
+
+typedef struct {
+  int32_t converged;
+  int32_t its[MGBX_MAX_LEVELS];   /* Newton iterations per level (SOL.its) */
+  double y;                       /* last objective value */
+  double gnorm;                   /* last |g| */
+  double inc;                     /* last Newton decrement squared */
+  int32_t f01_evals, f2_evals, linear_solves, pcg_iters;
+  double ms_f01, ms_f2, ms_solve; /* device time (CUDA events) spent per stage */
+} mgbx_step_result;
+
+typedef struct {
+  double c_dot_Dz;                     /* sum_j dot(w .* f[:,j], D_j z) */
+  double var_max[MGBX_MAX_ND];         /* max over nodes of state variable k */
+  double var_absmax[MGBX_MAX_ND];      /* max |.| */
+  int32_t all_finite;
+} mgbx_scalars_out;
+
+typedef struct mgbx_handle mgbx_handle;
+
+void mgbx_default_config(mgbx_config *cfg);
+void mgbx_default_step_opts(mgbx_step_opts *o, int64_t n);
+int mgbx_abi_version(void);
+int mgbx_device_count(void);
+
+int mgbx_create(const mgbx_problem *prob, const mgbx_config *cfg, mgbx_handle **out);
+void mgbx_destroy(mgbx_handle *h);
+const char *mgbx_last_error(const mgbx_handle *h);   /* h may be NULL: last create error */
+
+/* the hot path */
+int mgbx_step(mgbx_handle *h, int which, double t, const mgbx_step_opts *o, mgbx_step_result *r);
+int mgbx_scalars(mgbx_handle *h, int which, mgbx_scalars_out *out);
+
+/* phase I (src/mgb.jl:417-566) */
+int mgbx_phase1_init(mgbx_handle *h, int32_t *needs_phase1, double *b, double *zabsmax);
+int mgbx_set_feasibility_box(mgbx_handle *h, double b, double Rbox);
+int mgbx_reset_feasibility_state(mgbx_handle *h);    /* z_feas <- (z_main, initial slack): no warm start between box rounds */
+int mgbx_handoff(mgbx_handle *h);                    /* z_main <- leading block of z_feas */
+int mgbx_matched_t(mgbx_handle *h, double t_default, double *t_out, double *tstar_out);
+
+/* state I/O: z is the stacked state vector, length nu*n of the selected AMG */
+int mgbx_get_z(mgbx_handle *h, int which, double *z_host);
+int mgbx_set_z(mgbx_handle *h, int which, const double *z_host);
+/* replace the cost / boundary-data grids in place (parabolic_solve re-assembly, src/Parabolic.jl:162-167) */
+int mgbx_set_grids(mgbx_handle *h, const double *f_grid, const double *g_grid);
+
+/* parity hooks.  level is 0-based; s has m_level entries.
+ * order 0: out[0] = f0;  order 1: out[0..m) = f1;  values of f2 through mgbx_hessian_values. */
+int64_t mgbx_level_size(mgbx_handle *h, int which, int level);
+int mgbx_barrier_eval(mgbx_handle *h, int which, int level, double t, const double *s, int order,
+                      double *out);
+int mgbx_hessian_pattern(mgbx_handle *h, int which, int level, int64_t *nnz, int64_t *rowptr,
+                         int64_t *colind);           /* rowptr/colind may be NULL to query nnz */
+int mgbx_hessian_values(mgbx_handle *h, int which, int level, double t, const double *s, double *val);
+int mgbx_solve_newton_system(mgbx_handle *h, int which, int level, double t, const double *s,
+                             const double *rhs, double *x, int32_t *pcg_iters);
+
+/* number of kernels launched through this handle so far (bench.py's gpu_launches) */
+int64_t mgbx_launch_count(const mgbx_handle *h);
+
+/* host-only (no GPU needed): the reference assembly plan's output pattern for R'HR
+ * (src/BlockMatrices.jl:344-446) from R (CSR, rows = nu blocks of N elements x p nodes). */
+int mgbx_plan_pattern(const mgbx_csr *R, int64_t N, int32_t p, int32_t nu, int32_t nD,
+                      const int32_t *D_var, int64_t *nnz, int64_t *rowptr, int64_t *colind);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGBX_H */

@@ -1,0 +1,761 @@
+// kernels.cuh -- sm_100a device kernels of the barrier-Newton hot path.
+//
+// What each kernel replaces in the reference (paths under /root/reference):
+//   k_node            apply_D + map_rows_gpu(F0/F1/F2) + the (1/n)·y + w.*c combination
+//                     src/convex.jl:125,155-202,213-257; ext/MultiGridBarrierCUDAExt/map_rows_gpu.jl:20-63,
+//                     block_ops.jl:118-133 (_block_matvec_kernel!)
+//   k_blockgrad       sum_k D_k' y_k                    src/convex.jl:173-178; block_ops.jl:135-148
+//   k_blockhess       sum_{j,k} D_j' diag(y_jk) D_k     src/convex.jl:185-200; block_ops.jl:58-75 (called nD^2 times there)
+//   k_csr_gather      R'HR into the fixed pattern       src/BlockMatrices.jl:506-555; block_ops.jl:229-249 (FP64 atomics there;
+//                                                       here a fixed-order gather, deterministic)
+//   k_spmv*           R*s, R'*g                          CUSPARSE in the reference (src/convex.jl:156,178)
+//   k_spgemm_numeric  Galerkin T'(A T) for the V-cycle   (north-star item 3; no counterpart: the reference factorises H directly)
+//   k_jacobi*, k_pcg* multigrid-preconditioned CG        replaces cuDSS LDL' (ext/.../cudss_solver.jl:264-381)
+//   k_chol_*          dense Cholesky at the coarsest level / small systems
+// All reductions are fixed-order (block tree + last-block pass): results are run-to-run deterministic.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "node_barrier.cuh"
+
+namespace mgbx {
+
+#define MGBX_MAX_OPS 8
+constexpr int kRedBlocks = 592;   // 148 SMs x 4
+constexpr int kRedThreads = 256;
+
+struct DevCsr {
+  int64_t rows = 0, cols = 0, nnz = 0;
+  int64_t *ptr = nullptr;
+  int32_t *idx = nullptr;
+  double *val = nullptr;
+};
+
+// ------------------------------------------------------------------------------------------------
+// reductions
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block-reduce NV values (op[k] == 0: sum, 1: max); result valid in thread 0.
+template <int NV>
+__device__ __forceinline__ void block_reduce(double (&v)[NV], const int (&op)[NV]) {
+  __shared__ double sm[NV][32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    v[k] = op[k] ? warp_max(v[k]) : warp_sum(v[k]);
+    if (lane == 0) sm[k][wid] = v[k];
+  }
+  __syncthreads();
+  if (wid == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      double x = lane < nw ? sm[k][lane] : (op[k] ? -INFINITY : 0.0);
+      v[k] = op[k] ? warp_max(x) : warp_sum(x);
+    }
+  }
+  __syncthreads();
+}
+
+// Grid-wide fixed-order reduction: every block deposits its partials, the last block to arrive
+// (atomic ticket) combines them in block order and writes out[0..NV).
+template <int NV>
+__device__ __forceinline__ void grid_reduce(double (&v)[NV], const int (&op)[NV], double *partials,
+                                            unsigned int *ticket, double *out) {
+  block_reduce<NV>(v, op);
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) partials[(size_t)k * gridDim.x + blockIdx.x] = v[k];
+    __threadfence();
+    const unsigned int t = atomicAdd(ticket, 1u);
+    last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    double a[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      double acc = op[k] ? -INFINITY : 0.0;
+      for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+        const double x = ((volatile double *)partials)[(size_t)k * gridDim.x + b];
+        acc = op[k] ? fmax(acc, x) : acc + x;
+      }
+      a[k] = acc;
+    }
+    block_reduce<NV>(a, op);
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int k = 0; k < NV; ++k) out[k] = a[k];
+      *ticket = 0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// sparse matrix-vector products.  G threads cooperate on one row (G = 1, 4, 32).
+//   y = alpha * A x + (y0 ? y0 : 0)
+// ------------------------------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(256) k_spmv(DevCsr A, const double *__restrict__ x, const double *y0, double alpha,
+                                               double *y) {
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t row = gtid / G;
+  const int sub = (int)(gtid % G);
+  if (row >= A.rows) return;   // G divides 32 and the block size, so whole groups exit together
+  const int64_t b = A.ptr[row], e = A.ptr[row + 1];
+  double acc = 0.0;
+  for (int64_t k = b + sub; k < e; k += G) acc += A.val[k] * x[A.idx[k]];
+  if (G > 1) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, G);
+  }
+  if (sub == 0) y[row] = alpha * acc + (y0 ? y0[row] : 0.0);
+}
+
+// x_new = x + dinv .* (b - A x)      (one l1-Jacobi sweep; x == nullptr means x = 0)
+template <int G>
+__global__ void __launch_bounds__(256) k_jacobi(DevCsr A, const double *__restrict__ dinv, const double *__restrict__ b,
+                                                 const double *__restrict__ x, double *xnew) {
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t row = gtid / G;
+  const int sub = (int)(gtid % G);
+  if (row >= A.rows) return;
+  if (x == nullptr) {
+    if (sub == 0) xnew[row] = dinv[row] * b[row];
+    return;
+  }
+  const int64_t bb = A.ptr[row], e = A.ptr[row + 1];
+  double acc = 0.0;
+  for (int64_t k = bb + sub; k < e; k += G) acc += A.val[k] * x[A.idx[k]];
+  if (G > 1) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, G);
+  }
+  if (sub == 0) xnew[row] = x[row] + dinv[row] * (b[row] - acc);
+}
+
+// dinv = 1 / sum_k |a_ik|  (l1-Jacobi), diag = a_ii
+__global__ void k_l1diag(DevCsr A, double *dinv, double *diag) {
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= A.rows) return;
+  double s = 0.0, d = 0.0;
+  for (int64_t k = A.ptr[row]; k < A.ptr[row + 1]; ++k) {
+    s += fabs(A.val[k]);
+    if (A.idx[k] == row) d = A.val[k];
+  }
+  dinv[row] = s > 0.0 ? 1.0 / s : 0.0;
+  if (diag) diag[row] = d;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Galerkin product, numeric phase into a fixed pattern: C = A * B, one thread per row of C
+// (sequential accumulation per row => deterministic).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_spgemm_numeric(DevCsr A, DevCsr B, DevCsr C) {
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= C.rows) return;
+  const int64_t c0 = C.ptr[row], c1 = C.ptr[row + 1];
+  for (int64_t k = c0; k < c1; ++k) C.val[k] = 0.0;
+  for (int64_t k = A.ptr[row]; k < A.ptr[row + 1]; ++k) {
+    const double a = A.val[k];
+    const int64_t r = A.idx[k];
+    int64_t lo = c0;   // B's columns are sorted, so the search window only moves right
+    for (int64_t q = B.ptr[r]; q < B.ptr[r + 1]; ++q) {
+      const int32_t col = B.idx[q];
+      int64_t hi = c1 - 1;
+      while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (C.idx[mid] < col) lo = mid + 1;
+        else hi = mid;
+      }
+      C.val[lo] += a * B.val[q];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-node barrier kernel
+// ------------------------------------------------------------------------------------------------
+enum { NODE_F01 = 0, NODE_F2 = 1, NODE_SLACK = 2 };
+
+struct NodeParams {
+  int64_t n;
+  int p, nu, nD;
+  int D_var[MGBX_MAX_ND], D_op[MGBX_MAX_ND];
+  const double *ops[MGBX_MAX_OPS];   // each N x (p x p), offset e*p*p + col*p + row
+  const double *zf;                  // nu*n broken state  z0 + R s
+  const double *w, *f, *bw;          // weights, cost grid n x nD, barrier weights or nullptr
+  double t, inv_n;
+  ConvexDev cd;
+  // F01 outputs
+  double *G;                         // n x nD: bw*F1 + w*t*f
+  double *partials;                  // 4 x gridDim
+  unsigned int *ticket;
+  double *red_out;                   // [0] sum bw*F0 (or sum F0), [1] sum w*(c.Dz), [2] #non-finite F0, [3] max slack
+  // F2 outputs (condensed when nE > 0)
+  int nK, nE;
+  int Krow[MGBX_MAX_ND];             // D rows of the kept variables
+  int Erow[MGBX_MAX_ND];             // per D row: index of its eliminated variable, or -1
+  double *Hn;                        // n x nK(nK+1)/2, packed (a<=b): a*nK - a(a-1)/2 + (b-a)
+  double *hEEinv;                    // n x nE(nE+1)/2
+  double *hKE;                       // n x (nK*nE): entry (a, ev) at column a*nE + ev
+  // SLACK output
+  double *slack;                     // n
+};
+
+__device__ __forceinline__ void node_Dz(const NodeParams &P, int64_t i, double *y) {
+  const int64_t e = i / P.p;
+  const int r = (int)(i - e * P.p);
+  for (int j = 0; j < P.nD; ++j) {
+    const int v = P.D_var[j], o = P.D_op[j];
+    const double *zv = P.zf + (int64_t)v * P.n;
+    if (o < 0) {
+      y[j] = zv[i];
+    } else {
+      const double *blk = P.ops[o] + e * (int64_t)(P.p * P.p) + r;
+      const double *ze = zv + e * P.p;
+      double acc = 0.0;
+      for (int c = 0; c < P.p; ++c) acc += blk[(int64_t)c * P.p] * ze[c];
+      y[j] = acc;
+    }
+  }
+}
+
+// small symmetric positive definite inverse (nE <= 4) by Cholesky; packed lower-by-rows in/out is
+// avoided: we work on a full nE x nE array.
+__device__ __forceinline__ void spd_inverse(double *M, int m) {
+  // in-place Cholesky M = L L'
+  double L[16];
+  for (int i = 0; i < m; ++i)
+    for (int j = 0; j <= i; ++j) {
+      double s = M[i * m + j];
+      for (int k = 0; k < j; ++k) s -= L[i * m + k] * L[j * m + k];
+      L[i * m + j] = (i == j) ? sqrt(s) : s / L[j * m + j];
+    }
+  // Linv
+  double Li[16];
+  for (int i = 0; i < m; ++i)
+    for (int j = 0; j < m; ++j) Li[i * m + j] = 0.0;
+  for (int j = 0; j < m; ++j) {
+    Li[j * m + j] = 1.0 / L[j * m + j];
+    for (int i = j + 1; i < m; ++i) {
+      double s = 0.0;
+      for (int k = j; k < i; ++k) s -= L[i * m + k] * Li[k * m + j];
+      Li[i * m + j] = s / L[i * m + i];
+    }
+  }
+  for (int i = 0; i < m; ++i)
+    for (int j = 0; j < m; ++j) {
+      double s = 0.0;
+      for (int k = (i > j ? i : j); k < m; ++k) s += Li[k * m + i] * Li[k * m + j];
+      M[i * m + j] = s;
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kRedThreads) k_node(NodeParams P) {
+  double red[4] = {0.0, 0.0, 0.0, -INFINITY};
+  const int op[4] = {0, 0, 0, 1};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += (int64_t)gridDim.x * blockDim.x) {
+    double y[MGBX_MAX_ND];
+    node_Dz(P, i, y);
+    if (MODE == NODE_SLACK) {
+      const double s = node_slack(P.cd, P.n, i, y);
+      P.slack[i] = s;
+      red[3] = fmax(red[3], s);
+      continue;
+    }
+    const int nD = P.nD;
+    const double bwi = P.bw ? P.bw[i] : 1.0;
+    const bool active = !(P.bw && bwi == 0.0);
+    double F1[MGBX_MAX_ND];
+    if (MODE == NODE_F01) {
+      double F0 = 0.0;
+      if (active) F0 = node_eval(P.cd, P.n, i, y, 1, F1, nullptr);
+      else
+        for (int j = 0; j < nD; ++j) F1[j] = 0.0;
+      const double wi = P.w[i];
+      double lin = 0.0;
+      const double sc = P.bw ? bwi : P.inv_n;
+      for (int j = 0; j < nD; ++j) {
+        const double c = P.t * P.f[i + (int64_t)j * P.n];
+        lin += c * y[j];
+        P.G[i + (int64_t)j * P.n] = (active ? sc * F1[j] : 0.0) + wi * c;
+      }
+      red[0] += active ? (P.bw ? bwi * F0 : F0) : 0.0;
+      red[1] += wi * lin;
+      if (!isfinite(F0)) red[2] += 1.0;
+    } else {   // NODE_F2
+      double F2[MGBX_MAX_ND * MGBX_MAX_ND];
+      const double sc = P.bw ? bwi : P.inv_n;
+      if (active) {
+        node_eval(P.cd, P.n, i, y, 2, F1, F2);
+        for (int k = 0; k < nD * nD; ++k) F2[k] *= sc;
+      } else {
+        for (int k = 0; k < nD * nD; ++k) F2[k] = 0.0;
+      }
+      const int nK = P.nK, nE = P.nE;
+      if (nE == 0) {
+        int q = 0;
+        for (int a = 0; a < nK; ++a)
+          for (int b = a; b < nK; ++b, ++q) P.Hn[i + (int64_t)q * P.n] = F2[P.Krow[a] * nD + P.Krow[b]];
+      } else {
+        double hEE[16], hKE[MGBX_MAX_ND * 4];
+        for (int k = 0; k < nE * nE; ++k) hEE[k] = 0.0;
+        for (int k = 0; k < nK * nE; ++k) hKE[k] = 0.0;
+        for (int j = 0; j < nD; ++j) {
+          const int ej = P.Erow[j];
+          if (ej < 0) continue;
+          for (int k = 0; k < nD; ++k) {
+            const int ek = P.Erow[k];
+            if (ek >= 0) hEE[ej * nE + ek] += F2[j * nD + k];
+          }
+          for (int a = 0; a < nK; ++a) hKE[a * nE + ej] += F2[P.Krow[a] * nD + j];
+        }
+        spd_inverse(hEE, nE);
+        {
+          int q = 0;
+          for (int a = 0; a < nE; ++a)
+            for (int b = a; b < nE; ++b, ++q) P.hEEinv[i + (int64_t)q * P.n] = hEE[a * nE + b];
+        }
+        for (int k = 0; k < nK * nE; ++k) P.hKE[i + (int64_t)k * P.n] = hKE[k];
+        // W = hEEinv * hEK  (nE x nK);  Hn = hKK - hKE W
+        int q = 0;
+        for (int a = 0; a < nK; ++a)
+          for (int b = a; b < nK; ++b, ++q) {
+            double s = F2[P.Krow[a] * nD + P.Krow[b]];
+            for (int ev = 0; ev < nE; ++ev) {
+              double wv = 0.0;
+              for (int ew = 0; ew < nE; ++ew) wv += hEE[ev * nE + ew] * hKE[b * nE + ew];
+              s -= hKE[a * nE + ev] * wv;
+            }
+            P.Hn[i + (int64_t)q * P.n] = s;
+          }
+      }
+    }
+  }
+  if (MODE != NODE_F2) grid_reduce<4>(red, op, P.partials, P.ticket, P.red_out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// element-block kernels
+// ------------------------------------------------------------------------------------------------
+struct ElemParams {
+  int64_t n, N;
+  int p, nD;
+  int D_var[MGBX_MAX_ND], D_op[MGBX_MAX_ND];
+  const double *ops[MGBX_MAX_OPS];
+  int nK;                    // rows used (Hessian: kept rows; gradient: all rows)
+  int Krow[MGBX_MAX_ND];
+};
+
+// gb[v*n + e*p + c] = sum_{j in rows(v), j in Krow} sum_q D_j[q][c] * G[j*n + e*p + q]
+// one thread per (variable slot, broken node)
+__global__ void __launch_bounds__(256) k_blockgrad(ElemParams P, const double *__restrict__ G, double *gb, int nu) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= (int64_t)nu * P.n) return;
+  const int v = (int)(tid / P.n);
+  const int64_t i = tid - (int64_t)v * P.n;
+  const int64_t e = i / P.p;
+  const int c = (int)(i - e * P.p);
+  double acc = 0.0;
+  for (int jj = 0; jj < P.nK; ++jj) {
+    const int j = P.Krow[jj];
+    if (P.D_var[j] != v) continue;
+    const int o = P.D_op[j];
+    const double *g = G + (int64_t)j * P.n;
+    if (o < 0) acc += g[i];
+    else {
+      const double *blk = P.ops[o] + e * (int64_t)(P.p * P.p) + (int64_t)c * P.p;
+      const double *ge = g + e * P.p;
+      for (int q = 0; q < P.p; ++q) acc += blk[q] * ge[q];
+    }
+  }
+  gb[tid] = acc;
+}
+
+// Hblk[((pair*N + e)*p + r)*p + c] = sum_{j in rows(a), k in rows(b)} sum_q D_j[q][r] h_jk[q] D_k[q][c]
+// with h packed over the kept rows.  One thread per (pair, e, r, c).
+struct PairList {
+  int npairs;
+  int va[16], vb[16];
+};
+__global__ void __launch_bounds__(256) k_blockhess(ElemParams P, PairList PL, const double *__restrict__ Hn, double *Hblk) {
+  const int pp = P.p * P.p;
+  const int64_t total = (int64_t)PL.npairs * P.N * pp;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= total) return;
+  const int c = (int)(tid % P.p);
+  const int r = (int)((tid / P.p) % P.p);
+  const int64_t e = (tid / pp) % P.N;
+  const int pr = (int)(tid / ((int64_t)pp * P.N));
+  const int va = PL.va[pr], vb = PL.vb[pr];
+  const int nK = P.nK;
+  const int64_t base = e * P.p;
+  double acc = 0.0;
+  for (int ja = 0; ja < nK; ++ja) {
+    const int j = P.Krow[ja];
+    if (P.D_var[j] != va) continue;
+    const int oj = P.D_op[j];
+    for (int kb = 0; kb < nK; ++kb) {
+      const int k = P.Krow[kb];
+      if (P.D_var[k] != vb) continue;
+      const int ok = P.D_op[k];
+      const int a = ja < kb ? ja : kb, b = ja < kb ? kb : ja;
+      const double *h = Hn + (int64_t)(a * nK - (a * (a - 1)) / 2 + (b - a)) * P.n + base;
+      if (oj < 0 && ok < 0) {
+        if (r == c) acc += h[r];
+      } else if (oj < 0) {
+        acc += h[r] * P.ops[ok][e * (int64_t)pp + (int64_t)c * P.p + r];
+      } else if (ok < 0) {
+        acc += P.ops[oj][e * (int64_t)pp + (int64_t)r * P.p + c] * h[c];
+      } else {
+        const double *dj = P.ops[oj] + e * (int64_t)pp + (int64_t)r * P.p;
+        const double *dk = P.ops[ok] + e * (int64_t)pp + (int64_t)c * P.p;
+        double s = 0.0;
+        for (int q = 0; q < P.p; ++q) s += dj[q] * h[q] * dk[q];
+        acc += s;
+      }
+    }
+  }
+  Hblk[tid] = acc;
+}
+
+// val[nz] = sum_k gw[k] * Hblk[gidx[k]], k in [gptr[nz], gptr[nz+1])   (fixed order)
+__global__ void __launch_bounds__(256) k_csr_gather(int64_t nnz, const int64_t *__restrict__ gptr, const int64_t *__restrict__ gidx,
+                                                     const double *__restrict__ gw, const double *__restrict__ Hblk, double *val) {
+  const int64_t nz = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (nz >= nnz) return;
+  double acc = 0.0;
+  for (int64_t k = gptr[nz]; k < gptr[nz + 1]; ++k) acc += (gw ? gw[k] : 1.0) * Hblk[gidx[k]];
+  val[nz] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// condensation helpers (node-local elimination of the :full variables)
+// ------------------------------------------------------------------------------------------------
+struct CondParams {
+  int64_t n;
+  int nD, nK, nE;
+  int Krow[MGBX_MAX_ND];
+  int64_t Eoff[4];            // first index of eliminated variable ev in the level-L vector
+  const double *hEEinv, *hKE;
+};
+
+// Gt[Krow[a]*n + i] = - sum_ev hKE[a][ev] * (hEEinv * gE)[ev],  gE[ev] = g[Eoff[ev] + i]; other rows of Gt are not touched
+__global__ void __launch_bounds__(256) k_condense_rhs(CondParams P, const double *__restrict__ g, double *Gt) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.n) return;
+  double gE[4], tE[4], Hi[16];
+  const int nE = P.nE;
+  for (int ev = 0; ev < nE; ++ev) gE[ev] = g[P.Eoff[ev] + i];
+  int q = 0;
+  for (int a = 0; a < nE; ++a)
+    for (int b = a; b < nE; ++b, ++q) {
+      const double v = P.hEEinv[i + (int64_t)q * P.n];
+      Hi[a * nE + b] = v;
+      Hi[b * nE + a] = v;
+    }
+  for (int ev = 0; ev < nE; ++ev) {
+    double s = 0.0;
+    for (int ew = 0; ew < nE; ++ew) s += Hi[ev * nE + ew] * gE[ew];
+    tE[ev] = s;
+  }
+  for (int a = 0; a < P.nK; ++a) {
+    double s = 0.0;
+    for (int ev = 0; ev < nE; ++ev) s += P.hKE[i + (int64_t)(a * nE + ev) * P.n] * tE[ev];
+    Gt[i + (int64_t)P.Krow[a] * P.n] = -s;
+  }
+}
+
+// xE = hEEinv (gE - hEK * DnK):  x[Eoff[ev] + i]; DnK = rows Krow of D applied to the broken vector nb
+__global__ void __launch_bounds__(256) k_backsubst(CondParams P, NodeParams NP, const double *__restrict__ g, double *x) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.n) return;
+  double y[MGBX_MAX_ND];
+  node_Dz(NP, i, y);   // NP.zf = broken image of the kept part of the direction
+  const int nE = P.nE;
+  double rE[4], Hi[16];
+  for (int ev = 0; ev < nE; ++ev) {
+    double s = g[P.Eoff[ev] + i];
+    for (int a = 0; a < P.nK; ++a) s -= P.hKE[i + (int64_t)(a * nE + ev) * P.n] * y[P.Krow[a]];
+    rE[ev] = s;
+  }
+  int q = 0;
+  for (int a = 0; a < nE; ++a)
+    for (int b = a; b < nE; ++b, ++q) {
+      const double v = P.hEEinv[i + (int64_t)q * P.n];
+      Hi[a * nE + b] = v;
+      Hi[b * nE + a] = v;
+    }
+  for (int ev = 0; ev < nE; ++ev) {
+    double s = 0.0;
+    for (int ew = 0; ew < nE; ++ew) s += Hi[ev * nE + ew] * rE[ew];
+    x[P.Eoff[ev] + i] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// vector kernels (all scalars stay on the device)
+// ------------------------------------------------------------------------------------------------
+// out[0] = a.b, out[1] = a.a, out[2] = #non-finite entries of a
+__global__ void __launch_bounds__(kRedThreads) k_dot2(int64_t m, const double *__restrict__ a, const double *__restrict__ b,
+                                                       double *partials, unsigned int *ticket, double *out) {
+  double red[3] = {0.0, 0.0, 0.0};
+  const int op[3] = {0, 0, 0};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+    const double x = a[i];
+    red[0] += x * (b ? b[i] : 0.0);
+    red[1] += x * x;
+    if (!isfinite(x)) red[2] += 1.0;
+  }
+  grid_reduce<3>(red, op, partials, ticket, out);
+}
+
+// xn = x - s*d;  out[0] = |xn - x|^2 (exactly as evaluated in floating point: stall detection, src/newton.jl:141)
+__global__ void __launch_bounds__(kRedThreads) k_trial(int64_t m, const double *__restrict__ x, const double *__restrict__ d, double s,
+                                                        double *xn, double *partials, unsigned int *ticket, double *out) {
+  double red[1] = {0.0};
+  const int op[1] = {0};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+    const double xi = x[i];
+    const double v = xi - s * d[i];
+    xn[i] = v;
+    const double df = v - xi;
+    red[0] += df * df;
+  }
+  grid_reduce<1>(red, op, partials, ticket, out);
+}
+
+__global__ void k_axpby(int64_t m, double a, const double *__restrict__ x, double b, const double *__restrict__ y, double *out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) out[i] = a * x[i] + (y ? b * y[i] : 0.0);
+}
+__global__ void k_mul(int64_t m, const double *__restrict__ a, const double *__restrict__ b, double *out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) out[i] = a[i] * b[i];
+}
+
+// PCG: scal = {rz, pAp, rr, rz_new}.
+//  step A: alpha = rz/pAp;  x += alpha p;  r -= alpha Ap;  rr = r.r
+__global__ void __launch_bounds__(kRedThreads) k_pcg_update(int64_t m, double *scal, const double *__restrict__ p, const double *__restrict__ Ap,
+                                                             double *x, double *r, double *partials, unsigned int *ticket) {
+  const double alpha = scal[0] / scal[1];
+  double red[1] = {0.0};
+  const int op[1] = {0};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+    x[i] += alpha * p[i];
+    const double ri = r[i] - alpha * Ap[i];
+    r[i] = ri;
+    red[0] += ri * ri;
+  }
+  grid_reduce<1>(red, op, partials, ticket, scal + 2);
+}
+//  step B: beta = rz_new/rz;  p = z + beta p;  then rz <- rz_new   (done by thread 0 of the LAST block only after all reads:
+//  we avoid the hazard by passing beta through a separate slot written by k_pcg_beta)
+__global__ void k_pcg_beta(double *scal) {   // scal[4] = beta = scal[3]/scal[0]; scal[0] = scal[3]
+  scal[4] = scal[3] / scal[0];
+  scal[0] = scal[3];
+}
+__global__ void k_pcg_dir(int64_t m, const double *scal, const double *__restrict__ z, double *p) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) p[i] = z[i] + scal[4] * p[i];
+}
+// out[slot] = a.b
+__global__ void __launch_bounds__(kRedThreads) k_dot(int64_t m, const double *__restrict__ a, const double *__restrict__ b, double *partials,
+                                                      unsigned int *ticket, double *out) {
+  double red[1] = {0.0};
+  const int op[1] = {0};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) red[0] += a[i] * b[i];
+  grid_reduce<1>(red, op, partials, ticket, out);
+}
+
+// per-variable max and max|.| of the state: out[2k] = max, out[2k+1] = absmax  (one launch per variable)
+__global__ void __launch_bounds__(kRedThreads) k_maxabs(int64_t m, const double *__restrict__ a, double *partials, unsigned int *ticket,
+                                                         double *out) {
+  double red[3] = {-INFINITY, -INFINITY, 0.0};
+  const int op[3] = {1, 1, 0};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+    const double v = a[i];
+    red[0] = fmax(red[0], v);
+    red[1] = fmax(red[1], fabs(v));
+    if (!isfinite(v)) red[2] += 1.0;
+  }
+  grid_reduce<3>(red, op, partials, ticket, out);
+}
+
+// sl[i] = 2*max(slack[i], 1)   (src/mgb.jl:437-440)
+__global__ void k_phase1_slack(int64_t n, const double *slack, double *out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = 2.0 * fmax(slack[i], 1.0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// dense Cholesky (row-major, lower), blocked right-looking with NB = 32
+// ------------------------------------------------------------------------------------------------
+constexpr int NB = 32;
+
+// Ad = 0 then Ad[i][j] = a_ij * d_i * d_j  with d = 1/sqrt(a_ii)
+__global__ void k_dense_scale_diag(DevCsr A, double *d) {
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= A.rows) return;
+  double dg = 0.0;
+  for (int64_t k = A.ptr[row]; k < A.ptr[row + 1]; ++k)
+    if (A.idx[k] == row) dg = A.val[k];
+  d[row] = dg > 0.0 ? 1.0 / sqrt(dg) : 1.0;
+}
+__global__ void k_csr_to_dense(DevCsr A, const double *d, double *Ad) {
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= A.rows) return;
+  const double di = d[row];
+  for (int64_t k = A.ptr[row]; k < A.ptr[row + 1]; ++k) Ad[row * A.rows + A.idx[k]] = A.val[k] * di * d[A.idx[k]];
+}
+
+// factor the diagonal block [k0, k0+nb) in shared memory (one block)
+__global__ void __launch_bounds__(256) k_chol_diag(double *A, int m, int k0) {
+  __shared__ double L[NB][NB + 1];
+  const int nb = min(NB, m - k0);
+  for (int t = threadIdx.x; t < NB * NB; t += blockDim.x) {
+    const int i = t / NB, j = t % NB;
+    L[i][j] = (i < nb && j < nb && j <= i) ? A[(size_t)(k0 + i) * m + k0 + j] : 0.0;
+  }
+  __syncthreads();
+  for (int j = 0; j < nb; ++j) {
+    if (threadIdx.x == 0) L[j][j] = sqrt(L[j][j]);
+    __syncthreads();
+    if ((int)threadIdx.x > j && (int)threadIdx.x < nb) L[threadIdx.x][j] /= L[j][j];
+    __syncthreads();
+    // trailing update inside the block: L[i][k] -= L[i][j]*L[k][j] for j < k <= i
+    for (int t = threadIdx.x; t < nb * nb; t += blockDim.x) {
+      const int i = t / nb, k = t % nb;
+      if (k > j && i >= k) L[i][k] -= L[i][j] * L[k][j];
+    }
+    __syncthreads();
+  }
+  for (int t = threadIdx.x; t < nb * nb; t += blockDim.x) {
+    const int i = t / nb, j = t % nb;
+    if (j <= i) A[(size_t)(k0 + i) * m + k0 + j] = L[i][j];
+  }
+}
+
+// panel rows below the (already factored) diagonal block: X L' = A21, row-wise forward substitution
+__global__ void __launch_bounds__(64) k_chol_trsm(double *A, int m, int k0) {
+  __shared__ double L[NB][NB + 1];
+  const int nb = min(NB, m - k0);
+  for (int t = threadIdx.x; t < NB * NB; t += blockDim.x) {
+    const int i = t / NB, j = t % NB;
+    L[i][j] = (i < nb && j < nb && j <= i) ? A[(size_t)(k0 + i) * m + k0 + j] : 0.0;
+  }
+  __syncthreads();
+  const int row = k0 + nb + blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= m) return;
+  double x[NB];
+  double *a = A + (size_t)row * m + k0;
+#pragma unroll
+  for (int c = 0; c < NB; ++c) {
+    if (c < nb) {
+      double s = a[c];
+#pragma unroll
+      for (int j = 0; j < NB; ++j)
+        if (j < c) s -= x[j] * L[c][j];
+      x[c] = s / L[c][c];
+    } else {
+      x[c] = 0.0;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NB; ++c)
+    if (c < nb) a[c] = x[c];
+}
+
+// trailing update A22[i][j] -= sum_c L21[i][c] L21[j][c], lower tiles only; one 32x32 tile per block (32x8 threads)
+__global__ void __launch_bounds__(256) k_chol_syrk(double *A, int m, int k0) {
+  __shared__ double Li[NB][NB + 1], Lj[NB][NB + 1];
+  const int nb = min(NB, m - k0);
+  const int r0 = k0 + nb;
+  // decode lower-triangular tile index
+  int t = blockIdx.x, ti = 0;
+  while (t >= ti + 1) {
+    t -= ti + 1;
+    ++ti;
+  }
+  const int tj = t;
+  const int i0 = r0 + ti * NB, j0 = r0 + tj * NB;
+  const int tx = threadIdx.x % NB, ty = threadIdx.x / NB;   // 32 x 8
+  for (int rr = ty; rr < NB; rr += 8) {
+    Li[rr][tx] = (i0 + rr < m && tx < nb) ? A[(size_t)(i0 + rr) * m + k0 + tx] : 0.0;
+    Lj[rr][tx] = (j0 + rr < m && tx < nb) ? A[(size_t)(j0 + rr) * m + k0 + tx] : 0.0;
+  }
+  __syncthreads();
+  for (int rr = ty; rr < NB; rr += 8) {
+    const int i = i0 + rr, j = j0 + tx;
+    if (i < m && j < m && j <= i) {
+      double s = 0.0;
+#pragma unroll
+      for (int c = 0; c < NB; ++c) s += Li[rr][c] * Lj[tx][c];
+      A[(size_t)i * m + j] -= s;
+    }
+  }
+}
+
+// Solve L L' x = b for nrhs right-hand sides; one block per right-hand side.  B is m x nrhs column-major
+// (column stride m); eye != 0: the right-hand sides are the columns of the identity (explicit inverse).
+__global__ void __launch_bounds__(256) k_chol_solve(const double *__restrict__ L, int m, double *B, int eye) {
+  extern __shared__ double xs[];
+  double *col = B + (size_t)blockIdx.x * m;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) xs[i] = eye ? (i == (int)blockIdx.x ? 1.0 : 0.0) : col[i];
+  __syncthreads();
+  __shared__ double wsum[8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  // forward: x_k = (b_k - sum_{j<k} L[k][j] x_j) / L[k][k]
+  for (int k = (eye ? (int)blockIdx.x : 0); k < m; ++k) {
+    const double *row = L + (size_t)k * m;
+    double s = 0.0;
+    for (int j = threadIdx.x; j < k; j += blockDim.x) s += row[j] * xs[j];
+    s = warp_sum(s);
+    if (lane == 0) wsum[wid] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0.0;
+      for (int w2 = 0; w2 < (int)(blockDim.x >> 5); ++w2) tot += wsum[w2];
+      xs[k] = (xs[k] - tot) / row[k];
+    }
+    __syncthreads();
+  }
+  // backward: L' x = y, column-oriented: x_k = y_k / L[k][k]; y_j -= L[k][j] x_k for j < k
+  for (int k = m - 1; k >= 0; --k) {
+    const double *row = L + (size_t)k * m;
+    if (threadIdx.x == 0) xs[k] = xs[k] / row[k];
+    __syncthreads();
+    const double xk = xs[k];
+    for (int j = threadIdx.x; j < k; j += blockDim.x) xs[j] -= row[j] * xk;
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < m; i += blockDim.x) col[i] = xs[i];
+}
+
+// y = M x for a dense symmetric m x m matrix stored as m columns (coarse inverse); one warp per row
+__global__ void __launch_bounds__(256) k_dense_symv(const double *__restrict__ M, int m, const double *__restrict__ x, double *y) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= m) return;
+  const double *r = M + (size_t)row * m;
+  double s = 0.0;
+  for (int j = lane; j < m; j += 32) s += r[j] * x[j];
+  s = warp_sum(s);
+  if (lane == 0) y[row] = s;
+}
+
+}  // namespace mgbx

@@ -1,0 +1,1546 @@
+// mgbx.cu -- handle, setup plans, device-resident Newton / line search / mgb_step, and the C ABI.
+//
+// Reference behaviour implemented here (paths under /root/reference/src):
+//   newton.jl:227-287          newton          -> Engine::newton
+//   newton.jl:35-50,139-154    backtracking    -> Engine::newton (inlined trial loop)
+//   newton.jl:187,222-225      stopping rules  -> Engine::stop_test
+//   mgb.jl:10-82               divide_and_conquer / mgb_step -> Engine::step
+//   mgb.jl:307-330             _matched_t      -> Engine::matched_t
+//   convex.jl:155-202          f0 / f1 / f2    -> Engine::eval_f01 / assemble
+//   BlockMatrices.jl:322-555   assembly plan   -> build_system (host, once) + k_blockhess/k_csr_gather
+//   utils.jl:142-145           solve           -> Engine::solve (dense Cholesky or V-cycle PCG)
+// The t-ramp (mgb_core) and phase-I control flow (mgb_driver) stay on the host side of the ABI:
+// they only exchange scalars with this library.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "host_sparse.hpp"
+#include "kernels.cuh"
+
+using namespace mgbx;
+
+#define CK(call)                                                                                      \
+  do {                                                                                                \
+    cudaError_t e_ = (call);                                                                          \
+    if (e_ != cudaSuccess)                                                                            \
+      throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " + __FILE__ + ":" + \
+                               std::to_string(__LINE__));                                             \
+  } while (0)
+
+static thread_local std::string g_last_error;
+
+namespace {
+
+struct ArgError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+inline unsigned int nblk(int64_t work, int threads = 256) { return (unsigned int)((work + threads - 1) / threads); }
+
+// ------------------------------------------------------------------------------------------------
+// device memory pool (freed at destroy)
+// ------------------------------------------------------------------------------------------------
+struct Pool {
+  std::vector<void *> ptrs;
+  size_t bytes = 0;
+  template <class T>
+  T *alloc(size_t n) {
+    if (n == 0) n = 1;
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+    if (e != cudaSuccess) throw std::runtime_error(std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
+    ptrs.push_back(p);
+    bytes += n * sizeof(T);
+    return (T *)p;
+  }
+  template <class T>
+  T *upload(const T *h, size_t n, cudaStream_t s) {
+    T *d = alloc<T>(n);
+    if (n) CK(cudaMemcpyAsync(d, h, n * sizeof(T), cudaMemcpyHostToDevice, s));
+    return d;
+  }
+  template <class T>
+  T *zeros(size_t n, cudaStream_t s) {
+    T *d = alloc<T>(n);
+    CK(cudaMemsetAsync(d, 0, (n ? n : 1) * sizeof(T), s));
+    return d;
+  }
+  void release() {
+    for (void *p : ptrs) cudaFree(p);
+    ptrs.clear();
+  }
+};
+
+DevCsr upload_csr(Pool &pool, const HostCsr &H, cudaStream_t s, bool with_values = true) {
+  DevCsr D;
+  D.rows = H.rows;
+  D.cols = H.cols;
+  D.nnz = H.nnz();
+  D.ptr = pool.upload<int64_t>(H.ptr.data(), H.ptr.size(), s);
+  D.idx = pool.upload<int32_t>(H.idx.data(), H.idx.size(), s);
+  if (with_values && !H.val.empty()) D.val = pool.upload<double>(H.val.data(), H.val.size(), s);
+  else D.val = pool.zeros<double>(H.idx.size(), s);
+  return D;
+}
+
+// ------------------------------------------------------------------------------------------------
+// linear systems: top-level assembly plan + Galerkin hierarchy
+// ------------------------------------------------------------------------------------------------
+struct SysLevel {
+  int64_t m = 0;
+  DevCsr A;
+  DevCsr T, Tt, AT;          // T: this level (rows) <- next coarser level (cols)
+  bool has_coarser = false, T_identity = false;
+  double *dinv = nullptr, *diag = nullptr;
+  double *b = nullptr, *x = nullptr, *x2 = nullptr, *r = nullptr;   // V-cycle work
+  double *dense = nullptr, *dense_inv = nullptr, *dscale = nullptr;
+  int spmv_group = 1;
+  std::vector<int64_t> off;  // system offsets of the kept variables (+ end)
+};
+
+struct System {
+  bool condensed = false;
+  std::vector<int> kept, elim;       // state variable ids
+  std::vector<SysLevel> lev;         // lev[k] <-> AMG level L-1-k
+  PairList pl;
+  int nK = 0, nE = 0;
+  int Krow[MGBX_MAX_ND], Erow[MGBX_MAX_ND];
+  int64_t *gptr = nullptr, *gidx = nullptr;
+  double *gw = nullptr;
+  double *Hblk = nullptr;
+  int64_t hblk_size = 0;
+  int cut = -1;                      // V-cycle bottom (dense inverse) level index, -1: none
+  // PCG work at the largest size
+  double *pc_r = nullptr, *pc_z = nullptr, *pc_p = nullptr, *pc_Ap = nullptr, *pc_x = nullptr, *pc_b = nullptr;
+  int values_top = -1;               // lev index whose hierarchy values are current (for reuse checks)
+};
+
+struct Amg {
+  int64_t n = 0, N = 0;
+  int p = 0, nu = 0, nD = 0, L = 0, nops = 0;
+  int D_var[MGBX_MAX_ND], D_op[MGBX_MAX_ND];
+  double *w = nullptr, *f = nullptr, *bw = nullptr, *z = nullptr, *zsave = nullptr, *zinit = nullptr;
+  const double *ops[MGBX_MAX_OPS];
+  HostCsr hRL;
+  std::vector<HostCsr> hT;
+  DevCsr RL, RLt;
+  std::vector<DevCsr> T, Tt;
+  std::vector<std::vector<int64_t>> voff;   // L x (nu+1)
+  std::vector<int64_t> m;
+  ConvexDev cd;
+  // work
+  double *zf = nullptr, *G = nullptr, *gb = nullptr, *Hn = nullptr, *hEEinv = nullptr, *hKE = nullptr, *slack = nullptr;
+  std::vector<double *> chain;              // per level work vector (m_l)
+  std::vector<double *> chain2;
+  double *x = nullptr, *xn = nullptr, *g = nullptr, *gn = nullptr, *dir = nullptr, *rhs = nullptr, *tmp = nullptr, *xbest = nullptr,
+         *gbest = nullptr;
+  std::unique_ptr<System> sys_cond, sys_full;
+  double fb = 0.0, fR = 0.0;
+};
+
+struct EvalOut {
+  double y, gnorm;
+  bool finite;
+  double nonfinite_nodes, lin;
+};
+
+}  // namespace
+
+struct mgbx_handle {
+  std::string err;
+  mgbx_config cfg;
+  cudaStream_t stream = nullptr;
+  Pool pool;
+  Amg amg[2];
+  bool has_feas = false;
+  // reduction scratch
+  double *partials = nullptr;
+  unsigned int *ticket = nullptr;
+  double *dscal = nullptr;   // device scalars
+  double *hscal = nullptr;   // pinned host mirror
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // stats of the current step
+  mgbx_step_result *res = nullptr;
+  mgbx_step_result scratch_res;
+  int64_t launches = 0;
+};
+
+namespace {
+
+struct Engine {
+  mgbx_handle *h;
+  cudaStream_t s;
+  explicit Engine(mgbx_handle *hh) : h(hh), s(hh->stream) {}
+
+  void sync() { CK(cudaStreamSynchronize(s)); }
+  void fetch(int count) {
+    CK(cudaMemcpyAsync(h->hscal, h->dscal, sizeof(double) * count, cudaMemcpyDeviceToHost, s));
+    sync();
+  }
+  void check_launch() {
+    h->launches++;
+    CK(cudaGetLastError());
+  }
+
+  // ---------------------------------------------------------------- sparse helpers
+  static int group_for(const DevCsr &A) {
+    const double avg = A.rows ? (double)A.nnz / (double)A.rows : 0.0;
+    return avg > 48.0 ? 32 : (avg > 6.0 ? 4 : 1);
+  }
+  void spmv(const DevCsr &A, const double *x, const double *y0, double alpha, double *y, int G = 0) {
+    if (A.rows == 0) return;
+    if (G == 0) G = group_for(A);
+    if (G == 32) k_spmv<32><<<nblk(A.rows * 32), 256, 0, s>>>(A, x, y0, alpha, y);
+    else if (G == 4) k_spmv<4><<<nblk(A.rows * 4), 256, 0, s>>>(A, x, y0, alpha, y);
+    else k_spmv<1><<<nblk(A.rows), 256, 0, s>>>(A, x, y0, alpha, y);
+    check_launch();
+  }
+  void jacobi(const SysLevel &Lv, const double *b, const double *x, double *xnew) {
+    const int G = Lv.spmv_group;
+    if (G == 32) k_jacobi<32><<<nblk(Lv.m * 32), 256, 0, s>>>(Lv.A, Lv.dinv, b, x, xnew);
+    else if (G == 4) k_jacobi<4><<<nblk(Lv.m * 4), 256, 0, s>>>(Lv.A, Lv.dinv, b, x, xnew);
+    else k_jacobi<1><<<nblk(Lv.m), 256, 0, s>>>(Lv.A, Lv.dinv, b, x, xnew);
+    check_launch();
+  }
+  void copy(double *dst, const double *src, int64_t m) {
+    if (m) CK(cudaMemcpyAsync(dst, src, sizeof(double) * m, cudaMemcpyDeviceToDevice, s));
+  }
+  void zero(double *dst, int64_t m) {
+    if (m) CK(cudaMemsetAsync(dst, 0, sizeof(double) * m, s));
+  }
+
+  // ---------------------------------------------------------------- level chain
+  // zf = z + R_L * T_{L-2} ... T_J * x
+  void prolong_to_fine(Amg &A, int J, const double *x, const double *zbase, double *zf) {
+    const double *v = x;
+    for (int l = J; l < A.L - 1; ++l) {
+      spmv(A.T[l], v, nullptr, 1.0, A.chain[l + 1]);
+      v = A.chain[l + 1];
+    }
+    spmv(A.RL, v, zbase, 1.0, zf);
+  }
+  // g_J = T_J' ... T_{L-2}' R_L' gb
+  void restrict_from_fine(Amg &A, int J, const double *gb, double *gJ) {
+    if (J == A.L - 1) {
+      spmv(A.RLt, gb, nullptr, 1.0, gJ);
+      return;
+    }
+    spmv(A.RLt, gb, nullptr, 1.0, A.chain2[A.L - 1]);
+    const double *v = A.chain2[A.L - 1];
+    for (int l = A.L - 2; l >= J; --l) {
+      double *out = (l == J) ? gJ : A.chain2[l];
+      spmv(A.Tt[l], v, nullptr, 1.0, out);
+      v = out;
+    }
+  }
+
+  NodeParams node_params(Amg &A, double t) {
+    NodeParams P;
+    memset(&P, 0, sizeof(P));
+    P.n = A.n;
+    P.p = A.p;
+    P.nu = A.nu;
+    P.nD = A.nD;
+    for (int j = 0; j < A.nD; ++j) {
+      P.D_var[j] = A.D_var[j];
+      P.D_op[j] = A.D_op[j];
+    }
+    for (int o = 0; o < A.nops; ++o) P.ops[o] = A.ops[o];
+    P.zf = A.zf;
+    P.w = A.w;
+    P.f = A.f;
+    P.bw = A.bw;
+    P.t = t;
+    P.inv_n = 1.0 / (double)A.n;
+    P.cd = A.cd;
+    P.G = A.G;
+    P.partials = h->partials;
+    P.ticket = h->ticket;
+    P.red_out = h->dscal;
+    P.slack = A.slack;
+    return P;
+  }
+  ElemParams elem_params(Amg &A) {
+    ElemParams P;
+    memset(&P, 0, sizeof(P));
+    P.n = A.n;
+    P.N = A.N;
+    P.p = A.p;
+    P.nD = A.nD;
+    for (int j = 0; j < A.nD; ++j) {
+      P.D_var[j] = A.D_var[j];
+      P.D_op[j] = A.D_op[j];
+    }
+    for (int o = 0; o < A.nops; ++o) P.ops[o] = A.ops[o];
+    P.nK = A.nD;
+    for (int j = 0; j < A.nD; ++j) P.Krow[j] = j;
+    return P;
+  }
+  unsigned int red_grid(int64_t work) {
+    const int64_t b = (work + kRedThreads - 1) / kRedThreads;
+    return (unsigned int)std::max<int64_t>(1, std::min<int64_t>(b, kRedBlocks));
+  }
+
+  // ---------------------------------------------------------------- f0 + f1 at level J
+  // zbase: broken state the level correction is added to; x: level-J coefficients; gout: level-J gradient
+  EvalOut eval_f01(Amg &A, int J, double t, const double *zbase, const double *x, double *gout, bool use_bw = true) {
+    cudaEventRecord(h->ev0, s);
+    prolong_to_fine(A, J, x, zbase, A.zf);
+    NodeParams P = node_params(A, t);
+    if (!use_bw) P.bw = nullptr;
+    k_node<NODE_F01><<<red_grid(A.n), kRedThreads, 0, s>>>(P);
+    check_launch();
+    ElemParams E = elem_params(A);
+    k_blockgrad<<<nblk((int64_t)A.nu * A.n), 256, 0, s>>>(E, A.G, A.gb, A.nu);
+    check_launch();
+    restrict_from_fine(A, J, A.gb, gout);
+    k_dot2<<<red_grid(A.m[J]), kRedThreads, 0, s>>>(A.m[J], gout, nullptr, h->partials, h->ticket, h->dscal + 4);
+    check_launch();
+    cudaEventRecord(h->ev1, s);
+    fetch(8);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    if (h->res) {
+      h->res->ms_f01 += ms;
+      h->res->f01_evals++;
+    }
+    EvalOut o;
+    const double bar = (use_bw && A.bw) ? h->hscal[0] : h->hscal[0] * (1.0 / (double)A.n);
+    o.lin = h->hscal[1];
+    o.y = bar + h->hscal[1];
+    o.nonfinite_nodes = h->hscal[2];
+    o.gnorm = std::sqrt(h->hscal[5]);
+    o.finite = std::isfinite(o.y) && (h->hscal[6] == 0.0) && std::isfinite(h->hscal[5]);
+    return o;
+  }
+
+  // ---------------------------------------------------------------- system assembly
+  System &system_for(Amg &A, int J);
+  void assemble(Amg &A, System &S, int J, double t, const double *zbase, const double *x);
+  void setup_hierarchy(Amg &A, System &S, int ktop);
+  void dense_factor(System &S, SysLevel &Lv, bool want_inverse);
+  void dense_apply(SysLevel &Lv, const double *b, double *x);      // x = A^{-1} b via factor (direct)
+  void vcycle(System &S, int k);
+  int pcg(System &S, int ktop, const double *b, double *x);
+  int solve_compact(System &S, int ktop, const double *b, double *x);
+  int solve(Amg &A, System &S, int J, const double *g, double *dir);
+
+  // ---------------------------------------------------------------- Newton
+  struct NewtonOut {
+    bool converged;
+    int k;
+    int status;   // MGBX_OK or MGBX_NON_FINITE
+    double y, gnorm, inc;
+  };
+  bool stop_test(int kind, double lambda_tol, double theta, double ymin, double ynext, double gmin, double gnext, double ndec) {
+    const bool ex = (ynext >= ymin) && (gnext >= theta * gmin);
+    if (kind == 0) return ex;
+    return (ndec < lambda_tol) || ex;
+  }
+  NewtonOut newton(Amg &A, int J, double t, int maxit, int stop_kind, double lambda_tol, double theta, const mgbx_step_opts &o);
+  int step(int which, double t, const mgbx_step_opts &o, mgbx_step_result *r);
+  int matched_t(double t_default, double *t_out, double *tstar_out);
+};
+
+// -------------------------------------------------------------------------------------------------
+// host-side plan construction
+// -------------------------------------------------------------------------------------------------
+std::unique_ptr<System> build_system(mgbx_handle *h, Amg &A, bool condensed) {
+  auto S = std::make_unique<System>();
+  Pool &pool = h->pool;
+  cudaStream_t s = h->stream;
+  const int L = A.L;
+  S->condensed = condensed;
+  // which variables can be eliminated node-locally at the fine level: R block == identity and every D row is :id
+  std::vector<char> is_elim(A.nu, 0);
+  if (condensed) {
+    for (int v = 0; v < A.nu; ++v) {
+      const int64_t c0 = A.voff[L - 1][v], c1 = A.voff[L - 1][v + 1];
+      if (c1 - c0 != A.n) continue;
+      bool idonly = true, any = false;
+      for (int j = 0; j < A.nD; ++j)
+        if (A.D_var[j] == v) {
+          any = true;
+          if (A.D_op[j] >= 0) idonly = false;
+        }
+      if (!any || !idonly) continue;
+      HostCsr blk = submatrix(A.hRL, (int64_t)v * A.n, (int64_t)(v + 1) * A.n, c0, c1);
+      if (is_identity(blk)) is_elim[v] = 1;
+    }
+    int ne = 0;
+    for (int v = 0; v < A.nu; ++v) ne += is_elim[v];
+    if (ne > 4) {   // keep at most 4 eliminated variables (register budget of the node kernel)
+      for (int v = A.nu - 1; v >= 0 && ne > 4; --v)
+        if (is_elim[v]) {
+          is_elim[v] = 0;
+          --ne;
+        }
+    }
+    if (ne == A.nu) is_elim[0] = 0;   // keep at least one variable in the reduced system
+  }
+  for (int v = 0; v < A.nu; ++v) (is_elim[v] ? S->elim : S->kept).push_back(v);
+  S->nE = (int)S->elim.size();
+  // row classification
+  S->nK = 0;
+  for (int j = 0; j < A.nD; ++j) {
+    S->Erow[j] = -1;
+    for (int e = 0; e < S->nE; ++e)
+      if (S->elim[e] == A.D_var[j]) S->Erow[j] = e;
+    if (S->Erow[j] < 0) S->Krow[S->nK++] = j;
+  }
+  // variables of the kept set that own at least one D row form the block pairs
+  std::vector<int> used;
+  for (int v : S->kept) {
+    bool any = false;
+    for (int j = 0; j < A.nD; ++j) any = any || (A.D_var[j] == v);
+    if (any) used.push_back(v);
+  }
+  if ((int)(used.size() * used.size()) > 16) throw ArgError("too many coupled state variables (max 4 kept variables)");
+  S->pl.npairs = 0;
+  for (int a : used)
+    for (int b : used) {
+      S->pl.va[S->pl.npairs] = a;
+      S->pl.vb[S->pl.npairs] = b;
+      S->pl.npairs++;
+    }
+  // levels
+  const int nlev = L;
+  S->lev.resize(nlev);
+  for (int k = 0; k < nlev; ++k) {
+    const int l = L - 1 - k;
+    SysLevel &Lv = S->lev[k];
+    Lv.off.assign(1, 0);
+    for (int v : S->kept) Lv.off.push_back(Lv.off.back() + (A.voff[l][v + 1] - A.voff[l][v]));
+    Lv.m = Lv.off.back();
+  }
+  // top pattern = reference plan pattern restricted to the kept variables
+  const int64_t mtop = S->lev[0].m;
+  std::vector<int64_t> colmap(A.m[L - 1], -1);
+  for (size_t q = 0; q < S->kept.size(); ++q) {
+    const int v = S->kept[q];
+    for (int64_t c = A.voff[L - 1][v]; c < A.voff[L - 1][v + 1]; ++c) colmap[c] = S->lev[0].off[q] + (c - A.voff[L - 1][v]);
+  }
+  HostCsr Einc = element_incidence(A.hRL, A.N, A.p, used, A.n, colmap, mtop);
+  HostCsr pat = plan_pattern(Einc);
+  // gather lists: for each nz of the pattern, the Hblk entries (and weights) that sum into it
+  const int p = A.p;
+  const int64_t pp = (int64_t)p * p;
+  S->hblk_size = (int64_t)S->pl.npairs * A.N * pp;
+  {
+    const int64_t nnz = pat.nnz();
+    std::vector<int64_t> cnt(nnz + 1, 0);
+    bool unit = true;
+    auto visit = [&](auto &&fn) {
+      for (int pr = 0; pr < S->pl.npairs; ++pr) {
+        const int va = S->pl.va[pr], vb = S->pl.vb[pr];
+        for (int64_t e = 0; e < A.N; ++e)
+          for (int r = 0; r < p; ++r) {
+            const int64_t ra = (int64_t)va * A.n + e * p + r;
+            for (int64_t ka = A.hRL.ptr[ra]; ka < A.hRL.ptr[ra + 1]; ++ka) {
+              const int64_t row = colmap[A.hRL.idx[ka]];
+              if (row < 0) continue;
+              for (int c = 0; c < p; ++c) {
+                const int64_t rb = (int64_t)vb * A.n + e * p + c;
+                for (int64_t kb = A.hRL.ptr[rb]; kb < A.hRL.ptr[rb + 1]; ++kb) {
+                  const int64_t col = colmap[A.hRL.idx[kb]];
+                  if (col < 0) continue;
+                  const int64_t nz = find_in_row(pat, row, (int32_t)col);
+                  if (nz < 0) throw std::runtime_error("internal: assembly pattern misses an entry");
+                  fn(nz, ((int64_t)pr * A.N + e) * pp + (int64_t)r * p + c, A.hRL.val[ka] * A.hRL.val[kb]);
+                }
+              }
+            }
+          }
+      }
+    };
+    visit([&](int64_t nz, int64_t, double wgt) {
+      cnt[nz + 1]++;
+      if (wgt != 1.0) unit = false;
+    });
+    for (int64_t k = 0; k < nnz; ++k) cnt[k + 1] += cnt[k];
+    std::vector<int64_t> gidx(cnt[nnz]);
+    std::vector<double> gw(unit ? 0 : cnt[nnz]);
+    std::vector<int64_t> pos(cnt.begin(), cnt.end() - 1);
+    visit([&](int64_t nz, int64_t src, double wgt) {
+      const int64_t q = pos[nz]++;
+      gidx[q] = src;
+      if (!unit) gw[q] = wgt;
+    });
+    S->gptr = pool.upload<int64_t>(cnt.data(), cnt.size(), s);
+    S->gidx = pool.upload<int64_t>(gidx.data(), gidx.size(), s);
+    S->gw = unit ? nullptr : pool.upload<double>(gw.data(), gw.size(), s);
+    CK(cudaStreamSynchronize(s));
+  }
+  S->Hblk = pool.alloc<double>(S->hblk_size);
+  // hierarchy patterns
+  HostCsr cur = pat;
+  for (int k = 0; k < nlev; ++k) {
+    SysLevel &Lv = S->lev[k];
+    const int l = L - 1 - k;
+    Lv.A = upload_csr(pool, cur, s, false);
+    Lv.spmv_group = Engine::group_for(Lv.A);
+    Lv.dinv = pool.alloc<double>(Lv.m);
+    Lv.diag = pool.alloc<double>(Lv.m);
+    Lv.b = pool.alloc<double>(Lv.m);
+    Lv.x = pool.alloc<double>(Lv.m);
+    Lv.x2 = pool.alloc<double>(Lv.m);
+    Lv.r = pool.alloc<double>(Lv.m);
+    if (k + 1 < nlev) {
+      // transfer from level l-1 to level l restricted to the kept variables
+      std::vector<HostCsr> blocks;
+      for (int v : S->kept)
+        blocks.push_back(submatrix(A.hT[l - 1], A.voff[l][v], A.voff[l][v + 1], A.voff[l - 1][v], A.voff[l - 1][v + 1]));
+      HostCsr Tk = block_diag(blocks);
+      Lv.has_coarser = true;
+      Lv.T_identity = is_identity(Tk);
+      HostCsr Ttk = transpose(Tk);
+      HostCsr ATp = spgemm_symbolic(cur, Tk);
+      HostCsr nxt = spgemm_symbolic(Ttk, ATp);
+      Lv.T = upload_csr(pool, Tk, s);
+      Lv.Tt = upload_csr(pool, Ttk, s);
+      Lv.AT = upload_csr(pool, ATp, s, false);
+      cur = std::move(nxt);
+    }
+  }
+  // V-cycle cut
+  S->cut = -1;
+  for (int k = 0; k < nlev; ++k)
+    if (S->lev[k].m <= h->cfg.coarse_max) {
+      S->cut = k;
+      break;
+    }
+  if (S->cut < 0 && S->lev[nlev - 1].m <= 4096) S->cut = nlev - 1;
+  const int64_t mx = S->lev[0].m;
+  S->pc_r = pool.alloc<double>(mx);
+  S->pc_z = pool.alloc<double>(mx);
+  S->pc_p = pool.alloc<double>(mx);
+  S->pc_Ap = pool.alloc<double>(mx);
+  S->pc_x = pool.alloc<double>(mx);
+  S->pc_b = pool.alloc<double>(mx);
+  CK(cudaStreamSynchronize(s));
+  return S;
+}
+
+System &Engine::system_for(Amg &A, int J) {
+  const bool fine = (J == A.L - 1);
+  if (fine && h->cfg.condense) {
+    if (!A.sys_cond) A.sys_cond = build_system(h, A, true);
+    return *A.sys_cond;
+  }
+  if (!A.sys_full) A.sys_full = build_system(h, A, false);
+  return *A.sys_full;
+}
+
+// Evaluate the node Hessians at zbase + R_J x and fill the system matrices from the top level down to
+// level index ktop (= L-1-J), then the preconditioner hierarchy below it.
+void Engine::assemble(Amg &A, System &S, int J, double t, const double *zbase, const double *x) {
+  cudaEventRecord(h->ev0, s);
+  prolong_to_fine(A, J, x, zbase, A.zf);
+  NodeParams P = node_params(A, t);
+  P.nK = S.nK;
+  P.nE = S.nE;
+  for (int j = 0; j < MGBX_MAX_ND; ++j) {
+    P.Krow[j] = S.Krow[j];
+    P.Erow[j] = S.Erow[j];
+  }
+  P.Hn = A.Hn;
+  P.hEEinv = A.hEEinv;
+  P.hKE = A.hKE;
+  k_node<NODE_F2><<<red_grid(A.n), kRedThreads, 0, s>>>(P);
+  check_launch();
+  ElemParams E = elem_params(A);
+  E.nK = S.nK;
+  for (int j = 0; j < S.nK; ++j) E.Krow[j] = S.Krow[j];
+  k_blockhess<<<nblk(S.hblk_size), 256, 0, s>>>(E, S.pl, A.Hn, S.Hblk);
+  check_launch();
+  SysLevel &top = S.lev[0];
+  k_csr_gather<<<nblk(top.A.nnz), 256, 0, s>>>(top.A.nnz, S.gptr, S.gidx, S.gw, S.Hblk, top.A.val);
+  check_launch();
+  const int ktop = A.L - 1 - J;
+  setup_hierarchy(A, S, ktop);
+  cudaEventRecord(h->ev1, s);
+  sync();
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+  if (h->res) {
+    h->res->ms_f2 += ms;
+    h->res->f2_evals++;
+  }
+}
+
+void Engine::setup_hierarchy(Amg &A, System &S, int ktop) {
+  const int nlev = (int)S.lev.size();
+  SysLevel &Ltop = S.lev[ktop];
+  const bool direct = Ltop.m <= h->cfg.dense_direct_max;
+  int kend = ktop;
+  if (!direct) kend = (S.cut >= 0) ? std::max(S.cut, ktop) : nlev - 1;
+  for (int k = 0; k < kend; ++k) {
+    SysLevel &Lv = S.lev[k];
+    SysLevel &Lc = S.lev[k + 1];
+    if (Lv.T_identity) {
+      copy(Lc.A.val, Lv.A.val, Lv.A.nnz);
+    } else {
+      k_spgemm_numeric<<<nblk(Lv.AT.rows), 256, 0, s>>>(Lv.A, Lv.T, Lv.AT);
+      check_launch();
+      k_spgemm_numeric<<<nblk(Lc.A.rows), 256, 0, s>>>(Lv.Tt, Lv.AT, Lc.A);
+      check_launch();
+    }
+  }
+  if (direct) {
+    dense_factor(S, Ltop, false);
+    return;
+  }
+  for (int k = ktop; k <= kend; ++k) {
+    SysLevel &Lv = S.lev[k];
+    k_l1diag<<<nblk(Lv.m), 256, 0, s>>>(Lv.A, Lv.dinv, Lv.diag);
+    check_launch();
+  }
+  if (S.cut >= 0 && S.cut >= ktop) dense_factor(S, S.lev[S.cut], true);
+}
+
+void Engine::dense_factor(System &S, SysLevel &Lv, bool want_inverse) {
+  const int m = (int)Lv.m;
+  if (m == 0) return;
+  if (!Lv.dense) {
+    Lv.dense = h->pool.alloc<double>((size_t)m * m);
+    Lv.dscale = h->pool.alloc<double>(m);
+  }
+  if (want_inverse && !Lv.dense_inv) Lv.dense_inv = h->pool.alloc<double>((size_t)m * m);
+  zero(Lv.dense, (int64_t)m * m);
+  k_dense_scale_diag<<<nblk(m), 256, 0, s>>>(Lv.A, Lv.dscale);
+  check_launch();
+  k_csr_to_dense<<<nblk(m), 256, 0, s>>>(Lv.A, Lv.dscale, Lv.dense);
+  check_launch();
+  for (int k0 = 0; k0 < m; k0 += NB) {
+    k_chol_diag<<<1, 256, 0, s>>>(Lv.dense, m, k0);
+    check_launch();
+    const int nb = std::min(NB, m - k0);
+    const int rem = m - k0 - nb;
+    if (rem > 0) {
+      k_chol_trsm<<<nblk(rem, 64), 64, 0, s>>>(Lv.dense, m, k0);
+      check_launch();
+      const int nt = (rem + NB - 1) / NB;
+      k_chol_syrk<<<nt * (nt + 1) / 2, 256, 0, s>>>(Lv.dense, m, k0);
+      check_launch();
+    }
+  }
+  if (want_inverse) {
+    k_chol_solve<<<m, 256, sizeof(double) * m, s>>>(Lv.dense, m, Lv.dense_inv, 1);
+    check_launch();
+  }
+}
+
+// x = A^{-1} b through the scaled Cholesky factor (one right-hand side), uses Lv.r as scratch
+void Engine::dense_apply(SysLevel &Lv, const double *b, double *x) {
+  const int m = (int)Lv.m;
+  k_mul<<<nblk(m), 256, 0, s>>>(m, b, Lv.dscale, x);
+  check_launch();
+  k_chol_solve<<<1, 256, sizeof(double) * m, s>>>(Lv.dense, m, x, 0);
+  check_launch();
+  k_mul<<<nblk(m), 256, 0, s>>>(m, x, Lv.dscale, x);
+  check_launch();
+}
+
+void Engine::vcycle(System &S, int k) {
+  SysLevel &Lv = S.lev[k];
+  const int nlev = (int)S.lev.size();
+  if (k == S.cut) {
+    // x = D Minv D b
+    k_mul<<<nblk(Lv.m), 256, 0, s>>>(Lv.m, Lv.b, Lv.dscale, Lv.r);
+    check_launch();
+    k_dense_symv<<<nblk(Lv.m * 32), 256, 0, s>>>(Lv.dense_inv, (int)Lv.m, Lv.r, Lv.x2);
+    check_launch();
+    k_mul<<<nblk(Lv.m), 256, 0, s>>>(Lv.m, Lv.x2, Lv.dscale, Lv.x);
+    check_launch();
+    return;
+  }
+  const bool bottom = (k == nlev - 1);
+  if (!bottom && Lv.T_identity) {
+    SysLevel &Lc = S.lev[k + 1];
+    copy(Lc.b, Lv.b, Lv.m);
+    vcycle(S, k + 1);
+    copy(Lv.x, Lc.x, Lv.m);
+    return;
+  }
+  const int nu = bottom ? 30 : std::max(1, h->cfg.smoother_sweeps);
+  // pre-smoothing from x = 0
+  double *xa = Lv.x, *xb = Lv.x2;
+  jacobi(Lv, Lv.b, nullptr, xa);
+  for (int it = 1; it < nu; ++it) {
+    jacobi(Lv, Lv.b, xa, xb);
+    std::swap(xa, xb);
+  }
+  if (!bottom) {
+    SysLevel &Lc = S.lev[k + 1];
+    spmv(Lv.A, xa, Lv.b, -1.0, Lv.r, Lv.spmv_group);           // r = b - A x
+    spmv(Lv.Tt, Lv.r, nullptr, 1.0, Lc.b);
+    vcycle(S, k + 1);
+    spmv(Lv.T, Lc.x, xa, 1.0, xa);                              // x += T xc (row-local, in place)
+    for (int it = 0; it < nu; ++it) {
+      jacobi(Lv, Lv.b, xa, xb);
+      std::swap(xa, xb);
+    }
+  }
+  if (xa != Lv.x) copy(Lv.x, xa, Lv.m);
+}
+
+// Preconditioned CG on lev[ktop]; returns the iteration count (negative: breakdown)
+int Engine::pcg(System &S, int ktop, const double *b, double *x) {
+  SysLevel &Lv = S.lev[ktop];
+  const int64_t m = Lv.m;
+  double *r = S.pc_r, *z = S.pc_z, *p = S.pc_p, *Ap = S.pc_Ap;
+  double *scal = h->dscal + 8;   // {rz, pAp, rr, rz_new, beta}
+  const unsigned int rg = red_grid(m);
+  zero(x, m);
+  copy(r, b, m);
+  k_dot<<<rg, kRedThreads, 0, s>>>(m, r, r, h->partials, h->ticket, scal + 2);
+  check_launch();
+  CK(cudaMemcpyAsync(h->hscal + 8, scal, sizeof(double) * 5, cudaMemcpyDeviceToHost, s));
+  sync();
+  const double bb = h->hscal[10];
+  if (!(bb > 0.0) || !std::isfinite(bb)) return 0;
+  const double target = h->cfg.pcg_rtol * h->cfg.pcg_rtol * bb;
+  int it = 0;
+  double best = bb;
+  int since_best = 0;
+  for (; it < h->cfg.pcg_maxit;) {
+    copy(Lv.b, r, m);
+    vcycle(S, ktop);
+    const double *zz = Lv.x;
+    if (it == 0) {
+      k_dot<<<rg, kRedThreads, 0, s>>>(m, r, zz, h->partials, h->ticket, scal + 0);
+      check_launch();
+      copy(p, zz, m);
+    } else {
+      k_dot<<<rg, kRedThreads, 0, s>>>(m, r, zz, h->partials, h->ticket, scal + 3);
+      check_launch();
+      k_pcg_beta<<<1, 1, 0, s>>>(scal);
+      check_launch();
+      k_pcg_dir<<<nblk(m), 256, 0, s>>>(m, scal, zz, p);
+      check_launch();
+    }
+    (void)z;
+    spmv(Lv.A, p, nullptr, 1.0, Ap, Lv.spmv_group);
+    k_dot<<<rg, kRedThreads, 0, s>>>(m, p, Ap, h->partials, h->ticket, scal + 1);
+    check_launch();
+    k_pcg_update<<<rg, kRedThreads, 0, s>>>(m, scal, p, Ap, x, r, h->partials, h->ticket);
+    check_launch();
+    ++it;
+    CK(cudaMemcpyAsync(h->hscal + 8, scal, sizeof(double) * 5, cudaMemcpyDeviceToHost, s));
+    sync();
+    const double rr = h->hscal[10];
+    if (!std::isfinite(rr) || !(h->hscal[9] > 0.0)) return -it;   // breakdown (indefinite or non-finite)
+    if (rr <= target) break;
+    if (rr < best * 0.999) {
+      best = rr;
+      since_best = 0;
+    } else if (++since_best >= 25) {
+      break;   // stagnation at the attainable accuracy
+    }
+  }
+  return it;
+}
+
+int Engine::solve_compact(System &S, int ktop, const double *b, double *x) {
+  SysLevel &Lv = S.lev[ktop];
+  if (Lv.m <= h->cfg.dense_direct_max) {
+    dense_apply(Lv, b, x);
+    // one step of iterative refinement against the CSR operator
+    spmv(Lv.A, x, b, -1.0, Lv.r, Lv.spmv_group);
+    dense_apply(Lv, Lv.r, Lv.x2);
+    k_axpby<<<nblk(Lv.m), 256, 0, s>>>(Lv.m, 1.0, x, 1.0, Lv.x2, x);
+    check_launch();
+    return 0;
+  }
+  return pcg(S, ktop, b, x);
+}
+
+// dir = H_J^{-1} g  (full level-J vectors).  With a condensed system the node-local variables are
+// eliminated exactly first and recovered by back-substitution.
+int Engine::solve(Amg &A, System &S, int J, const double *g, double *dir) {
+  cudaEventRecord(h->ev0, s);
+  const int ktop = A.L - 1 - J;
+  SysLevel &Lv = S.lev[ktop];
+  int iters = 0;
+  if (S.nE == 0) {
+    iters = solve_compact(S, ktop, g, dir);
+  } else {
+    // (only at the fine level)  rhs_K = g_K + R_K' sum_j D_j' gt_j
+    CondParams C;
+    memset(&C, 0, sizeof(C));
+    C.n = A.n;
+    C.nD = A.nD;
+    C.nK = S.nK;
+    C.nE = S.nE;
+    for (int j = 0; j < S.nK; ++j) C.Krow[j] = S.Krow[j];
+    for (int e = 0; e < S.nE; ++e) C.Eoff[e] = A.voff[A.L - 1][S.elim[e]];
+    C.hEEinv = A.hEEinv;
+    C.hKE = A.hKE;
+    k_condense_rhs<<<nblk(A.n), 256, 0, s>>>(C, g, A.G);
+    check_launch();
+    ElemParams E = elem_params(A);
+    E.nK = S.nK;
+    for (int j = 0; j < S.nK; ++j) E.Krow[j] = S.Krow[j];
+    k_blockgrad<<<nblk((int64_t)A.nu * A.n), 256, 0, s>>>(E, A.G, A.gb, A.nu);
+    check_launch();
+    spmv(A.RLt, A.gb, g, 1.0, A.tmp);                 // tmp = g + R' gb   (entries of eliminated variables unused)
+    for (size_t q = 0; q < S.kept.size(); ++q)
+      copy(S.pc_b + Lv.off[q], A.tmp + A.voff[A.L - 1][S.kept[q]], Lv.off[q + 1] - Lv.off[q]);
+    iters = solve_compact(S, ktop, S.pc_b, S.pc_x);
+    zero(dir, A.m[A.L - 1]);
+    for (size_t q = 0; q < S.kept.size(); ++q)
+      copy(dir + A.voff[A.L - 1][S.kept[q]], S.pc_x + Lv.off[q], Lv.off[q + 1] - Lv.off[q]);
+    // broken image of the kept part, then back-substitution
+    spmv(A.RL, dir, nullptr, 1.0, A.gb);
+    NodeParams NP = node_params(A, 0.0);
+    NP.zf = A.gb;
+    k_backsubst<<<nblk(A.n), 256, 0, s>>>(C, NP, g, dir);
+    check_launch();
+  }
+  cudaEventRecord(h->ev1, s);
+  // inc = g . dir, finiteness of dir
+  k_dot2<<<red_grid(A.m[J]), kRedThreads, 0, s>>>(A.m[J], dir, g, h->partials, h->ticket, h->dscal + 4);
+  check_launch();
+  fetch(8);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+  if (h->res) {
+    h->res->ms_solve += ms;
+    h->res->linear_solves++;
+    h->res->pcg_iters += iters > 0 ? iters : -iters;
+  }
+  return iters;
+}
+
+Engine::NewtonOut Engine::newton(Amg &A, int J, double t, int maxit, int stop_kind, double lambda_tol, double theta,
+                                 const mgbx_step_opts &o) {
+  NewtonOut out{false, 0, MGBX_OK, 0.0, 0.0, 0.0};
+  const int64_t m = A.m[J];
+  System &S = system_for(A, J);
+  zero(A.x, m);
+  EvalOut e0 = eval_f01(A, J, t, A.z, A.x, A.g);
+  if (!e0.finite) {
+    out.status = MGBX_NON_FINITE;
+    out.y = e0.y;
+    return out;
+  }
+  double y = e0.y, gnorm = e0.gnorm;
+  double ymin = y, gmin = gnorm, incmin = INFINITY;
+  bool converged = false;
+  int k = 0;
+  const double eps = 2.220446049250313e-16;
+  while (k < maxit && !converged) {
+    ++k;
+    assemble(A, S, J, t, A.z, A.x);
+    solve(A, S, J, A.g, A.dir);
+    const double inc = h->hscal[4];
+    const bool dir_finite = (h->hscal[6] == 0.0) && std::isfinite(h->hscal[5]) && std::isfinite(inc);
+    out.inc = inc;
+    if (h->cfg.verbose > 1) fprintf(stderr, "[mgbx] newton J=%d k=%d y=%.17g |g|=%.6g lam2=%.6g\n", J, k, y, gnorm, inc);
+    if (!dir_finite) {
+      out.status = MGBX_NON_FINITE;
+      break;
+    }
+    if (inc <= 0.0) {
+      converged = std::fabs(inc) <= eps * std::max(std::fabs(y), 1.0);
+      break;
+    }
+    // backtracking line search (newton.jl:139-154 with the trial loop of :35-50)
+    double sstep = 1.0;
+    double yn = y, gnn = gnorm;
+    bool have_trial = false;   // xbest/gbest hold the last finite trial
+    while (sstep > 0.0) {
+      k_trial<<<red_grid(m), kRedThreads, 0, s>>>(m, A.x, A.dir, sstep, A.xn, h->partials, h->ticket, h->dscal + 3);
+      check_launch();
+      EvalOut et = eval_f01(A, J, t, A.z, A.xn, A.gn);
+      const bool stalled = (h->hscal[3] == 0.0);
+      if (et.finite) {
+        std::swap(A.xn, A.xbest);
+        std::swap(A.gn, A.gbest);
+        have_trial = true;
+        yn = et.y;
+        gnn = et.gnorm;
+        if (stalled || yn <= y - o.ls_c1 * inc * sstep) break;
+      }
+      sstep *= o.ls_beta;
+    }
+    if (stop_test(stop_kind, lambda_tol, theta, ymin, yn, gmin, gnn, std::sqrt(inc))) converged = true;
+    if (have_trial) {
+      std::swap(A.x, A.xbest);
+      std::swap(A.g, A.gbest);
+    }
+    y = yn;
+    gnorm = gnn;
+    gmin = std::min(gmin, gnorm);
+    ymin = std::min(ymin, y);
+    incmin = std::min(inc, incmin);
+  }
+  out.converged = converged;
+  out.k = k;
+  out.y = y;
+  out.gnorm = gnorm;
+  return out;
+}
+
+int Engine::step(int which, double t, const mgbx_step_opts &o, mgbx_step_result *r) {
+  Amg &A = h->amg[which];
+  memset(r, 0, sizeof(*r));
+  h->res = r;
+  const int L = A.L;
+  copy(A.zsave, A.z, (int64_t)A.nu * A.n);
+  int status = MGBX_OK;
+  // eta(j, J): Newton in range(R_fine[J]) around the current z (levels 1-based as in the reference)
+  auto eta = [&](int j, int J, int stop_kind, double ltol, double theta, int mxit) -> bool {
+    (void)j;
+    if (status != MGBX_OK) return false;
+    NewtonOut n = newton(A, J - 1, t, mxit, stop_kind, ltol, theta, o);
+    r->its[J - 1] += n.k;
+    r->y = n.y;
+    r->gnorm = n.gnorm;
+    r->inc = n.inc;
+    if (n.status != MGBX_OK) {
+      status = n.status;
+      return false;
+    }
+    if (n.converged) {
+      prolong_to_fine(A, J - 1, A.x, A.z, A.zf);
+      std::swap(A.z, A.zf);
+    }
+    return n.converged;
+  };
+  std::function<bool(int, int)> dac = [&](int j, int J) -> bool {
+    const int mn = (o.initial_step && J - j == 1) ? o.maxit : o.max_newton;
+    if (eta(j, J, o.stop_kind, o.stop_lambda_tol, o.stop_theta, mn)) return true;
+    const int jmid = (j + J) / 2;
+    if (jmid == j || jmid == J) return false;
+    return dac(j, jmid) && dac(jmid, J);
+  };
+  bool converged = dac(0, L);
+  if (o.finalize && status == MGBX_OK) {
+    const bool foo = eta(L - 1, L, 0, 0.0, o.finalize_theta, o.maxit);
+    converged = converged && foo;
+  }
+  r->converged = converged ? 1 : 0;
+  h->res = nullptr;
+  if (status != MGBX_OK || !converged) {
+    copy(A.z, A.zsave, (int64_t)A.nu * A.n);   // the caller discards a failed step (mgb.jl:147-163)
+    sync();
+    return status != MGBX_OK ? status : MGBX_NOT_CONVERGED;
+  }
+  sync();
+  return MGBX_OK;
+}
+
+int Engine::matched_t(double t_default, double *t_out, double *tstar_out) {
+  Amg &A = h->amg[MGBX_MAIN];
+  const int J = A.L - 1;
+  const int64_t m = A.m[J];
+  System &S = system_for(A, J);
+  zero(A.x, m);
+  EvalOut e0 = eval_f01(A, J, 0.0, A.z, A.x, A.g);        // g = grad of the barrier term
+  EvalOut e1 = eval_f01(A, J, 1.0, A.z, A.x, A.gn);       // gn = gphi + gc
+  (void)e0;
+  (void)e1;
+  k_axpby<<<nblk(m), 256, 0, s>>>(m, 1.0, A.gn, -1.0, A.g, A.gn);   // gn = gc
+  check_launch();
+  assemble(A, S, J, 1.0, A.z, A.x);
+  solve(A, S, J, A.g, A.dir);      // nphi
+  solve(A, S, J, A.gn, A.xn);      // nc
+  const double d = h->hscal[4];    // gc . nc
+  k_dot<<<red_grid(m), kRedThreads, 0, s>>>(m, A.g, A.xn, h->partials, h->ticket, h->dscal + 0);
+  check_launch();
+  k_dot<<<red_grid(m), kRedThreads, 0, s>>>(m, A.gn, A.dir, h->partials, h->ticket, h->dscal + 1);
+  check_launch();
+  fetch(2);
+  const double b = h->hscal[0] + h->hscal[1];
+  *tstar_out = NAN;
+  *t_out = t_default;
+  if (!(d > 0.0)) return MGBX_OK;
+  const double tstar = -b / (2.0 * d);
+  *tstar_out = tstar;
+  if (!(std::isfinite(tstar) && tstar > 0.0)) return MGBX_OK;
+  *t_out = std::min(std::max(tstar, std::sqrt(2.220446049250313e-16)), t_default);
+  return MGBX_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// create
+// -------------------------------------------------------------------------------------------------
+void upload_convex(mgbx_handle *h, const mgbx_convex &Q, int64_t n, int nD_user, ConvexDev &cd) {
+  Pool &pool = h->pool;
+  cudaStream_t s = h->stream;
+  memset(&cd, 0, sizeof(cd));
+  if (Q.npieces < 0 || Q.npieces > MGBX_MAX_PIECES) throw ArgError("convex set: unsupported number of pieces");
+  cd.npieces = Q.npieces;
+  for (int k = 0; k < Q.npieces; ++k) {
+    const mgbx_piece &q = Q.pieces[k];
+    PieceDev &d = cd.pc[k];
+    if (q.kind != MGBX_PIECE_EP && q.kind != MGBX_PIECE_LINEAR) throw ArgError("convex piece: unknown kind");
+    if (q.ni < 1 || q.ni > MGBX_MAX_NI || q.nc < 1 || q.nc > MGBX_MAX_NC) throw ArgError("convex piece: ni / nc out of range");
+    if (q.kind == MGBX_PIECE_EP && q.nc != q.ni) throw ArgError("EP piece needs a square A (nc == ni == nz)");
+    if (q.kind == MGBX_PIECE_EP && q.nc < 1) throw ArgError("EP piece needs nz >= 1");
+    d.kind = q.kind;
+    d.ni = q.ni;
+    d.nc = q.nc;
+    for (int c = 0; c < q.ni; ++c) {
+      d.idx[c] = q.idx ? q.idx[c] : c;
+      if (d.idx[c] < 0 || d.idx[c] >= nD_user) throw ArgError("convex piece indexes a D row that does not exist");
+    }
+    // grid compression: identity A / zero b / uniform p, mu are passed as constants (no HBM traffic)
+    bool Aid = (q.nc == q.ni);
+    if (Aid && q.A)
+      for (int c = 0; c < q.ni && Aid; ++c)
+        for (int r = 0; r < q.nc && Aid; ++r) {
+          const double want = (r == c) ? 1.0 : 0.0;
+          const double *col = q.A + (int64_t)(c * q.nc + r) * n;
+          for (int64_t i = 0; i < n; ++i)
+            if (col[i] != want) {
+              Aid = false;
+              break;
+            }
+        }
+    if (!q.A && !(q.nc == q.ni)) throw ArgError("convex piece: A missing");
+    d.A = (Aid || !q.A) ? nullptr : pool.upload<double>(q.A, (size_t)n * q.nc * q.ni, s);
+    bool bz = true;
+    if (q.b)
+      for (int64_t i = 0; i < n * q.nc; ++i)
+        if (q.b[i] != 0.0) {
+          bz = false;
+          break;
+        }
+    d.b = (bz || !q.b) ? nullptr : pool.upload<double>(q.b, (size_t)n * q.nc, s);
+    d.p_uniform = 2.0;
+    d.mu_uniform = 0.0;
+    d.p = d.mu = nullptr;
+    if (q.kind == MGBX_PIECE_EP) {
+      if (!q.p || !q.mu) throw ArgError("EP piece: p / mu grids missing");
+      bool pu = true, mu_u = true;
+      for (int64_t i = 1; i < n; ++i) {
+        if (q.p[i] != q.p[0]) pu = false;
+        if (q.mu[i] != q.mu[0]) mu_u = false;
+      }
+      if (pu) d.p_uniform = q.p[0];
+      else d.p = pool.upload<double>(q.p, n, s);
+      if (mu_u) d.mu_uniform = q.mu[0];
+      else d.mu = pool.upload<double>(q.mu, n, s);
+    }
+  }
+  cd.select = nullptr;
+  if (Q.select) {
+    bool all = true;
+    for (int64_t i = 0; i < n * Q.npieces; ++i)
+      if (Q.select[i] == 0.0) {
+        all = false;
+        break;
+      }
+    if (!all) cd.select = pool.upload<double>(Q.select, (size_t)n * Q.npieces, s);
+  }
+  cd.feas = 0;
+  cd.NC = nD_user + 1;
+  cd.NF = nD_user;
+}
+
+void create_amg(mgbx_handle *h, const mgbx_amg &in, Amg &A) {
+  Pool &pool = h->pool;
+  cudaStream_t s = h->stream;
+  if (in.n <= 0 || in.N <= 0 || in.p <= 0 || in.n != in.N * (int64_t)in.p) throw ArgError("amg: n must equal p*N");
+  if (in.nu < 1 || in.nu > MGBX_MAX_ND) throw ArgError("amg: nu out of range");
+  if (in.nD < 1 || in.nD > MGBX_MAX_ND) throw ArgError("amg: nD out of range (MGBX_MAX_ND)");
+  if (in.L < 1 || in.L > MGBX_MAX_LEVELS) throw ArgError("amg: L out of range");
+  if (in.nops < 0 || in.nops > MGBX_MAX_OPS) throw ArgError("amg: too many distinct operators");
+  A.n = in.n;
+  A.N = in.N;
+  A.p = in.p;
+  A.nu = in.nu;
+  A.nD = in.nD;
+  A.L = in.L;
+  A.nops = in.nops;
+  for (int j = 0; j < in.nD; ++j) {
+    A.D_var[j] = in.D_var[j];
+    A.D_op[j] = in.D_op[j];
+    if (A.D_var[j] < 0 || A.D_var[j] >= in.nu) throw ArgError("amg: D row references a state variable that does not exist");
+    if (A.D_op[j] >= in.nops) throw ArgError("amg: D row references an operator that does not exist");
+  }
+  const size_t ppN = (size_t)in.p * in.p * in.N;
+  for (int o = 0; o < in.nops; ++o) A.ops[o] = pool.upload<double>(in.op_data[o], ppN, s);
+  A.w = pool.upload<double>(in.w, in.n, s);
+  A.voff.resize(in.L);
+  A.m.resize(in.L);
+  for (int l = 0; l < in.L; ++l) {
+    A.voff[l].assign(in.var_offsets + (size_t)l * (in.nu + 1), in.var_offsets + (size_t)(l + 1) * (in.nu + 1));
+    A.m[l] = A.voff[l][in.nu];
+    if (A.voff[l][0] != 0) throw ArgError("amg: var_offsets must start at 0");
+    if (in.R_fine[l].cols != A.m[l] || in.R_fine[l].rows != (int64_t)in.nu * in.n)
+      throw ArgError("amg: R_fine dimension mismatch (rows must be nu*n, cols must match var_offsets)");
+  }
+  A.hRL = csr_from_abi(in.R_fine[in.L - 1]);
+  A.RL = upload_csr(pool, A.hRL, s);
+  A.RLt = upload_csr(pool, transpose(A.hRL), s);
+  A.hT.resize(std::max(0, in.L - 1));
+  A.T.resize(A.hT.size());
+  A.Tt.resize(A.hT.size());
+  for (int l = 0; l + 1 < in.L; ++l) {
+    if (!in.T) throw ArgError("amg: level transfers T are required when L > 1");
+    if (in.T[l].rows != A.m[l + 1] || in.T[l].cols != A.m[l]) throw ArgError("amg: T dimension mismatch");
+    A.hT[l] = csr_from_abi(in.T[l]);
+    A.T[l] = upload_csr(pool, A.hT[l], s);
+    A.Tt[l] = upload_csr(pool, transpose(A.hT[l]), s);
+  }
+  const int64_t nun = (int64_t)in.nu * in.n;
+  A.z = pool.zeros<double>(nun, s);
+  A.zsave = pool.zeros<double>(nun, s);
+  A.zinit = pool.zeros<double>(nun, s);
+  A.zf = pool.zeros<double>(nun, s);
+  A.gb = pool.zeros<double>(nun, s);
+  A.G = pool.zeros<double>((size_t)in.n * in.nD, s);
+  A.f = pool.zeros<double>((size_t)in.n * in.nD, s);
+  A.Hn = pool.alloc<double>((size_t)in.n * (in.nD * (in.nD + 1) / 2));
+  A.hEEinv = pool.alloc<double>((size_t)in.n * 10);
+  A.hKE = pool.alloc<double>((size_t)in.n * in.nD * 4);
+  A.slack = pool.alloc<double>(in.n);
+  A.chain.resize(in.L);
+  A.chain2.resize(in.L);
+  for (int l = 0; l < in.L; ++l) {
+    A.chain[l] = pool.alloc<double>(A.m[l]);
+    A.chain2[l] = pool.alloc<double>(A.m[l]);
+  }
+  int64_t mmax = 0;
+  for (int l = 0; l < in.L; ++l) mmax = std::max(mmax, A.m[l]);
+  A.x = pool.zeros<double>(mmax, s);
+  A.xn = pool.zeros<double>(mmax, s);
+  A.g = pool.zeros<double>(mmax, s);
+  A.gn = pool.zeros<double>(mmax, s);
+  A.dir = pool.zeros<double>(mmax, s);
+  A.rhs = pool.zeros<double>(mmax, s);
+  A.tmp = pool.zeros<double>(mmax, s);
+  A.xbest = pool.zeros<double>(mmax, s);
+  A.gbest = pool.zeros<double>(mmax, s);
+}
+
+int guarded(mgbx_handle *h, const std::function<int()> &fn) {
+  try {
+    return fn();
+  } catch (const ArgError &e) {
+    if (h) h->err = e.what();
+    g_last_error = e.what();
+    return MGBX_ERR_ARG;
+  } catch (const std::invalid_argument &e) {
+    if (h) h->err = e.what();
+    g_last_error = e.what();
+    return MGBX_ERR_ARG;
+  } catch (const std::bad_alloc &) {
+    if (h) h->err = "host allocation failed";
+    g_last_error = "host allocation failed";
+    return MGBX_ERR_ALLOC;
+  } catch (const std::exception &e) {
+    if (h) h->err = e.what();
+    g_last_error = e.what();
+    const bool cuda = std::string(e.what()).find("CUDA") != std::string::npos || std::string(e.what()).find("cudaMalloc") != std::string::npos;
+    return cuda ? MGBX_ERR_CUDA : MGBX_ERR_INTERNAL;
+  }
+}
+
+}  // namespace
+
+// -------------------------------------------------------------------------------------------------
+// C ABI
+// -------------------------------------------------------------------------------------------------
+extern "C" {
+
+void mgbx_default_config(mgbx_config *c) {
+  c->dense_direct_max = 2048;
+  c->coarse_max = 512;
+  c->pcg_maxit = 400;
+  c->pcg_rtol = 1e-11;
+  c->smoother_sweeps = 2;
+  c->condense = 1;
+  c->device = -1;
+  c->verbose = 0;
+}
+
+void mgbx_default_step_opts(mgbx_step_opts *o, int64_t n) {
+  o->maxit = 10000;
+  o->max_newton = 8;   // ceil(log2(-log2(eps))) + 2 for Float64 (src/mgb.jl:101)
+  o->initial_step = 0;
+  o->stop_kind = 1;
+  o->stop_lambda_tol = 0.25 / std::sqrt((double)n);
+  o->stop_theta = 0.9;
+  o->finalize = 0;
+  o->finalize_theta = 0.9;
+  o->line_search = 0;
+  o->ls_beta = 0.5;
+  o->ls_c1 = 0.1;
+}
+
+int mgbx_abi_version(void) { return MGBX_ABI_VERSION; }
+
+int mgbx_device_count(void) {
+  int c = 0;
+  if (cudaGetDeviceCount(&c) != cudaSuccess) return 0;
+  return c;
+}
+
+const char *mgbx_last_error(const mgbx_handle *h) { return h ? h->err.c_str() : g_last_error.c_str(); }
+
+int mgbx_create(const mgbx_problem *prob, const mgbx_config *cfg, mgbx_handle **out) {
+  if (!prob || !out) {
+    g_last_error = "mgbx_create: null argument";
+    return MGBX_ERR_ARG;
+  }
+  *out = nullptr;
+  mgbx_handle *h = new mgbx_handle();
+  if (cfg) h->cfg = *cfg;
+  else mgbx_default_config(&h->cfg);
+  if (h->cfg.dense_direct_max > 4096) h->cfg.dense_direct_max = 4096;
+  if (h->cfg.coarse_max > h->cfg.dense_direct_max) h->cfg.coarse_max = h->cfg.dense_direct_max;
+  int rc = guarded(h, [&]() -> int {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+      throw std::runtime_error("CUDA device required: libmgbx has no CPU fallback (cudaGetDeviceCount: " +
+                               std::string(cudaGetErrorString(e)) + ")");
+    if (h->cfg.device >= 0) CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&h->ev0));
+    CK(cudaEventCreate(&h->ev1));
+    h->partials = h->pool.zeros<double>((size_t)kRedBlocks * 8, h->stream);
+    h->ticket = h->pool.zeros<unsigned int>(4, h->stream);
+    h->dscal = h->pool.zeros<double>(32, h->stream);
+    CK(cudaMallocHost((void **)&h->hscal, sizeof(double) * 32));
+    const mgbx_amg &a0 = prob->amg[0];
+    create_amg(h, a0, h->amg[0]);
+    Amg &A = h->amg[0];
+    if (!prob->f_grid || !prob->g_grid) throw ArgError("f_grid / g_grid missing");
+    CK(cudaMemcpyAsync(A.f, prob->f_grid, sizeof(double) * A.n * A.nD, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(A.z, prob->g_grid, sizeof(double) * A.n * A.nu, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(A.zinit, prob->g_grid, sizeof(double) * A.n * A.nu, cudaMemcpyHostToDevice, h->stream));
+    if (prob->barrier_weights) A.bw = h->pool.upload<double>(prob->barrier_weights, A.n, h->stream);
+    upload_convex(h, prob->Q, A.n, A.nD, A.cd);
+    if (prob->amg[1].n > 0) {
+      const mgbx_amg &a1 = prob->amg[1];
+      if (a1.n != a0.n || a1.nu != a0.nu + 1 || a1.nD != a0.nD + 1 + a0.nu)
+        throw ArgError("feasibility AMG must have nu+1 state variables and nD+1+nu rows (src/multigrid.jl:522-536)");
+      create_amg(h, a1, h->amg[1]);
+      Amg &F = h->amg[1];
+      F.cd = A.cd;          // same grids, wrapped
+      F.cd.feas = 1;
+      F.cd.NC = A.nD + 1;
+      F.cd.NF = F.nD;
+      F.cd.fb = 1.0;
+      F.cd.fR = 10.0;
+      // phase-I cost: integral of the slack = row nD of D (0-based) (src/mgb.jl:446-448)
+      std::vector<double> c1((size_t)F.n * F.nD, 0.0);
+      for (int64_t i = 0; i < F.n; ++i) c1[(size_t)A.nD * F.n + i] = 1.0;
+      CK(cudaMemcpyAsync(F.f, c1.data(), sizeof(double) * c1.size(), cudaMemcpyHostToDevice, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      h->has_feas = true;
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return MGBX_OK;
+  });
+  if (rc != MGBX_OK) {
+    g_last_error = h->err;
+    mgbx_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return MGBX_OK;
+}
+
+void mgbx_destroy(mgbx_handle *h) {
+  if (!h) return;
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  h->pool.release();
+  if (h->hscal) cudaFreeHost(h->hscal);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int mgbx_step(mgbx_handle *h, int which, double t, const mgbx_step_opts *o, mgbx_step_result *r) {
+  if (!h || !o || !r) return MGBX_ERR_ARG;
+  return guarded(h, [&]() -> int {
+    if (which < 0 || which > 1 || (which == 1 && !h->has_feas)) throw ArgError("mgbx_step: no such AMG");
+    if (o->line_search != 0) {
+      h->err = "line_search = illinois is not implemented yet";
+      return MGBX_ERR_UNSUPPORTED;
+    }
+    Engine E(h);
+    return E.step(which, t, *o, r);
+  });
+}
+
+int mgbx_scalars(mgbx_handle *h, int which, mgbx_scalars_out *out) {
+  if (!h || !out) return MGBX_ERR_ARG;
+  return guarded(h, [&]() -> int {
+    if (which < 0 || which > 1 || (which == 1 && !h->has_feas)) throw ArgError("mgbx_scalars: no such AMG");
+    Engine E(h);
+    Amg &A = h->amg[which];
+    memset(out, 0, sizeof(*out));
+    // c_dot_Dz = sum_j dot(w .* f[:, j], D_j z): the linear part of f0 at t = 1, s = 0
+    CK(cudaMemsetAsync(A.x, 0, sizeof(double) * A.m[A.L - 1], h->stream));
+    EvalOut e = E.eval_f01(A, A.L - 1, 1.0, A.z, A.x, A.gn);
+    out->c_dot_Dz = e.lin;
+    out->all_finite = 1;
+    for (int v = 0; v < A.nu; ++v) {
+      k_maxabs<<<E.red_grid(A.n), kRedThreads, 0, h->stream>>>(A.n, A.z + (int64_t)v * A.n, h->partials, h->ticket, h->dscal);
+      E.check_launch();
+      E.fetch(3);
+      out->var_max[v] = h->hscal[0];
+      out->var_absmax[v] = h->hscal[1];
+      if (h->hscal[2] != 0.0) out->all_finite = 0;
+    }
+    return MGBX_OK;
+  });
+}
+
+int mgbx_phase1_init(mgbx_handle *h, int32_t *needs_phase1, double *b, double *zabsmax) {
+  if (!h || !needs_phase1 || !b || !zabsmax) return MGBX_ERR_ARG;
+  return guarded(h, [&]() -> int {
+    Engine E(h);
+    Amg &A = h->amg[0];
+    // feasibility probe: the barrier at every node of D*z0, ignoring barrier weights (src/mgb.jl:417-420)
+    CK(cudaMemsetAsync(A.x, 0, sizeof(double) * A.m[A.L - 1], h->stream));
+    EvalOut e = E.eval_f01(A, A.L - 1, 0.0, A.z, A.x, A.gn, /*use_bw=*/false);
+    *needs_phase1 = (e.nonfinite_nodes > 0.0 || !std::isfinite(e.y)) ? 1 : 0;
+    double zmax = 0.0;
+    for (int v = 0; v < A.nu; ++v) {
+      k_maxabs<<<E.red_grid(A.n), kRedThreads, 0, h->stream>>>(A.n, A.z + (int64_t)v * A.n, h->partials, h->ticket, h->dscal);
+      E.check_launch();
+      E.fetch(3);
+      zmax = std::max(zmax, h->hscal[1]);
+    }
+    *zabsmax = zmax;
+    *b = 0.0;
+    if (*needs_phase1) {
+      if (!h->has_feas) throw ArgError("phase I needed but the problem carries no feasibility AMG");
+      Amg &F = h->amg[1];
+      // slack_i = 2*max(slack_fn(D z0), 1);  b = 2*max(1, max slack)   (src/mgb.jl:437-445)
+      NodeParams P = E.node_params(A, 0.0);   // A.zf holds z0 from the probe
+      k_node<NODE_SLACK><<<E.red_grid(A.n), kRedThreads, 0, h->stream>>>(P);
+      E.check_launch();
+      k_phase1_slack<<<nblk(A.n), 256, 0, h->stream>>>(A.n, A.slack, F.zinit + (int64_t)A.nu * A.n);
+      E.check_launch();
+      E.copy(F.zinit, A.z, (int64_t)A.nu * A.n);
+      E.copy(F.z, F.zinit, (int64_t)F.nu * F.n);
+      k_maxabs<<<E.red_grid(A.n), kRedThreads, 0, h->stream>>>(A.n, F.zinit + (int64_t)A.nu * A.n, h->partials, h->ticket, h->dscal);
+      E.check_launch();
+      E.fetch(3);
+      *b = 2.0 * std::max(1.0, h->hscal[0]);
+    }
+    return MGBX_OK;
+  });
+}
+
+int mgbx_set_feasibility_box(mgbx_handle *h, double b, double Rbox) {
+  if (!h || !h->has_feas) return MGBX_ERR_ARG;
+  h->amg[1].cd.fb = b;
+  h->amg[1].cd.fR = Rbox;
+  return MGBX_OK;
+}
+
+int mgbx_reset_feasibility_state(mgbx_handle *h) {
+  if (!h || !h->has_feas) return MGBX_ERR_ARG;
+  return guarded(h, [&]() -> int {
+    Amg &F = h->amg[1];
+    CK(cudaMemcpyAsync(F.z, F.zinit, sizeof(double) * F.nu * F.n, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MGBX_OK;
+  });
+}
+
+int mgbx_handoff(mgbx_handle *h) {
+  if (!h || !h->has_feas) return MGBX_ERR_ARG;
+  return guarded(h, [&]() -> int {
+    Amg &A = h->amg[0], &F = h->amg[1];
+    CK(cudaMemcpyAsync(A.z, F.z, sizeof(double) * A.nu * A.n, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MGBX_OK;
+  });
+}
+
+int mgbx_matched_t(mgbx_handle *h, double t_default, double *t_out, double *tstar_out) {
+  if (!h || !t_out || !tstar_out) return MGBX_ERR_ARG;
+  return guarded(h, [&]() -> int {
+    Engine E(h);
+    return E.matched_t(t_default, t_out, tstar_out);
+  });
+}
+
+int mgbx_get_z(mgbx_handle *h, int which, double *z_host) {
+  if (!h || !z_host || which < 0 || which > 1) return MGBX_ERR_ARG;
+  return guarded(h, [&]() -> int {
+    Amg &A = h->amg[which];
+    CK(cudaMemcpyAsync(z_host, A.z, sizeof(double) * A.nu * A.n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MGBX_OK;
+  });
+}
+
+int mgbx_set_z(mgbx_handle *h, int which, const double *z_host) {
+  if (!h || !z_host || which < 0 || which > 1) return MGBX_ERR_ARG;
+  return guarded(h, [&]() -> int {
+    Amg &A = h->amg[which];
+    CK(cudaMemcpyAsync(A.z, z_host, sizeof(double) * A.nu * A.n, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MGBX_OK;
+  });
+}
+
+int mgbx_set_grids(mgbx_handle *h, const double *f_grid, const double *g_grid) {
+  if (!h) return MGBX_ERR_ARG;
+  return guarded(h, [&]() -> int {
+    Amg &A = h->amg[0];
+    if (f_grid) CK(cudaMemcpyAsync(A.f, f_grid, sizeof(double) * A.n * A.nD, cudaMemcpyHostToDevice, h->stream));
+    if (g_grid) {
+      CK(cudaMemcpyAsync(A.z, g_grid, sizeof(double) * A.n * A.nu, cudaMemcpyHostToDevice, h->stream));
+      CK(cudaMemcpyAsync(A.zinit, g_grid, sizeof(double) * A.n * A.nu, cudaMemcpyHostToDevice, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return MGBX_OK;
+  });
+}
+
+int64_t mgbx_launch_count(const mgbx_handle *h) { return h ? h->launches : 0; }
+
+int64_t mgbx_level_size(mgbx_handle *h, int which, int level) {
+  if (!h || which < 0 || which > 1 || level < 0 || level >= h->amg[which].L) return -1;
+  return h->amg[which].m[level];
+}
+
+int mgbx_barrier_eval(mgbx_handle *h, int which, int level, double t, const double *s, int order, double *out) {
+  if (!h || !s || !out) return MGBX_ERR_ARG;
+  return guarded(h, [&]() -> int {
+    if (which < 0 || which > 1 || (which == 1 && !h->has_feas)) throw ArgError("no such AMG");
+    Amg &A = h->amg[which];
+    if (level < 0 || level >= A.L) throw ArgError("no such level");
+    if (order != 0 && order != 1) throw ArgError("order must be 0 or 1 (use mgbx_hessian_values for f2)");
+    Engine E(h);
+    CK(cudaMemcpyAsync(A.xn, s, sizeof(double) * A.m[level], cudaMemcpyHostToDevice, h->stream));
+    EvalOut e = E.eval_f01(A, level, t, A.z, A.xn, A.gn);
+    if (order == 0) out[0] = e.y;
+    else {
+      CK(cudaMemcpyAsync(out, A.gn, sizeof(double) * A.m[level], cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+    }
+    return MGBX_OK;
+  });
+}
+
+int mgbx_hessian_pattern(mgbx_handle *h, int which, int level, int64_t *nnz, int64_t *rowptr, int64_t *colind) {
+  if (!h || !nnz) return MGBX_ERR_ARG;
+  return guarded(h, [&]() -> int {
+    if (which < 0 || which > 1 || (which == 1 && !h->has_feas)) throw ArgError("no such AMG");
+    Amg &A = h->amg[which];
+    if (level < 0 || level >= A.L) throw ArgError("no such level");
+    if (!A.sys_full) A.sys_full = build_system(h, A, false);
+    SysLevel &Lv = A.sys_full->lev[A.L - 1 - level];
+    *nnz = Lv.A.nnz;
+    if (rowptr) CK(cudaMemcpy(rowptr, Lv.A.ptr, sizeof(int64_t) * (Lv.m + 1), cudaMemcpyDeviceToHost));
+    if (colind) {
+      std::vector<int32_t> tmp(Lv.A.nnz);
+      CK(cudaMemcpy(tmp.data(), Lv.A.idx, sizeof(int32_t) * Lv.A.nnz, cudaMemcpyDeviceToHost));
+      for (int64_t k = 0; k < Lv.A.nnz; ++k) colind[k] = tmp[k];
+    }
+    return MGBX_OK;
+  });
+}
+
+int mgbx_hessian_values(mgbx_handle *h, int which, int level, double t, const double *s, double *val) {
+  if (!h || !s || !val) return MGBX_ERR_ARG;
+  return guarded(h, [&]() -> int {
+    if (which < 0 || which > 1 || (which == 1 && !h->has_feas)) throw ArgError("no such AMG");
+    Amg &A = h->amg[which];
+    if (level < 0 || level >= A.L) throw ArgError("no such level");
+    Engine E(h);
+    if (!A.sys_full) A.sys_full = build_system(h, A, false);
+    System &S = *A.sys_full;
+    CK(cudaMemcpyAsync(A.xn, s, sizeof(double) * A.m[level], cudaMemcpyHostToDevice, h->stream));
+    {
+      E.prolong_to_fine(A, level, A.xn, A.z, A.zf);
+      NodeParams P = E.node_params(A, t);
+      P.nK = S.nK;
+      P.nE = 0;
+      for (int j = 0; j < MGBX_MAX_ND; ++j) {
+        P.Krow[j] = S.Krow[j];
+        P.Erow[j] = -1;
+      }
+      P.Hn = A.Hn;
+      k_node<NODE_F2><<<E.red_grid(A.n), kRedThreads, 0, h->stream>>>(P);
+      E.check_launch();
+      ElemParams EP = E.elem_params(A);
+      k_blockhess<<<nblk(S.hblk_size), 256, 0, h->stream>>>(EP, S.pl, A.Hn, S.Hblk);
+      E.check_launch();
+      k_csr_gather<<<nblk(S.lev[0].A.nnz), 256, 0, h->stream>>>(S.lev[0].A.nnz, S.gptr, S.gidx, S.gw, S.Hblk, S.lev[0].A.val);
+      E.check_launch();
+      const int ktop = A.L - 1 - level;
+      for (int k = 0; k < ktop; ++k) {
+        SysLevel &Lv = S.lev[k];
+        SysLevel &Lc = S.lev[k + 1];
+        k_spgemm_numeric<<<nblk(Lv.AT.rows), 256, 0, h->stream>>>(Lv.A, Lv.T, Lv.AT);
+        E.check_launch();
+        k_spgemm_numeric<<<nblk(Lc.A.rows), 256, 0, h->stream>>>(Lv.Tt, Lv.AT, Lc.A);
+        E.check_launch();
+      }
+      SysLevel &Lv = S.lev[ktop];
+      CK(cudaMemcpyAsync(val, Lv.A.val, sizeof(double) * Lv.A.nnz, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+    }
+    return MGBX_OK;
+  });
+}
+
+int mgbx_solve_newton_system(mgbx_handle *h, int which, int level, double t, const double *s, const double *rhs, double *x,
+                             int32_t *pcg_iters) {
+  if (!h || !s || !rhs || !x) return MGBX_ERR_ARG;
+  return guarded(h, [&]() -> int {
+    if (which < 0 || which > 1 || (which == 1 && !h->has_feas)) throw ArgError("no such AMG");
+    Amg &A = h->amg[which];
+    if (level < 0 || level >= A.L) throw ArgError("no such level");
+    Engine E(h);
+    System &S = E.system_for(A, level);
+    const int64_t m = A.m[level];
+    CK(cudaMemcpyAsync(A.xn, s, sizeof(double) * m, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(A.gn, rhs, sizeof(double) * m, cudaMemcpyHostToDevice, h->stream));
+    E.assemble(A, S, level, t, A.z, A.xn);
+    const int it = E.solve(A, S, level, A.gn, A.dir);
+    if (pcg_iters) *pcg_iters = it;
+    CK(cudaMemcpyAsync(x, A.dir, sizeof(double) * m, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MGBX_OK;
+  });
+}
+
+int mgbx_plan_pattern(const mgbx_csr *R, int64_t N, int32_t p, int32_t nu, int32_t nD, const int32_t *D_var, int64_t *nnz,
+                      int64_t *rowptr, int64_t *colind) {
+  if (!R || !nnz || !D_var) return MGBX_ERR_ARG;
+  return guarded(nullptr, [&]() -> int {
+    const int64_t n = N * (int64_t)p;
+    if (R->rows != (int64_t)nu * n) throw ArgError("mgbx_plan_pattern: R must have nu*p*N rows");
+    HostCsr H = csr_from_abi(*R, false);
+    std::vector<int> used;
+    for (int v = 0; v < nu; ++v) {
+      bool any = false;
+      for (int j = 0; j < nD; ++j) any = any || (D_var[j] == v);
+      if (any) used.push_back(v);
+    }
+    std::vector<int64_t> colmap(R->cols);
+    std::iota(colmap.begin(), colmap.end(), (int64_t)0);
+    HostCsr pat = plan_pattern(element_incidence(H, N, p, used, n, colmap, R->cols));
+    *nnz = pat.nnz();
+    if (rowptr) std::copy(pat.ptr.begin(), pat.ptr.end(), rowptr);
+    if (colind)
+      for (int64_t k = 0; k < pat.nnz(); ++k) colind[k] = pat.idx[k];
+    return MGBX_OK;
+  });
+}
+
+}  // extern "C"

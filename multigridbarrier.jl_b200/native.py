@@ -1,0 +1,396 @@
+"""ctypes binding of the C ABI in include/mgbx.h (the same entry points a Julia `ccall` shim binds).
+
+Only data marshalling lives here: numpy (C-order, 0-based) -> the column-major / int64 layouts of
+the ABI.  There is no compute and no fallback: if libmgbx.so is missing or no CUDA device is
+present the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional
+
+import numpy as np
+import scipy.sparse as sp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIBPATH = os.path.join(HERE, "libmgbx.so")
+
+MAX_LEVELS, MAX_ND = 32, 12
+OK, NOT_CONVERGED, NON_FINITE = 0, 1, 2
+ERR_ARG, ERR_CUDA, ERR_ALLOC, ERR_UNSUPPORTED, ERR_INTERNAL = -1, -2, -3, -4, -5
+MAIN, FEAS = 0, 1
+
+c_i64p = C.POINTER(C.c_int64)
+c_i32p = C.POINTER(C.c_int32)
+c_f64p = C.POINTER(C.c_double)
+
+
+class Csr(C.Structure):
+    _fields_ = [("rows", C.c_int64), ("cols", C.c_int64), ("rowptr", c_i64p), ("colind", c_i64p),
+                ("val", c_f64p)]
+
+
+class Piece(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("ni", C.c_int32), ("nc", C.c_int32), ("idx", c_i32p),
+                ("A", c_f64p), ("b", c_f64p), ("p", c_f64p), ("mu", c_f64p)]
+
+
+class Convex(C.Structure):
+    _fields_ = [("npieces", C.c_int32), ("pieces", C.POINTER(Piece)), ("select", c_f64p)]
+
+
+class Amg(C.Structure):
+    _fields_ = [("n", C.c_int64), ("N", C.c_int64), ("p", C.c_int32), ("nu", C.c_int32),
+                ("nD", C.c_int32), ("L", C.c_int32), ("w", c_f64p), ("nops", C.c_int32),
+                ("op_data", C.POINTER(c_f64p)), ("D_var", c_i32p), ("D_op", c_i32p),
+                ("R_fine", C.POINTER(Csr)), ("T", C.POINTER(Csr)), ("var_offsets", c_i64p)]
+
+
+class Problem(C.Structure):
+    _fields_ = [("amg", Amg * 2), ("f_grid", c_f64p), ("g_grid", c_f64p), ("Q", Convex),
+                ("barrier_weights", c_f64p)]
+
+
+class Config(C.Structure):
+    _fields_ = [("dense_direct_max", C.c_int32), ("coarse_max", C.c_int32), ("pcg_maxit", C.c_int32),
+                ("pcg_rtol", C.c_double), ("smoother_sweeps", C.c_int32), ("condense", C.c_int32),
+                ("device", C.c_int32), ("verbose", C.c_int32)]
+
+
+class StepOpts(C.Structure):
+    _fields_ = [("maxit", C.c_int32), ("max_newton", C.c_int32), ("initial_step", C.c_int32),
+                ("stop_kind", C.c_int32), ("stop_lambda_tol", C.c_double), ("stop_theta", C.c_double),
+                ("finalize", C.c_int32), ("finalize_theta", C.c_double), ("line_search", C.c_int32),
+                ("ls_beta", C.c_double), ("ls_c1", C.c_double)]
+
+
+class StepResult(C.Structure):
+    _fields_ = [("converged", C.c_int32), ("its", C.c_int32 * MAX_LEVELS), ("y", C.c_double),
+                ("gnorm", C.c_double), ("inc", C.c_double), ("f01_evals", C.c_int32),
+                ("f2_evals", C.c_int32), ("linear_solves", C.c_int32), ("pcg_iters", C.c_int32),
+                ("ms_f01", C.c_double), ("ms_f2", C.c_double), ("ms_solve", C.c_double)]
+
+
+class ScalarsOut(C.Structure):
+    _fields_ = [("c_dot_Dz", C.c_double), ("var_max", C.c_double * MAX_ND),
+                ("var_absmax", C.c_double * MAX_ND), ("all_finite", C.c_int32)]
+
+
+EXPORTS = [
+    "mgbx_default_config", "mgbx_default_step_opts", "mgbx_abi_version", "mgbx_device_count",
+    "mgbx_create", "mgbx_destroy", "mgbx_last_error", "mgbx_step", "mgbx_scalars",
+    "mgbx_phase1_init", "mgbx_set_feasibility_box", "mgbx_reset_feasibility_state", "mgbx_handoff",
+    "mgbx_matched_t", "mgbx_get_z", "mgbx_set_z", "mgbx_set_grids", "mgbx_level_size",
+    "mgbx_barrier_eval", "mgbx_hessian_pattern", "mgbx_hessian_values", "mgbx_solve_newton_system",
+    "mgbx_plan_pattern", "mgbx_launch_count",
+]
+
+_lib = None
+
+
+class MgbxError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libmgbx error %d: %s" % (code, msg))
+        self.code = code
+
+
+def lib():
+    """Load libmgbx.so (built in-tree by build.py).  Raises if it is missing: there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIBPATH):
+        raise ImportError("libmgbx.so has not been built: run `python -m mgbx.build` or "
+                          "__graft_entry__.build() (nvcc, sm_100a). There is no CPU fallback.")
+    L = C.CDLL(LIBPATH)
+    H = C.c_void_p
+    L.mgbx_default_config.argtypes = [C.POINTER(Config)]
+    L.mgbx_default_config.restype = None
+    L.mgbx_default_step_opts.argtypes = [C.POINTER(StepOpts), C.c_int64]
+    L.mgbx_default_step_opts.restype = None
+    L.mgbx_abi_version.restype = C.c_int
+    L.mgbx_device_count.restype = C.c_int
+    L.mgbx_create.argtypes = [C.POINTER(Problem), C.POINTER(Config), C.POINTER(H)]
+    L.mgbx_destroy.argtypes = [H]
+    L.mgbx_destroy.restype = None
+    L.mgbx_last_error.argtypes = [H]
+    L.mgbx_last_error.restype = C.c_char_p
+    L.mgbx_step.argtypes = [H, C.c_int, C.c_double, C.POINTER(StepOpts), C.POINTER(StepResult)]
+    L.mgbx_scalars.argtypes = [H, C.c_int, C.POINTER(ScalarsOut)]
+    L.mgbx_phase1_init.argtypes = [H, c_i32p, c_f64p, c_f64p]
+    L.mgbx_set_feasibility_box.argtypes = [H, C.c_double, C.c_double]
+    L.mgbx_reset_feasibility_state.argtypes = [H]
+    L.mgbx_handoff.argtypes = [H]
+    L.mgbx_matched_t.argtypes = [H, C.c_double, c_f64p, c_f64p]
+    L.mgbx_get_z.argtypes = [H, C.c_int, c_f64p]
+    L.mgbx_set_z.argtypes = [H, C.c_int, c_f64p]
+    L.mgbx_set_grids.argtypes = [H, c_f64p, c_f64p]
+    L.mgbx_level_size.argtypes = [H, C.c_int, C.c_int]
+    L.mgbx_level_size.restype = C.c_int64
+    L.mgbx_barrier_eval.argtypes = [H, C.c_int, C.c_int, C.c_double, c_f64p, C.c_int, c_f64p]
+    L.mgbx_hessian_pattern.argtypes = [H, C.c_int, C.c_int, c_i64p, c_i64p, c_i64p]
+    L.mgbx_hessian_values.argtypes = [H, C.c_int, C.c_int, C.c_double, c_f64p, c_f64p]
+    L.mgbx_solve_newton_system.argtypes = [H, C.c_int, C.c_int, C.c_double, c_f64p, c_f64p, c_f64p, c_i32p]
+    L.mgbx_plan_pattern.argtypes = [C.POINTER(Csr), C.c_int64, C.c_int32, C.c_int32, C.c_int32, c_i32p,
+                                    c_i64p, c_i64p, c_i64p]
+    L.mgbx_launch_count.argtypes = [H]
+    L.mgbx_launch_count.restype = C.c_int64
+    _lib = L
+    return L
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a, t=c_f64p):
+    return a.ctypes.data_as(t)
+
+
+class _Keep:
+    """Owns the numpy buffers a ctypes struct points into."""
+
+    def __init__(self):
+        self.bufs = []
+
+    def f64(self, a):
+        a = _f64(a)
+        self.bufs.append(a)
+        return _ptr(a)
+
+    def colmajor(self, a):
+        """(n, k) C-order grid -> column-major buffer (k contiguous columns of length n)."""
+        a = np.asarray(a, dtype=np.float64)
+        if a.ndim == 1:
+            return self.f64(a)
+        b = np.ascontiguousarray(a.T)
+        self.bufs.append(b)
+        return _ptr(b)
+
+    def i64(self, a):
+        a = np.ascontiguousarray(a, dtype=np.int64)
+        self.bufs.append(a)
+        return _ptr(a, c_i64p)
+
+    def i32(self, a):
+        a = np.ascontiguousarray(a, dtype=np.int32)
+        self.bufs.append(a)
+        return _ptr(a, c_i32p)
+
+    def csr(self, M) -> Csr:
+        M = sp.csr_matrix(M)
+        M.sum_duplicates()
+        M.sort_indices()
+        return Csr(M.shape[0], M.shape[1], self.i64(M.indptr), self.i64(M.indices), self.f64(M.data))
+
+
+def _pack_amg(keep: _Keep, M) -> Amg:
+    geom = M.geometry
+    n, N, p = geom.n, geom.N, geom.V
+    names, D_var, D_op = [], [], []
+    for (var, op) in M.D:
+        blocks = geom.operators[op]
+        ident = bool(np.array_equal(blocks, np.broadcast_to(np.eye(p), blocks.shape)))
+        if ident:
+            oid = -1
+        else:
+            if op not in names:
+                names.append(op)
+            oid = names.index(op)
+        D_var.append(var)
+        D_op.append(oid)
+    ops = (c_f64p * max(1, len(names)))()
+    for k, nm in enumerate(names):
+        # numpy ops[e, r, c]  ->  BlockDiag.data[r, c, e] column-major == memory order [e][c][r]
+        ops[k] = keep.f64(np.ascontiguousarray(geom.operators[nm].transpose(0, 2, 1)))
+    keep.bufs.append(ops)
+    L = len(M.R_fine)
+    Rs = (Csr * L)(*[keep.csr(R) for R in M.R_fine])
+    Ts = (Csr * max(1, L - 1))(*[keep.csr(T) for T in M.T])
+    keep.bufs += [Rs, Ts]
+    voff = np.asarray(M.var_offsets, dtype=np.int64).reshape(L, M.nu + 1)
+    return Amg(n, N, p, M.nu, M.nD, L, keep.f64(M.w), len(names),
+               C.cast(ops, C.POINTER(c_f64p)), keep.i32(D_var), keep.i32(D_op),
+               C.cast(Rs, C.POINTER(Csr)), C.cast(Ts, C.POINTER(Csr)), keep.i64(voff))
+
+
+def _pack_convex(keep: _Keep, Q, n) -> Convex:
+    K = len(Q.pieces)
+    arr = (Piece * K)()
+    for k, pc in enumerate(Q.pieces):
+        arr[k].kind = pc.kind
+        arr[k].ni = pc.ni
+        arr[k].nc = pc.nc
+        arr[k].idx = keep.i32(pc.idx) if pc.idx is not None else None
+        arr[k].A = keep.colmajor(pc.A)
+        arr[k].b = keep.colmajor(pc.b)
+        arr[k].p = keep.f64(pc.p) if pc.p is not None else None
+        arr[k].mu = keep.f64(pc.mu) if pc.mu is not None else None
+    keep.bufs.append(arr)
+    sel = keep.colmajor(Q.select) if Q.select is not None else None
+    return Convex(K, C.cast(arr, C.POINTER(Piece)), sel)
+
+
+def default_config(**kw) -> Config:
+    cfg = Config()
+    lib().mgbx_default_config(C.byref(cfg))
+    for k, v in kw.items():
+        if not hasattr(cfg, k):
+            raise TypeError("unknown mgbx_config field %r" % k)
+        setattr(cfg, k, v)
+    return cfg
+
+
+class Handle:
+    """Device-resident problem (the result of native_to_device in the reference)."""
+
+    def __init__(self, prob, barrier_weights=None, with_feasibility=True, **cfg):
+        L = lib()
+        keep = _Keep()
+        P = Problem()
+        P.amg[0] = _pack_amg(keep, prob.M[0])
+        if with_feasibility and prob.M[1] is not None:
+            P.amg[1] = _pack_amg(keep, prob.M[1])
+        n = prob.M[0].geometry.n
+        P.f_grid = keep.colmajor(prob.f)
+        P.g_grid = keep.colmajor(prob.g)
+        P.Q = _pack_convex(keep, prob.Q, n)
+        P.barrier_weights = keep.f64(barrier_weights) if barrier_weights is not None else None
+        self.cfg = default_config(**cfg)
+        self._h = C.c_void_p()
+        rc = L.mgbx_create(C.byref(P), C.byref(self.cfg), C.byref(self._h))
+        if rc != OK:
+            raise MgbxError(rc, (L.mgbx_last_error(None) or b"").decode())
+        self.n = n
+        self.nu = [prob.M[0].nu, prob.M[1].nu if prob.M[1] is not None else 0]
+        self.nD = [prob.M[0].nD, prob.M[1].nD if prob.M[1] is not None else 0]
+        self.L = [len(prob.M[0].R_fine), len(prob.M[1].R_fine) if prob.M[1] is not None else 0]
+
+    def _check(self, rc, allow=()):
+        if rc < 0 or (rc > 0 and rc not in allow):
+            raise MgbxError(rc, (lib().mgbx_last_error(self._h) or b"").decode())
+        return rc
+
+    def close(self):
+        if self._h:
+            lib().mgbx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- hot path
+    def step_opts(self, **kw) -> StepOpts:
+        o = StepOpts()
+        lib().mgbx_default_step_opts(C.byref(o), self.n)
+        for k, v in kw.items():
+            setattr(o, k, v)
+        return o
+
+    def step(self, which, t, opts: StepOpts):
+        r = StepResult()
+        rc = self._check(lib().mgbx_step(self._h, which, float(t), C.byref(opts), C.byref(r)),
+                         allow=(NOT_CONVERGED, NON_FINITE))
+        return rc, r
+
+    def scalars(self, which=MAIN) -> ScalarsOut:
+        out = ScalarsOut()
+        self._check(lib().mgbx_scalars(self._h, which, C.byref(out)))
+        return out
+
+    # ---- phase I
+    def phase1_init(self):
+        need, b, zmax = C.c_int32(), C.c_double(), C.c_double()
+        self._check(lib().mgbx_phase1_init(self._h, C.byref(need), C.byref(b), C.byref(zmax)))
+        return bool(need.value), b.value, zmax.value
+
+    def set_feasibility_box(self, b, R):
+        self._check(lib().mgbx_set_feasibility_box(self._h, float(b), float(R)))
+
+    def reset_feasibility_state(self):
+        self._check(lib().mgbx_reset_feasibility_state(self._h))
+
+    def handoff(self):
+        self._check(lib().mgbx_handoff(self._h))
+
+    def matched_t(self, t_default):
+        t, ts = C.c_double(), C.c_double()
+        self._check(lib().mgbx_matched_t(self._h, float(t_default), C.byref(t), C.byref(ts)))
+        return t.value, ts.value
+
+    # ---- state
+    def get_z(self, which=MAIN):
+        z = np.empty(self.nu[which] * self.n)
+        self._check(lib().mgbx_get_z(self._h, which, _ptr(z)))
+        return z
+
+    def set_z(self, z, which=MAIN):
+        z = _f64(z).reshape(-1)
+        assert z.size == self.nu[which] * self.n
+        self._check(lib().mgbx_set_z(self._h, which, _ptr(z)))
+
+    def set_grids(self, f_grid=None, g_grid=None):
+        keep = _Keep()
+        self._check(lib().mgbx_set_grids(self._h, keep.colmajor(f_grid) if f_grid is not None else None,
+                                         keep.colmajor(g_grid) if g_grid is not None else None))
+
+    def launch_count(self):
+        return int(lib().mgbx_launch_count(self._h))
+
+    # ---- parity hooks
+    def level_size(self, which, level):
+        return int(lib().mgbx_level_size(self._h, which, level))
+
+    def barrier_eval(self, which, level, t, s, order):
+        s = _f64(s)
+        out = np.empty(1 if order == 0 else s.size)
+        self._check(lib().mgbx_barrier_eval(self._h, which, level, float(t), _ptr(s), order, _ptr(out)))
+        return float(out[0]) if order == 0 else out
+
+    def hessian_pattern(self, which, level):
+        nnz = C.c_int64()
+        self._check(lib().mgbx_hessian_pattern(self._h, which, level, C.byref(nnz), None, None))
+        m = self.level_size(which, level)
+        ptr = np.empty(m + 1, np.int64)
+        ind = np.empty(nnz.value, np.int64)
+        self._check(lib().mgbx_hessian_pattern(self._h, which, level, C.byref(nnz), _ptr(ptr, c_i64p),
+                                               _ptr(ind, c_i64p)))
+        return ptr, ind
+
+    def hessian(self, which, level, t, s):
+        ptr, ind = self.hessian_pattern(which, level)
+        s = _f64(s)
+        val = np.empty(ind.size)
+        self._check(lib().mgbx_hessian_values(self._h, which, level, float(t), _ptr(s), _ptr(val)))
+        m = ptr.size - 1
+        return sp.csr_matrix((val, ind, ptr), shape=(m, m))
+
+    def solve_newton_system(self, which, level, t, s, rhs):
+        s, rhs = _f64(s), _f64(rhs)
+        x = np.empty_like(rhs)
+        it = C.c_int32()
+        self._check(lib().mgbx_solve_newton_system(self._h, which, level, float(t), _ptr(s), _ptr(rhs),
+                                                   _ptr(x), C.byref(it)))
+        return x, it.value
+
+
+def plan_pattern(R, N, p, nu, D_var):
+    """Host-only: reference assembly-plan pattern of R'HR (no GPU needed)."""
+    keep = _Keep()
+    Rc = keep.csr(R)
+    nnz = C.c_int64()
+    dv = np.ascontiguousarray(D_var, dtype=np.int32)
+    rc = lib().mgbx_plan_pattern(C.byref(Rc), N, p, nu, len(dv), _ptr(dv, c_i32p), C.byref(nnz), None, None)
+    if rc != OK:
+        raise MgbxError(rc, (lib().mgbx_last_error(None) or b"").decode())
+    ptr = np.empty(R.shape[1] + 1, np.int64)
+    ind = np.empty(nnz.value, np.int64)
+    rc = lib().mgbx_plan_pattern(C.byref(Rc), N, p, nu, len(dv), _ptr(dv, c_i32p), C.byref(nnz),
+                                 _ptr(ptr, c_i64p), _ptr(ind, c_i64p))
+    if rc != OK:
+        raise MgbxError(rc, (lib().mgbx_last_error(None) or b"").decode())
+    return ptr, ind

@@ -1,0 +1,72 @@
+"""CPU-side checks of the C-ABI library: it loads, exports every symbol include/mgbx.h declares, fails
+loudly without a GPU, and its host-only assembly-plan pattern is bit-exact with the oracle's restatement
+of src/BlockMatrices.jl:344-446."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import mgb_oracle as O
+from helpers import GEOMS, default_problem
+from mgbx import native
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "mgbx.h")).read()
+    declared = set(re.findall(r"\b(mgbx_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no prototypes found"
+    L = native.lib()
+    for name in sorted(declared):
+        assert hasattr(L, name), name
+    assert set(native.EXPORTS) == declared
+    assert L.mgbx_abi_version() == 1
+
+
+def test_struct_sizes_match_header():
+    cfg = native.default_config()
+    assert cfg.dense_direct_max == 2048 and cfg.condense == 1
+    o = native.StepOpts()
+    native.lib().mgbx_default_step_opts(C.byref(o), 100)
+    assert o.max_newton == 8 and o.maxit == 10000 and abs(o.stop_lambda_tol - 0.025) < 1e-15
+    assert o.ls_beta == 0.5 and o.ls_c1 == 0.1 and o.finalize_theta == 0.9
+
+
+@pytest.mark.parametrize("geom", ["fem1d_5nodes", "fem2d_P2_quickstart", "fem2d_P1_L2", "fem2d_P2_L2", "fem3d_k1_L2"])
+def test_plan_pattern_bit_exact(geom):
+    prob = default_problem(geom, 1.0)
+    for M in prob.M:
+        g = M.geometry
+        D_var = [v for (v, _) in M.D]
+        for J in range(len(M.R_fine)):
+            ptr, ind = native.plan_pattern(sp.csr_matrix(M.R_fine[J]), g.N, g.V, M.nu, D_var)
+            optr, oind = O.hessian_pattern(M, J)
+            assert np.array_equal(ptr, optr) and np.array_equal(ind, oind)
+
+
+def test_no_gpu_is_a_loud_error():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    prob = default_problem("fem1d_3nodes", 1.0)
+    with pytest.raises(native.MgbxError) as e:
+        native.Handle(prob)
+    assert e.value.code == native.ERR_CUDA
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_bad_arguments_are_reported():
+    # column index out of range in R
+    R = sp.csr_matrix(np.eye(4))
+    keep = native._Keep()
+    Rc = keep.csr(R)
+    Rc.cols = 2
+    nnz = C.c_int64()
+    dv = np.zeros(1, np.int32)
+    rc = native.lib().mgbx_plan_pattern(C.byref(Rc), 2, 2, 1, 1, native._ptr(dv, native.c_i32p), C.byref(nnz), None, None)
+    assert rc == native.ERR_ARG
+    assert b"out of range" in native.lib().mgbx_last_error(None)
