@@ -857,10 +857,10 @@ Engine::NewtonOut Engine::newton(Amg &A, int J, double t, int maxit, int stop_ki
     double yn = y, gnn = gnorm;
     bool have_trial = false;   // xbest/gbest hold the last finite trial
     while (sstep > 0.0) {
-      k_trial<<<red_grid(m), kRedThreads, 0, s>>>(m, A.x, A.dir, sstep, A.xn, h->partials, h->ticket, h->dscal + 3);
+      k_trial<<<red_grid(m), kRedThreads, 0, s>>>(m, A.x, A.dir, sstep, A.xn, h->partials, h->ticket, h->dscal + 7);
       check_launch();
       EvalOut et = eval_f01(A, J, t, A.z, A.xn, A.gn);
-      const bool stalled = (h->hscal[3] == 0.0);
+      const bool stalled = (h->hscal[7] == 0.0);
       if (et.finite) {
         std::swap(A.xn, A.xbest);
         std::swap(A.gn, A.gbest);
