@@ -121,6 +121,7 @@ typedef struct {
   int32_t condense;          /* 1 (default): eliminate node-local :full variables exactly before PCG */
   int32_t device;            /* CUDA device ordinal, -1 = current */
   int32_t verbose;
+  int32_t profile;           /* 1: time every kernel launch with CUDA events on the handle's stream (mgbx_kernel_stats) */
 } mgbx_config;
 
 /* options of one mgb_step (src/mgb.jl:16-30; defaults src/mgb.jl:360-363) */
@@ -195,6 +196,11 @@ int mgbx_solve_newton_system(mgbx_handle *h, int which, int level, double t, con
 
 /* number of kernels launched through this handle so far (bench.py's gpu_launches) */
 int64_t mgbx_launch_count(const mgbx_handle *h);
+
+/* per-kernel-class launch counts and (with profile on) summed device time in ms; names[k] are static strings.
+ * Arrays must hold at least 16 entries. */
+int mgbx_kernel_stats(mgbx_handle *h, int reset, int32_t *nclasses, const char **names, int64_t *launches, double *ms);
+int mgbx_set_profile(mgbx_handle *h, int on);
 
 /* host-only (no GPU needed): the reference assembly plan's output pattern for R'HR
  * (src/BlockMatrices.jl:344-446) from R (CSR, rows = nu blocks of N elements x p nodes). */

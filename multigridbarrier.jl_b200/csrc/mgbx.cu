@@ -36,6 +36,24 @@ using namespace mgbx;
 
 static thread_local std::string g_last_error;
 
+// kernel classes for the optional per-class device timing (cfg.profile) and launch statistics
+enum KClass { KC_NODE_F01 = 0, KC_NODE_F2, KC_BLOCKGRAD, KC_BLOCKHESS, KC_GATHER, KC_SPMV, KC_JACOBI, KC_SPGEMM, KC_VEC, KC_COND,
+              KC_DENSE, KC_COUNT };
+static const char *kKClassNames[KC_COUNT] = {"node_f01", "node_f2", "blockgrad", "blockhess", "csr_gather", "spmv", "jacobi",
+                                             "spgemm", "vector", "condense", "dense"};
+#define LAUNCH(kc, ...)   \
+  do {                    \
+    pre_launch(kc);       \
+    __VA_ARGS__;          \
+    post_launch(kc);      \
+  } while (0)
+#define E_LAUNCH(kc, ...) \
+  do {                    \
+    E.pre_launch(kc);     \
+    __VA_ARGS__;          \
+    E.post_launch(kc);    \
+  } while (0)
+
 namespace {
 
 struct ArgError : std::runtime_error {
@@ -170,6 +188,16 @@ struct mgbx_handle {
   mgbx_step_result *res = nullptr;
   mgbx_step_result scratch_res;
   int64_t launches = 0;
+  // per-class statistics; device time only when cfg.profile != 0
+  int64_t kc_launches[KC_COUNT] = {0};
+  double kc_ms[KC_COUNT] = {0};
+  std::vector<cudaEvent_t> ev_free;
+  struct Pending {
+    int kc;
+    cudaEvent_t a, b;
+  };
+  std::vector<Pending> ev_pending;
+  cudaEvent_t ev_cur = nullptr;
 };
 
 namespace {
@@ -179,14 +207,48 @@ struct Engine {
   cudaStream_t s;
   explicit Engine(mgbx_handle *hh) : h(hh), s(hh->stream) {}
 
-  void sync() { CK(cudaStreamSynchronize(s)); }
+  void sync() {
+    CK(cudaStreamSynchronize(s));
+    if (!h->ev_pending.empty()) {
+      for (auto &p : h->ev_pending) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, p.a, p.b);
+        h->kc_ms[p.kc] += ms;
+        h->ev_free.push_back(p.a);
+        h->ev_free.push_back(p.b);
+      }
+      h->ev_pending.clear();
+    }
+  }
+  cudaEvent_t get_event() {
+    if (!h->ev_free.empty()) {
+      cudaEvent_t e = h->ev_free.back();
+      h->ev_free.pop_back();
+      return e;
+    }
+    cudaEvent_t e;
+    CK(cudaEventCreate(&e));
+    return e;
+  }
+  void pre_launch(int kc) {
+    if (h->cfg.profile) {
+      h->ev_cur = get_event();
+      cudaEventRecord(h->ev_cur, s);
+    }
+  }
+  void post_launch(int kc) {
+    h->launches++;
+    h->kc_launches[kc]++;
+    if (h->cfg.profile) {
+      cudaEvent_t b = get_event();
+      cudaEventRecord(b, s);
+      h->ev_pending.push_back({kc, h->ev_cur, b});
+    }
+    CK(cudaGetLastError());
+  }
   void fetch(int count) {
     CK(cudaMemcpyAsync(h->hscal, h->dscal, sizeof(double) * count, cudaMemcpyDeviceToHost, s));
     sync();
-  }
-  void check_launch() {
-    h->launches++;
-    CK(cudaGetLastError());
   }
 
   // ---------------------------------------------------------------- sparse helpers
@@ -199,15 +261,13 @@ struct Engine {
     if (G == 0) G = group_for(A);
     if (G == 32) k_spmv<32><<<nblk(A.rows * 32), 256, 0, s>>>(A, x, y0, alpha, y);
     else if (G == 4) k_spmv<4><<<nblk(A.rows * 4), 256, 0, s>>>(A, x, y0, alpha, y);
-    else k_spmv<1><<<nblk(A.rows), 256, 0, s>>>(A, x, y0, alpha, y);
-    check_launch();
+    else LAUNCH(KC_SPMV, k_spmv<1><<<nblk(A.rows), 256, 0, s>>>(A, x, y0, alpha, y));
   }
   void jacobi(const SysLevel &Lv, const double *b, const double *x, double *xnew) {
     const int G = Lv.spmv_group;
     if (G == 32) k_jacobi<32><<<nblk(Lv.m * 32), 256, 0, s>>>(Lv.A, Lv.dinv, b, x, xnew);
     else if (G == 4) k_jacobi<4><<<nblk(Lv.m * 4), 256, 0, s>>>(Lv.A, Lv.dinv, b, x, xnew);
-    else k_jacobi<1><<<nblk(Lv.m), 256, 0, s>>>(Lv.A, Lv.dinv, b, x, xnew);
-    check_launch();
+    else LAUNCH(KC_JACOBI, k_jacobi<1><<<nblk(Lv.m), 256, 0, s>>>(Lv.A, Lv.dinv, b, x, xnew));
   }
   void copy(double *dst, const double *src, int64_t m) {
     if (m) CK(cudaMemcpyAsync(dst, src, sizeof(double) * m, cudaMemcpyDeviceToDevice, s));
@@ -295,14 +355,11 @@ struct Engine {
     prolong_to_fine(A, J, x, zbase, A.zf);
     NodeParams P = node_params(A, t);
     if (!use_bw) P.bw = nullptr;
-    k_node<NODE_F01><<<red_grid(A.n), kRedThreads, 0, s>>>(P);
-    check_launch();
+    LAUNCH(KC_NODE_F01, k_node<NODE_F01><<<red_grid(A.n), kRedThreads, 0, s>>>(P));
     ElemParams E = elem_params(A);
-    k_blockgrad<<<nblk((int64_t)A.nu * A.n), 256, 0, s>>>(E, A.G, A.gb, A.nu);
-    check_launch();
+    LAUNCH(KC_BLOCKGRAD, k_blockgrad<<<nblk((int64_t)A.nu * A.n), 256, 0, s>>>(E, A.G, A.gb, A.nu));
     restrict_from_fine(A, J, A.gb, gout);
-    k_dot2<<<red_grid(A.m[J]), kRedThreads, 0, s>>>(A.m[J], gout, nullptr, h->partials, h->ticket, h->dscal + 4);
-    check_launch();
+    LAUNCH(KC_VEC, k_dot2<<<red_grid(A.m[J]), kRedThreads, 0, s>>>(A.m[J], gout, nullptr, h->partials, h->ticket, h->dscal + 4));
     cudaEventRecord(h->ev1, s);
     fetch(8);
     float ms = 0.f;
@@ -553,16 +610,13 @@ void Engine::assemble(Amg &A, System &S, int J, double t, const double *zbase, c
   P.Hn = A.Hn;
   P.hEEinv = A.hEEinv;
   P.hKE = A.hKE;
-  k_node<NODE_F2><<<red_grid(A.n), kRedThreads, 0, s>>>(P);
-  check_launch();
+  LAUNCH(KC_NODE_F2, k_node<NODE_F2><<<red_grid(A.n), kRedThreads, 0, s>>>(P));
   ElemParams E = elem_params(A);
   E.nK = S.nK;
   for (int j = 0; j < S.nK; ++j) E.Krow[j] = S.Krow[j];
-  k_blockhess<<<nblk(S.hblk_size), 256, 0, s>>>(E, S.pl, A.Hn, S.Hblk);
-  check_launch();
+  LAUNCH(KC_BLOCKHESS, k_blockhess<<<nblk(S.hblk_size), 256, 0, s>>>(E, S.pl, A.Hn, S.Hblk));
   SysLevel &top = S.lev[0];
-  k_csr_gather<<<nblk(top.A.nnz), 256, 0, s>>>(top.A.nnz, S.gptr, S.gidx, S.gw, S.Hblk, top.A.val);
-  check_launch();
+  LAUNCH(KC_GATHER, k_csr_gather<<<nblk(top.A.nnz), 256, 0, s>>>(top.A.nnz, S.gptr, S.gidx, S.gw, S.Hblk, top.A.val));
   const int ktop = A.L - 1 - J;
   setup_hierarchy(A, S, ktop);
   cudaEventRecord(h->ev1, s);
@@ -587,10 +641,8 @@ void Engine::setup_hierarchy(Amg &A, System &S, int ktop) {
     if (Lv.T_identity) {
       copy(Lc.A.val, Lv.A.val, Lv.A.nnz);
     } else {
-      k_spgemm_numeric<<<nblk(Lv.AT.rows), 256, 0, s>>>(Lv.A, Lv.T, Lv.AT);
-      check_launch();
-      k_spgemm_numeric<<<nblk(Lc.A.rows), 256, 0, s>>>(Lv.Tt, Lv.AT, Lc.A);
-      check_launch();
+      LAUNCH(KC_SPGEMM, k_spgemm_numeric<<<nblk(Lv.AT.rows), 256, 0, s>>>(Lv.A, Lv.T, Lv.AT));
+      LAUNCH(KC_SPGEMM, k_spgemm_numeric<<<nblk(Lc.A.rows), 256, 0, s>>>(Lv.Tt, Lv.AT, Lc.A));
     }
   }
   if (direct) {
@@ -599,8 +651,7 @@ void Engine::setup_hierarchy(Amg &A, System &S, int ktop) {
   }
   for (int k = ktop; k <= kend; ++k) {
     SysLevel &Lv = S.lev[k];
-    k_l1diag<<<nblk(Lv.m), 256, 0, s>>>(Lv.A, Lv.dinv, Lv.diag);
-    check_launch();
+    LAUNCH(KC_VEC, k_l1diag<<<nblk(Lv.m), 256, 0, s>>>(Lv.A, Lv.dinv, Lv.diag));
   }
   if (S.cut >= 0 && S.cut >= ktop) dense_factor(S, S.lev[S.cut], true);
 }
@@ -614,38 +665,29 @@ void Engine::dense_factor(System &S, SysLevel &Lv, bool want_inverse) {
   }
   if (want_inverse && !Lv.dense_inv) Lv.dense_inv = h->pool.alloc<double>((size_t)m * m);
   zero(Lv.dense, (int64_t)m * m);
-  k_dense_scale_diag<<<nblk(m), 256, 0, s>>>(Lv.A, Lv.dscale);
-  check_launch();
-  k_csr_to_dense<<<nblk(m), 256, 0, s>>>(Lv.A, Lv.dscale, Lv.dense);
-  check_launch();
+  LAUNCH(KC_DENSE, k_dense_scale_diag<<<nblk(m), 256, 0, s>>>(Lv.A, Lv.dscale));
+  LAUNCH(KC_DENSE, k_csr_to_dense<<<nblk(m), 256, 0, s>>>(Lv.A, Lv.dscale, Lv.dense));
   for (int k0 = 0; k0 < m; k0 += NB) {
-    k_chol_diag<<<1, 256, 0, s>>>(Lv.dense, m, k0);
-    check_launch();
+    LAUNCH(KC_DENSE, k_chol_diag<<<1, 256, 0, s>>>(Lv.dense, m, k0));
     const int nb = std::min(NB, m - k0);
     const int rem = m - k0 - nb;
     if (rem > 0) {
-      k_chol_trsm<<<nblk(rem, 64), 64, 0, s>>>(Lv.dense, m, k0);
-      check_launch();
+      LAUNCH(KC_DENSE, k_chol_trsm<<<nblk(rem, 64), 64, 0, s>>>(Lv.dense, m, k0));
       const int nt = (rem + NB - 1) / NB;
-      k_chol_syrk<<<nt * (nt + 1) / 2, 256, 0, s>>>(Lv.dense, m, k0);
-      check_launch();
+      LAUNCH(KC_DENSE, k_chol_syrk<<<nt * (nt + 1) / 2, 256, 0, s>>>(Lv.dense, m, k0));
     }
   }
   if (want_inverse) {
-    k_chol_solve<<<m, 256, sizeof(double) * m, s>>>(Lv.dense, m, Lv.dense_inv, 1);
-    check_launch();
+    LAUNCH(KC_DENSE, k_chol_solve<<<m, 256, sizeof(double) * m, s>>>(Lv.dense, m, Lv.dense_inv, 1));
   }
 }
 
 // x = A^{-1} b through the scaled Cholesky factor (one right-hand side), uses Lv.r as scratch
 void Engine::dense_apply(SysLevel &Lv, const double *b, double *x) {
   const int m = (int)Lv.m;
-  k_mul<<<nblk(m), 256, 0, s>>>(m, b, Lv.dscale, x);
-  check_launch();
-  k_chol_solve<<<1, 256, sizeof(double) * m, s>>>(Lv.dense, m, x, 0);
-  check_launch();
-  k_mul<<<nblk(m), 256, 0, s>>>(m, x, Lv.dscale, x);
-  check_launch();
+  LAUNCH(KC_VEC, k_mul<<<nblk(m), 256, 0, s>>>(m, b, Lv.dscale, x));
+  LAUNCH(KC_DENSE, k_chol_solve<<<1, 256, sizeof(double) * m, s>>>(Lv.dense, m, x, 0));
+  LAUNCH(KC_VEC, k_mul<<<nblk(m), 256, 0, s>>>(m, x, Lv.dscale, x));
 }
 
 void Engine::vcycle(System &S, int k) {
@@ -653,12 +695,9 @@ void Engine::vcycle(System &S, int k) {
   const int nlev = (int)S.lev.size();
   if (k == S.cut) {
     // x = D Minv D b
-    k_mul<<<nblk(Lv.m), 256, 0, s>>>(Lv.m, Lv.b, Lv.dscale, Lv.r);
-    check_launch();
-    k_dense_symv<<<nblk(Lv.m * 32), 256, 0, s>>>(Lv.dense_inv, (int)Lv.m, Lv.r, Lv.x2);
-    check_launch();
-    k_mul<<<nblk(Lv.m), 256, 0, s>>>(Lv.m, Lv.x2, Lv.dscale, Lv.x);
-    check_launch();
+    LAUNCH(KC_VEC, k_mul<<<nblk(Lv.m), 256, 0, s>>>(Lv.m, Lv.b, Lv.dscale, Lv.r));
+    LAUNCH(KC_DENSE, k_dense_symv<<<nblk(Lv.m * 32), 256, 0, s>>>(Lv.dense_inv, (int)Lv.m, Lv.r, Lv.x2));
+    LAUNCH(KC_VEC, k_mul<<<nblk(Lv.m), 256, 0, s>>>(Lv.m, Lv.x2, Lv.dscale, Lv.x));
     return;
   }
   const bool bottom = (k == nlev - 1);
@@ -700,8 +739,7 @@ int Engine::pcg(System &S, int ktop, const double *b, double *x) {
   const unsigned int rg = red_grid(m);
   zero(x, m);
   copy(r, b, m);
-  k_dot<<<rg, kRedThreads, 0, s>>>(m, r, r, h->partials, h->ticket, scal + 2);
-  check_launch();
+  LAUNCH(KC_VEC, k_dot<<<rg, kRedThreads, 0, s>>>(m, r, r, h->partials, h->ticket, scal + 2));
   CK(cudaMemcpyAsync(h->hscal + 8, scal, sizeof(double) * 5, cudaMemcpyDeviceToHost, s));
   sync();
   const double bb = h->hscal[10];
@@ -715,23 +753,17 @@ int Engine::pcg(System &S, int ktop, const double *b, double *x) {
     vcycle(S, ktop);
     const double *zz = Lv.x;
     if (it == 0) {
-      k_dot<<<rg, kRedThreads, 0, s>>>(m, r, zz, h->partials, h->ticket, scal + 0);
-      check_launch();
+      LAUNCH(KC_VEC, k_dot<<<rg, kRedThreads, 0, s>>>(m, r, zz, h->partials, h->ticket, scal + 0));
       copy(p, zz, m);
     } else {
-      k_dot<<<rg, kRedThreads, 0, s>>>(m, r, zz, h->partials, h->ticket, scal + 3);
-      check_launch();
-      k_pcg_beta<<<1, 1, 0, s>>>(scal);
-      check_launch();
-      k_pcg_dir<<<nblk(m), 256, 0, s>>>(m, scal, zz, p);
-      check_launch();
+      LAUNCH(KC_VEC, k_dot<<<rg, kRedThreads, 0, s>>>(m, r, zz, h->partials, h->ticket, scal + 3));
+      LAUNCH(KC_VEC, k_pcg_beta<<<1, 1, 0, s>>>(scal));
+      LAUNCH(KC_VEC, k_pcg_dir<<<nblk(m), 256, 0, s>>>(m, scal, zz, p));
     }
     (void)z;
     spmv(Lv.A, p, nullptr, 1.0, Ap, Lv.spmv_group);
-    k_dot<<<rg, kRedThreads, 0, s>>>(m, p, Ap, h->partials, h->ticket, scal + 1);
-    check_launch();
-    k_pcg_update<<<rg, kRedThreads, 0, s>>>(m, scal, p, Ap, x, r, h->partials, h->ticket);
-    check_launch();
+    LAUNCH(KC_VEC, k_dot<<<rg, kRedThreads, 0, s>>>(m, p, Ap, h->partials, h->ticket, scal + 1));
+    LAUNCH(KC_VEC, k_pcg_update<<<rg, kRedThreads, 0, s>>>(m, scal, p, Ap, x, r, h->partials, h->ticket));
     ++it;
     CK(cudaMemcpyAsync(h->hscal + 8, scal, sizeof(double) * 5, cudaMemcpyDeviceToHost, s));
     sync();
@@ -755,8 +787,7 @@ int Engine::solve_compact(System &S, int ktop, const double *b, double *x) {
     // one step of iterative refinement against the CSR operator
     spmv(Lv.A, x, b, -1.0, Lv.r, Lv.spmv_group);
     dense_apply(Lv, Lv.r, Lv.x2);
-    k_axpby<<<nblk(Lv.m), 256, 0, s>>>(Lv.m, 1.0, x, 1.0, Lv.x2, x);
-    check_launch();
+    LAUNCH(KC_VEC, k_axpby<<<nblk(Lv.m), 256, 0, s>>>(Lv.m, 1.0, x, 1.0, Lv.x2, x));
     return 0;
   }
   return pcg(S, ktop, b, x);
@@ -783,13 +814,11 @@ int Engine::solve(Amg &A, System &S, int J, const double *g, double *dir) {
     for (int e = 0; e < S.nE; ++e) C.Eoff[e] = A.voff[A.L - 1][S.elim[e]];
     C.hEEinv = A.hEEinv;
     C.hKE = A.hKE;
-    k_condense_rhs<<<nblk(A.n), 256, 0, s>>>(C, g, A.G);
-    check_launch();
+    LAUNCH(KC_COND, k_condense_rhs<<<nblk(A.n), 256, 0, s>>>(C, g, A.G));
     ElemParams E = elem_params(A);
     E.nK = S.nK;
     for (int j = 0; j < S.nK; ++j) E.Krow[j] = S.Krow[j];
-    k_blockgrad<<<nblk((int64_t)A.nu * A.n), 256, 0, s>>>(E, A.G, A.gb, A.nu);
-    check_launch();
+    LAUNCH(KC_BLOCKGRAD, k_blockgrad<<<nblk((int64_t)A.nu * A.n), 256, 0, s>>>(E, A.G, A.gb, A.nu));
     spmv(A.RLt, A.gb, g, 1.0, A.tmp);                 // tmp = g + R' gb   (entries of eliminated variables unused)
     for (size_t q = 0; q < S.kept.size(); ++q)
       copy(S.pc_b + Lv.off[q], A.tmp + A.voff[A.L - 1][S.kept[q]], Lv.off[q + 1] - Lv.off[q]);
@@ -801,13 +830,11 @@ int Engine::solve(Amg &A, System &S, int J, const double *g, double *dir) {
     spmv(A.RL, dir, nullptr, 1.0, A.gb);
     NodeParams NP = node_params(A, 0.0);
     NP.zf = A.gb;
-    k_backsubst<<<nblk(A.n), 256, 0, s>>>(C, NP, g, dir);
-    check_launch();
+    LAUNCH(KC_COND, k_backsubst<<<nblk(A.n), 256, 0, s>>>(C, NP, g, dir));
   }
   cudaEventRecord(h->ev1, s);
   // inc = g . dir, finiteness of dir
-  k_dot2<<<red_grid(A.m[J]), kRedThreads, 0, s>>>(A.m[J], dir, g, h->partials, h->ticket, h->dscal + 4);
-  check_launch();
+  LAUNCH(KC_VEC, k_dot2<<<red_grid(A.m[J]), kRedThreads, 0, s>>>(A.m[J], dir, g, h->partials, h->ticket, h->dscal + 4));
   fetch(8);
   float ms = 0.f;
   cudaEventElapsedTime(&ms, h->ev0, h->ev1);
@@ -857,8 +884,7 @@ Engine::NewtonOut Engine::newton(Amg &A, int J, double t, int maxit, int stop_ki
     double yn = y, gnn = gnorm;
     bool have_trial = false;   // xbest/gbest hold the last finite trial
     while (sstep > 0.0) {
-      k_trial<<<red_grid(m), kRedThreads, 0, s>>>(m, A.x, A.dir, sstep, A.xn, h->partials, h->ticket, h->dscal + 7);
-      check_launch();
+      LAUNCH(KC_VEC, k_trial<<<red_grid(m), kRedThreads, 0, s>>>(m, A.x, A.dir, sstep, A.xn, h->partials, h->ticket, h->dscal + 7));
       EvalOut et = eval_f01(A, J, t, A.z, A.xn, A.gn);
       const bool stalled = (h->hscal[7] == 0.0);
       if (et.finite) {
@@ -948,16 +974,13 @@ int Engine::matched_t(double t_default, double *t_out, double *tstar_out) {
   EvalOut e1 = eval_f01(A, J, 1.0, A.z, A.x, A.gn);       // gn = gphi + gc
   (void)e0;
   (void)e1;
-  k_axpby<<<nblk(m), 256, 0, s>>>(m, 1.0, A.gn, -1.0, A.g, A.gn);   // gn = gc
-  check_launch();
+  LAUNCH(KC_VEC, k_axpby<<<nblk(m), 256, 0, s>>>(m, 1.0, A.gn, -1.0, A.g, A.gn));   // gn = gc
   assemble(A, S, J, 1.0, A.z, A.x);
   solve(A, S, J, A.g, A.dir);      // nphi
   solve(A, S, J, A.gn, A.xn);      // nc
   const double d = h->hscal[4];    // gc . nc
-  k_dot<<<red_grid(m), kRedThreads, 0, s>>>(m, A.g, A.xn, h->partials, h->ticket, h->dscal + 0);
-  check_launch();
-  k_dot<<<red_grid(m), kRedThreads, 0, s>>>(m, A.gn, A.dir, h->partials, h->ticket, h->dscal + 1);
-  check_launch();
+  LAUNCH(KC_VEC, k_dot<<<red_grid(m), kRedThreads, 0, s>>>(m, A.g, A.xn, h->partials, h->ticket, h->dscal + 0));
+  LAUNCH(KC_VEC, k_dot<<<red_grid(m), kRedThreads, 0, s>>>(m, A.gn, A.dir, h->partials, h->ticket, h->dscal + 1));
   fetch(2);
   const double b = h->hscal[0] + h->hscal[1];
   *tstar_out = NAN;
@@ -1163,6 +1186,7 @@ void mgbx_default_config(mgbx_config *c) {
   c->condense = 1;
   c->device = -1;
   c->verbose = 0;
+  c->profile = 0;
 }
 
 void mgbx_default_step_opts(mgbx_step_opts *o, int64_t n) {
@@ -1261,6 +1285,11 @@ void mgbx_destroy(mgbx_handle *h) {
   if (h->hscal) cudaFreeHost(h->hscal);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  for (auto e : h->ev_free) cudaEventDestroy(e);
+  for (auto &p : h->ev_pending) {
+    cudaEventDestroy(p.a);
+    cudaEventDestroy(p.b);
+  }
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -1291,8 +1320,7 @@ int mgbx_scalars(mgbx_handle *h, int which, mgbx_scalars_out *out) {
     out->c_dot_Dz = e.lin;
     out->all_finite = 1;
     for (int v = 0; v < A.nu; ++v) {
-      k_maxabs<<<E.red_grid(A.n), kRedThreads, 0, h->stream>>>(A.n, A.z + (int64_t)v * A.n, h->partials, h->ticket, h->dscal);
-      E.check_launch();
+      E_LAUNCH(KC_VEC, k_maxabs<<<E.red_grid(A.n), kRedThreads, 0, h->stream>>>(A.n, A.z + (int64_t)v * A.n, h->partials, h->ticket, h->dscal));
       E.fetch(3);
       out->var_max[v] = h->hscal[0];
       out->var_absmax[v] = h->hscal[1];
@@ -1313,8 +1341,7 @@ int mgbx_phase1_init(mgbx_handle *h, int32_t *needs_phase1, double *b, double *z
     *needs_phase1 = (e.nonfinite_nodes > 0.0 || !std::isfinite(e.y)) ? 1 : 0;
     double zmax = 0.0;
     for (int v = 0; v < A.nu; ++v) {
-      k_maxabs<<<E.red_grid(A.n), kRedThreads, 0, h->stream>>>(A.n, A.z + (int64_t)v * A.n, h->partials, h->ticket, h->dscal);
-      E.check_launch();
+      E_LAUNCH(KC_VEC, k_maxabs<<<E.red_grid(A.n), kRedThreads, 0, h->stream>>>(A.n, A.z + (int64_t)v * A.n, h->partials, h->ticket, h->dscal));
       E.fetch(3);
       zmax = std::max(zmax, h->hscal[1]);
     }
@@ -1325,14 +1352,11 @@ int mgbx_phase1_init(mgbx_handle *h, int32_t *needs_phase1, double *b, double *z
       Amg &F = h->amg[1];
       // slack_i = 2*max(slack_fn(D z0), 1);  b = 2*max(1, max slack)   (src/mgb.jl:437-445)
       NodeParams P = E.node_params(A, 0.0);   // A.zf holds z0 from the probe
-      k_node<NODE_SLACK><<<E.red_grid(A.n), kRedThreads, 0, h->stream>>>(P);
-      E.check_launch();
-      k_phase1_slack<<<nblk(A.n), 256, 0, h->stream>>>(A.n, A.slack, F.zinit + (int64_t)A.nu * A.n);
-      E.check_launch();
+      E_LAUNCH(KC_NODE_F01, k_node<NODE_SLACK><<<E.red_grid(A.n), kRedThreads, 0, h->stream>>>(P));
+      E_LAUNCH(KC_VEC, k_phase1_slack<<<nblk(A.n), 256, 0, h->stream>>>(A.n, A.slack, F.zinit + (int64_t)A.nu * A.n));
       E.copy(F.zinit, A.z, (int64_t)A.nu * A.n);
       E.copy(F.z, F.zinit, (int64_t)F.nu * F.n);
-      k_maxabs<<<E.red_grid(A.n), kRedThreads, 0, h->stream>>>(A.n, F.zinit + (int64_t)A.nu * A.n, h->partials, h->ticket, h->dscal);
-      E.check_launch();
+      E_LAUNCH(KC_VEC, k_maxabs<<<E.red_grid(A.n), kRedThreads, 0, h->stream>>>(A.n, F.zinit + (int64_t)A.nu * A.n, h->partials, h->ticket, h->dscal));
       E.fetch(3);
       *b = 2.0 * std::max(1.0, h->hscal[0]);
     }
@@ -1411,6 +1435,28 @@ int mgbx_set_grids(mgbx_handle *h, const double *f_grid, const double *g_grid) {
 
 int64_t mgbx_launch_count(const mgbx_handle *h) { return h ? h->launches : 0; }
 
+int mgbx_kernel_stats(mgbx_handle *h, int reset, int32_t *nclasses, const char **names, int64_t *launches, double *ms) {
+  if (!h || !nclasses) return MGBX_ERR_ARG;
+  *nclasses = KC_COUNT;
+  for (int k = 0; k < KC_COUNT; ++k) {
+    if (names) names[k] = kKClassNames[k];
+    if (launches) launches[k] = h->kc_launches[k];
+    if (ms) ms[k] = h->kc_ms[k];
+    if (reset) {
+      h->kc_launches[k] = 0;
+      h->kc_ms[k] = 0.0;
+    }
+  }
+  return MGBX_OK;
+}
+
+int mgbx_set_profile(mgbx_handle *h, int on) {
+  if (!h) return MGBX_ERR_ARG;
+  cudaStreamSynchronize(h->stream);
+  h->cfg.profile = on;
+  return MGBX_OK;
+}
+
 int64_t mgbx_level_size(mgbx_handle *h, int which, int level) {
   if (!h || which < 0 || which > 1 || level < 0 || level >= h->amg[which].L) return -1;
   return h->amg[which].m[level];
@@ -1474,21 +1520,16 @@ int mgbx_hessian_values(mgbx_handle *h, int which, int level, double t, const do
         P.Erow[j] = -1;
       }
       P.Hn = A.Hn;
-      k_node<NODE_F2><<<E.red_grid(A.n), kRedThreads, 0, h->stream>>>(P);
-      E.check_launch();
+      E_LAUNCH(KC_NODE_F2, k_node<NODE_F2><<<E.red_grid(A.n), kRedThreads, 0, h->stream>>>(P));
       ElemParams EP = E.elem_params(A);
-      k_blockhess<<<nblk(S.hblk_size), 256, 0, h->stream>>>(EP, S.pl, A.Hn, S.Hblk);
-      E.check_launch();
-      k_csr_gather<<<nblk(S.lev[0].A.nnz), 256, 0, h->stream>>>(S.lev[0].A.nnz, S.gptr, S.gidx, S.gw, S.Hblk, S.lev[0].A.val);
-      E.check_launch();
+      E_LAUNCH(KC_BLOCKHESS, k_blockhess<<<nblk(S.hblk_size), 256, 0, h->stream>>>(EP, S.pl, A.Hn, S.Hblk));
+      E_LAUNCH(KC_GATHER, k_csr_gather<<<nblk(S.lev[0].A.nnz), 256, 0, h->stream>>>(S.lev[0].A.nnz, S.gptr, S.gidx, S.gw, S.Hblk, S.lev[0].A.val));
       const int ktop = A.L - 1 - level;
       for (int k = 0; k < ktop; ++k) {
         SysLevel &Lv = S.lev[k];
         SysLevel &Lc = S.lev[k + 1];
-        k_spgemm_numeric<<<nblk(Lv.AT.rows), 256, 0, h->stream>>>(Lv.A, Lv.T, Lv.AT);
-        E.check_launch();
-        k_spgemm_numeric<<<nblk(Lc.A.rows), 256, 0, h->stream>>>(Lv.Tt, Lv.AT, Lc.A);
-        E.check_launch();
+        E_LAUNCH(KC_SPGEMM, k_spgemm_numeric<<<nblk(Lv.AT.rows), 256, 0, h->stream>>>(Lv.A, Lv.T, Lv.AT));
+        E_LAUNCH(KC_SPGEMM, k_spgemm_numeric<<<nblk(Lc.A.rows), 256, 0, h->stream>>>(Lv.Tt, Lv.AT, Lc.A));
       }
       SysLevel &Lv = S.lev[ktop];
       CK(cudaMemcpyAsync(val, Lv.A.val, sizeof(double) * Lv.A.nnz, cudaMemcpyDeviceToHost, h->stream));

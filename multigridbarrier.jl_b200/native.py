@@ -55,7 +55,7 @@ class Problem(C.Structure):
 class Config(C.Structure):
     _fields_ = [("dense_direct_max", C.c_int32), ("coarse_max", C.c_int32), ("pcg_maxit", C.c_int32),
                 ("pcg_rtol", C.c_double), ("smoother_sweeps", C.c_int32), ("condense", C.c_int32),
-                ("device", C.c_int32), ("verbose", C.c_int32)]
+                ("device", C.c_int32), ("verbose", C.c_int32), ("profile", C.c_int32)]
 
 
 class StepOpts(C.Structure):
@@ -83,7 +83,7 @@ EXPORTS = [
     "mgbx_phase1_init", "mgbx_set_feasibility_box", "mgbx_reset_feasibility_state", "mgbx_handoff",
     "mgbx_matched_t", "mgbx_get_z", "mgbx_set_z", "mgbx_set_grids", "mgbx_level_size",
     "mgbx_barrier_eval", "mgbx_hessian_pattern", "mgbx_hessian_values", "mgbx_solve_newton_system",
-    "mgbx_plan_pattern", "mgbx_launch_count",
+    "mgbx_plan_pattern", "mgbx_launch_count", "mgbx_kernel_stats", "mgbx_set_profile",
 ]
 
 _lib = None
@@ -136,6 +136,8 @@ def lib():
                                     c_i64p, c_i64p, c_i64p]
     L.mgbx_launch_count.argtypes = [H]
     L.mgbx_launch_count.restype = C.c_int64
+    L.mgbx_kernel_stats.argtypes = [H, C.c_int, c_i32p, C.POINTER(C.c_char_p), c_i64p, c_f64p]
+    L.mgbx_set_profile.argtypes = [H, C.c_int]
     _lib = L
     return L
 
@@ -340,6 +342,18 @@ class Handle:
 
     def launch_count(self):
         return int(lib().mgbx_launch_count(self._h))
+
+    def set_profile(self, on):
+        self._check(lib().mgbx_set_profile(self._h, int(on)))
+
+    def kernel_stats(self, reset=False):
+        """{class: (launches, device ms)}; ms are only accumulated while profiling is on."""
+        nc = C.c_int32()
+        names = (C.c_char_p * 16)()
+        launches = np.zeros(16, np.int64)
+        ms = np.zeros(16)
+        self._check(lib().mgbx_kernel_stats(self._h, int(reset), C.byref(nc), names, _ptr(launches, c_i64p), _ptr(ms)))
+        return {names[k].decode(): (int(launches[k]), float(ms[k])) for k in range(nc.value)}
 
     # ---- parity hooks
     def level_size(self, which, level):

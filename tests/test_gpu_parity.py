@@ -1,0 +1,243 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (libmgbx.so), against
+  (a) the reference's golden vectors (tol 1e-6 on |z - gold|_2, test/runtests.jl:13-52, test/test_algebraic.jl:38-69),
+  (b) the CPU oracle on the same inputs, stage by stage (f0, f1, f2 values + pattern, Newton solve, whole solve),
+  (c) size-independent properties at the bench size (gradient consistency, residuals, determinism).
+Tolerances (north-star): CSR pattern bit-exact; objective 1e-8 relative; z 1e-6 relative L2; Newton counts +-1
+per barrier step."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import mgb_oracle as O
+from helpers import (GEOMS, PARABOLIC_CASES, SOLVE_CASES, default_problem, gold, lower_bound_problem)
+from mgbx import geometry as G, hierarchy as H, native, problem as P, solver
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-6
+
+
+def rel(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300)
+
+
+# ------------------------------------------------------------------------------------------ goldens
+@pytest.mark.parametrize("name,geom,p", SOLVE_CASES)
+def test_mgb_solve_golden(name, geom, p):
+    sol = solver.mgb_solve(default_problem(geom, p))
+    assert np.linalg.norm(sol["z"] - gold(name)) < TOL
+    assert sol["stats"]["gpu_launches"] > 0
+
+
+@pytest.mark.parametrize("name,geom", PARABOLIC_CASES)
+def test_parabolic_golden(name, geom):
+    sol = solver.parabolic_solve(H.amg(GEOMS[geom]()), h=0.5, p=1.0)
+    assert np.linalg.norm(np.stack(sol["u"], axis=2) - gold(name)) < TOL
+
+
+@pytest.mark.parametrize("name,geom,p", [c for c in SOLVE_CASES if c[1] in ("fem2d_P1_L2", "fem3d_k1_L2", "fem2d_P2_L2")])
+def test_golden_with_pcg_forced(name, geom, p):
+    """Same goldens with every Newton system solved by V-cycle PCG (no direct dense solve at the top)."""
+    sol = solver.mgb_solve(default_problem(geom, p), config=dict(dense_direct_max=8, coarse_max=8))
+    assert np.linalg.norm(sol["z"] - gold(name)) < TOL
+    assert sol["stats"]["pcg_iters"] > 0
+
+
+# ------------------------------------------------------------------------------------------ failure semantics
+def test_feasibility_escalation():
+    sol = solver.mgb_solve(lower_bound_problem(50.0))
+    assert sol["SOL_feasibility"] is not None
+    assert np.max(np.abs(sol["z"] - 50.0)) < 1e-3
+    assert "bounding box R=100.0" in sol["log"]
+
+
+def test_infeasible_certified():
+    with pytest.raises(solver.MGBConvergenceFailure) as e:
+        solver.mgb_solve(lower_bound_problem(0.0, infeasible_pair=True))
+    assert e.value.code == "infeasible"
+
+
+def test_feasibility_rmax():
+    with pytest.raises(solver.MGBConvergenceFailure) as e:
+        solver.mgb_solve(lower_bound_problem(1.0e6), feasibility_Rmax=1000.0)
+    assert e.value.code == "feasibility_Rmax"
+
+
+def test_feasible_start_skips_phase1():
+    sol = solver.mgb_solve(lower_bound_problem(-50.0))
+    assert sol["SOL_feasibility"] is None
+    assert np.max(np.abs(sol["z"] + 50.0)) < 1e-3
+
+
+def test_tiny_tolerance_is_a_convergence_failure():
+    """test/test_algebraic_coverage.jl:119-127: tol=1e-50 cannot be reached."""
+    with pytest.raises((solver.MGBConvergenceFailure, FloatingPointError)):
+        solver.mgb_solve(default_problem("fem1d_3nodes", 1.0), tol=1e-50, maxit=40)
+
+
+# ------------------------------------------------------------------------------------------ stage-by-stage vs oracle
+def _obstacle_problem():
+    """two-sided obstacle + p-Laplace cone as an intersection (linear + EP pieces, select grid)."""
+    mg = H.amg(G.subdivide(G.fem2d_P1(), 3))
+    n = mg.geometry.n
+    x = mg.geometry.xflat()
+    lin = P.convex_linear(mg, idx=(0,), A_grid=np.tile([1.0, -1.0], (n, 1)),
+                          b_grid=np.stack([3.0 + 0 * x[:, 0], 3.0 + x[:, 0] ** 2], axis=1))
+    ep = P.convex_Euclidian_power(mg, idx=(1, 2, 3), p_grid=np.where(x[:, 0] > 0, 1.5, 3.0))
+    sel = np.stack([np.ones(n), (x[:, 1] > -0.5).astype(float)], axis=1)
+    Q = P.convex_piecewise(mg, [lin, ep], select_grid=sel)
+    return P.assemble(mg, Q=Q, p=1.5)
+
+
+STAGE_PROBLEMS = {
+    "p1L3_p1.5": lambda: default_problem_l("p1", 3, 1.5),
+    "p2L2_p1": lambda: default_problem("fem2d_P2_L2", 1.0),
+    "q1L2_p1.5": lambda: default_problem("fem3d_k1_L2", 1.5),
+    "spectral2d": lambda: default_problem("spectral2d_n5", 1.0),
+    "piecewise": _obstacle_problem,
+}
+
+
+def default_problem_l(kind, L, p):
+    return P.assemble(H.amg(G.subdivide(G.fem2d_P1(), L)), p=p)
+
+
+@pytest.mark.parametrize("name", list(STAGE_PROBLEMS))
+@pytest.mark.parametrize("which", [0, 1])
+def test_stages_match_oracle(name, which):
+    prob = STAGE_PROBLEMS[name]()
+    M = prob.M[which]
+    n = M.geometry.n
+    t = 0.7
+    rng = np.random.default_rng(5)
+    bw = O.barrier_weights(M.w) if which == 0 else None
+    h = native.Handle(prob, barrier_weights=bw)
+    try:
+        Qo, c = prob.Q, t * prob.f
+        z0 = prob.g.T.reshape(-1).copy()
+        if which == 1:
+            # move the main state off-domain so that phase I is armed, then compare on the feasibility AMG
+            need, b, zabs = h.phase1_init()
+            if not need:
+                z_bad = z0.copy()
+                z_bad[-n:] = -1.0          # negative slack: outside every cone
+                h.set_z(z_bad, 0)
+                need, b, zabs = h.phase1_init()
+            assert need
+            h.set_feasibility_box(b, 50.0)
+            Qo = O.FeasibilityConvex(prob.Q, b, 50.0, prob.M[0].nD + 1)
+            c = np.zeros((n, M.nD))
+            c[:, prob.M[0].nD] = t
+            z0 = h.get_z(1)
+        B = O.Barrier(Qo, bw)
+        ops = O.operators(M)
+        for J in range(len(M.R_fine)):
+            R = M.R_fine[J]
+            s = 1e-3 * rng.normal(size=R.shape[1])
+            y_o = B.f0(s, M.w, c, R, ops, z0)
+            assert np.isfinite(y_o)
+            g_o = B.f1(s, M.w, c, R, ops, z0)
+            H_o = sp.csr_matrix(B.f2(s, M.w, c, R, ops, z0))
+            assert abs(h.barrier_eval(which, J, t, s, 0) - y_o) <= 1e-12 * max(1.0, abs(y_o))
+            assert rel(h.barrier_eval(which, J, t, s, 1), g_o) < 1e-11
+            H_d = h.hessian(which, J, t, s)
+            optr, oind = O.hessian_pattern(M, J)
+            assert np.array_equal(H_d.indptr, optr) and np.array_equal(H_d.indices, oind)   # bit-exact pattern
+            assert abs(H_d - H_o).sum() <= 1e-11 * abs(H_o).sum()
+            x_o = O.solve_sym(H_o, g_o)
+            x_d, _ = h.solve_newton_system(which, J, t, s, g_o)
+            assert rel(x_d, x_o) < 1e-8
+    finally:
+        h.close()
+
+
+def test_domain_escape_is_signalled_by_value():
+    """Log(x<=0) = -Inf, _safe_pow(s<=0) = 0 => f0 = +Inf outside the cone (src/utils.jl:14, convex_linear.jl:388-390)."""
+    prob = default_problem("fem2d_P1_L2", 1.0)
+    M = prob.M[0]
+    h = native.Handle(prob)
+    try:
+        J = len(M.R_fine) - 1
+        s = np.zeros(M.R_fine[J].shape[1])
+        s[-M.geometry.n:] = -1000.0      # slack far below |grad u|
+        assert h.barrier_eval(0, J, 1.0, s, 0) == np.inf
+    finally:
+        h.close()
+
+
+# ------------------------------------------------------------------------------------------ whole solve vs oracle
+@pytest.mark.parametrize("L,p,cfg", [(5, 1.5, {}), (6, 1.0, {}), (6, 1.5, dict(dense_direct_max=64, coarse_max=32))])
+def test_solve_matches_oracle_midsize(L, p, cfg):
+    prob = P.assemble(H.amg(G.subdivide(G.fem2d_P1(), L)), p=p)
+    sd = solver.mgb_solve(prob, config=cfg)
+    so = O.mgb_solve(prob)
+    assert rel(sd["z"], so["z"]) < 1e-6
+    od, oo = sd["SOL_main"]["c_dot_Dz"][-1], so["SOL_main"]["c_dot_Dz"][-1]
+    assert abs(od - oo) <= 1e-8 * abs(oo)
+    idv, iov = sd["SOL_main"]["its"], so["SOL_main"]["its"]
+    assert idv.shape == iov.shape
+    assert np.max(np.abs(idv.sum(axis=0) - iov.sum(axis=0))) <= 1     # Newton counts +-1 per barrier step
+    assert np.allclose(sd["SOL_main"]["ts"], so["SOL_main"]["ts"])
+
+
+def test_fem3d_midsize_matches_oracle():
+    prob = P.assemble(H.amg(G.subdivide(G.fem3d(k=1), 3)), p=1.0)
+    sd = solver.mgb_solve(prob, config=dict(dense_direct_max=64, coarse_max=32))
+    so = O.mgb_solve(prob)
+    assert rel(sd["z"], so["z"]) < 1e-6
+    assert np.max(np.abs(sd["SOL_main"]["its"].sum(axis=0) - so["SOL_main"]["its"].sum(axis=0))) <= 1
+
+
+# ------------------------------------------------------------------------------------------ bench-size properties
+@pytest.fixture(scope="module")
+def big_problem():
+    return P.assemble(H.amg(G.subdivide(G.fem2d_P1(), 9)), p=1.5)     # n = 393 216 (same family as the bench config)
+
+
+def test_bench_size_properties(big_problem):
+    prob = big_problem
+    M = prob.M[0]
+    J = len(M.R_fine) - 1
+    m = M.R_fine[J].shape[1]
+    rng = np.random.default_rng(11)
+    h = native.Handle(prob)
+    try:
+        s = 1e-3 * rng.normal(size=m)
+        d = rng.normal(size=m)
+        d /= np.linalg.norm(d)
+        t = 3.0
+        # f1 is the gradient of f0: central difference along a random direction
+        eps = 1e-6
+        fd = (h.barrier_eval(0, J, t, s + eps * d, 0) - h.barrier_eval(0, J, t, s - eps * d, 0)) / (2 * eps)
+        g = h.barrier_eval(0, J, t, s, 1)
+        assert abs(fd - g @ d) <= 1e-6 * max(1.0, abs(g @ d))
+        # f2 is the Jacobian of f1 and is symmetric
+        Hm = h.hessian(0, J, t, s)
+        assert abs(Hm - Hm.T).max() <= 1e-12 * abs(Hm).max()
+        gd = (h.barrier_eval(0, J, t, s + eps * d, 1) - h.barrier_eval(0, J, t, s - eps * d, 1)) / (2 * eps)
+        assert rel(Hm @ d, gd) < 1e-5
+        # the condensed V-cycle PCG solve satisfies the full (uncondensed) Newton system
+        x, its = h.solve_newton_system(0, J, t, s, g)
+        assert its > 0
+        assert np.linalg.norm(Hm @ x - g) <= 1e-8 * np.linalg.norm(g)
+        # run-to-run determinism (fixed-order reductions and assembly)
+        g2 = h.barrier_eval(0, J, t, s, 1)
+        x2, _ = h.solve_newton_system(0, J, t, s, g)
+        assert np.array_equal(g, g2) and np.array_equal(x, x2)
+    finally:
+        h.close()
+
+
+def test_bench_size_solve_is_a_minimiser(big_problem):
+    prob = big_problem
+    sol = solver.mgb_solve(prob)
+    SM = sol["SOL_main"]
+    assert SM["ts"][-1] >= 1.0 / np.sqrt(np.finfo(float).eps)
+    # the duality-gap scalar decreases monotonically to the optimum along the t-ramp (up to roundoff)
+    cd = SM["c_dot_Dz"]
+    assert np.all(np.diff(cd) <= 1e-7 * abs(cd[-1]))
+    # boundary data kept, slack dominates |grad u| (cone constraint s >= |grad u|^p) at every node
+    z = sol["z"]
+    assert np.all(np.isfinite(z))
+    Mm = prob.M[0]
+    Dz = O.operators(Mm).apply(z.T.reshape(-1))
+    assert np.all(Dz[:, 3] >= np.hypot(Dz[:, 1], Dz[:, 2]) ** 1.5 - 1e-9)

@@ -43,10 +43,18 @@ def stage_hooks(name, prob, which=0, t=0.1, cfgs=({}, {"condense": 0})):
     bw = O.barrier_weights(M.w) if which == 0 else None
     h = native.Handle(prob, barrier_weights=bw)
     try:
-        B = O.Barrier(prob.Q, bw)
+        Qo = prob.Q
+        if which == 1:
+            need, b, zabs = h.phase1_init()
+            h.set_feasibility_box(b, 100.0)
+            Qo = O.FeasibilityConvex(prob.Q, b, 100.0, prob.M[0].nD + 1)
+            c1 = np.zeros((n, M.nD)); c1[:, prob.M[0].nD] = 1.0
+        B = O.Barrier(Qo, bw)
         ops = O.operators(M)
         z0 = prob.g.T.reshape(-1).copy()
-        c = t * prob.f
+        if which == 1:
+            z0 = h.get_z(1)
+        c = t * (prob.f if which == 0 else c1)
         for J in range(L):
             R = M.R_fine[J]
             m = R.shape[1]
@@ -150,7 +158,7 @@ def main(argv):
                 prob = P.assemble(H.amg(G.subdivide(G.fem2d_P1(), Lr)), p=1.5)
                 if Lr <= 5:
                     stage_hooks(c, prob, cfgs=({}, {"condense": 0}, {"dense_direct_max": 64, "coarse_max": 32}))
-                for cfg in ({}, {"dense_direct_max": 64, "coarse_max": 32}):
+                for cfg in (({}, {"dense_direct_max": 64, "coarse_max": 32}) if Lr <= 7 else ({},)):
                     sol = stage_solve(c + str(cfg), prob, config=cfg)
                     if sol is not None and Lr <= 7:
                         compare_oracle(c, prob, sol)
