@@ -114,13 +114,14 @@ typedef struct {
 
 typedef struct {
   int32_t dense_direct_max;  /* Newton systems with <= this many unknowns: dense Cholesky (default 2048) */
-  int32_t coarse_max;        /* V-cycle is cut at the first level with <= this many unknowns (default 512) */
+  int32_t coarse_max;        /* V-cycle is cut at the first level with <= this many unknowns (default 128) */
   int32_t pcg_maxit;         /* default 400 */
   double pcg_rtol;           /* relative residual, default 1e-11 */
   int32_t smoother_sweeps;   /* l1-Jacobi / Chebyshev pre+post sweeps, default 2 */
   int32_t condense;          /* 1 (default): eliminate node-local :full variables exactly before PCG */
   int32_t device;            /* CUDA device ordinal, -1 = current */
   int32_t verbose;
+  int32_t use_graphs;        /* 1 (default): replay each PCG iteration (V-cycle + vector updates) as one CUDA graph */
   int32_t profile;           /* 1: time every kernel launch with CUDA events on the handle's stream (mgbx_kernel_stats) */
 } mgbx_config;
 

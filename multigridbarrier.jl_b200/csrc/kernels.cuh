@@ -146,6 +146,31 @@ __global__ void __launch_bounds__(256) k_jacobi(DevCsr A, const double *__restri
   if (sub == 0) xnew[row] = x[row] + dinv[row] * (b[row] - acc);
 }
 
+// two l1-Jacobi sweeps from x = 0 in one pass:  x1 = dinv b;  x2 = x1 + dinv (b - A x1)
+template <int G>
+__global__ void __launch_bounds__(256) k_jacobi_first2(DevCsr A, const double *__restrict__ dinv, const double *__restrict__ b,
+                                                        double *xnew) {
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t row = gtid / G;
+  const int sub = (int)(gtid % G);
+  if (row >= A.rows) return;
+  const int64_t bb = A.ptr[row], e = A.ptr[row + 1];
+  double acc = 0.0;
+  for (int64_t k = bb + sub; k < e; k += G) {
+    const int32_t j = A.idx[k];
+    acc += A.val[k] * (dinv[j] * b[j]);
+  }
+  if (G > 1) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, G);
+  }
+  if (sub == 0) {
+    const double d = dinv[row], bi = b[row];
+    const double x1 = d * bi;
+    xnew[row] = x1 + d * (bi - acc);
+  }
+}
+
 // dinv = 1 / sum_k |a_ik|  (l1-Jacobi), diag = a_ii
 __global__ void k_l1diag(DevCsr A, double *dinv, double *diag) {
   const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -565,6 +590,12 @@ __global__ void __launch_bounds__(kRedThreads) k_pcg_update(int64_t m, double *s
 }
 //  step B: beta = rz_new/rz;  p = z + beta p;  then rz <- rz_new   (done by thread 0 of the LAST block only after all reads:
 //  we avoid the hazard by passing beta through a separate slot written by k_pcg_beta)
+__global__ void k_pcg_init(double *scal) {   // rz = 1 so that the first beta is finite (p starts at 0)
+  scal[0] = 1.0;
+  scal[1] = 1.0;
+  scal[3] = 0.0;
+  scal[4] = 0.0;
+}
 __global__ void k_pcg_beta(double *scal) {   // scal[4] = beta = scal[3]/scal[0]; scal[0] = scal[3]
   scal[4] = scal[3] / scal[0];
   scal[0] = scal[3];

@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstring>
 #include <functional>
+#include <map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -115,6 +116,9 @@ struct SysLevel {
   int64_t m = 0;
   DevCsr A;
   DevCsr T, Tt, AT;          // T: this level (rows) <- next coarser level (cols)
+  // Galerkin gather plans: AT = A*T  and  A_coarse = T'*AT, one fixed-order gather kernel each
+  int64_t *g1ptr = nullptr, *g1src = nullptr, *g2ptr = nullptr, *g2src = nullptr;
+  double *g1w = nullptr, *g2w = nullptr;
   bool has_coarser = false, T_identity = false;
   double *dinv = nullptr, *diag = nullptr;
   double *b = nullptr, *x = nullptr, *x2 = nullptr, *r = nullptr;   // V-cycle work
@@ -137,7 +141,8 @@ struct System {
   int cut = -1;                      // V-cycle bottom (dense inverse) level index, -1: none
   // PCG work at the largest size
   double *pc_r = nullptr, *pc_z = nullptr, *pc_p = nullptr, *pc_Ap = nullptr, *pc_x = nullptr, *pc_b = nullptr;
-  int values_top = -1;               // lev index whose hierarchy values are current (for reuse checks)
+  std::map<int, cudaGraphExec_t> graphs;        // captured PCG iteration per top level
+  std::map<int, int64_t> graph_launches;
 };
 
 struct Amg {
@@ -259,15 +264,27 @@ struct Engine {
   void spmv(const DevCsr &A, const double *x, const double *y0, double alpha, double *y, int G = 0) {
     if (A.rows == 0) return;
     if (G == 0) G = group_for(A);
+    pre_launch(KC_SPMV);
     if (G == 32) k_spmv<32><<<nblk(A.rows * 32), 256, 0, s>>>(A, x, y0, alpha, y);
     else if (G == 4) k_spmv<4><<<nblk(A.rows * 4), 256, 0, s>>>(A, x, y0, alpha, y);
-    else LAUNCH(KC_SPMV, k_spmv<1><<<nblk(A.rows), 256, 0, s>>>(A, x, y0, alpha, y));
+    else k_spmv<1><<<nblk(A.rows), 256, 0, s>>>(A, x, y0, alpha, y);
+    post_launch(KC_SPMV);
   }
   void jacobi(const SysLevel &Lv, const double *b, const double *x, double *xnew) {
     const int G = Lv.spmv_group;
+    pre_launch(KC_JACOBI);
     if (G == 32) k_jacobi<32><<<nblk(Lv.m * 32), 256, 0, s>>>(Lv.A, Lv.dinv, b, x, xnew);
     else if (G == 4) k_jacobi<4><<<nblk(Lv.m * 4), 256, 0, s>>>(Lv.A, Lv.dinv, b, x, xnew);
-    else LAUNCH(KC_JACOBI, k_jacobi<1><<<nblk(Lv.m), 256, 0, s>>>(Lv.A, Lv.dinv, b, x, xnew));
+    else k_jacobi<1><<<nblk(Lv.m), 256, 0, s>>>(Lv.A, Lv.dinv, b, x, xnew);
+    post_launch(KC_JACOBI);
+  }
+  void jacobi2(const SysLevel &Lv, const double *b, double *xnew) {
+    const int G = Lv.spmv_group;
+    pre_launch(KC_JACOBI);
+    if (G == 32) k_jacobi_first2<32><<<nblk(Lv.m * 32), 256, 0, s>>>(Lv.A, Lv.dinv, b, xnew);
+    else if (G == 4) k_jacobi_first2<4><<<nblk(Lv.m * 4), 256, 0, s>>>(Lv.A, Lv.dinv, b, xnew);
+    else k_jacobi_first2<1><<<nblk(Lv.m), 256, 0, s>>>(Lv.A, Lv.dinv, b, xnew);
+    post_launch(KC_JACOBI);
   }
   void copy(double *dst, const double *src, int64_t m) {
     if (m) CK(cudaMemcpyAsync(dst, src, sizeof(double) * m, cudaMemcpyDeviceToDevice, s));
@@ -385,6 +402,7 @@ struct Engine {
   void dense_factor(System &S, SysLevel &Lv, bool want_inverse);
   void dense_apply(SysLevel &Lv, const double *b, double *x);      // x = A^{-1} b via factor (direct)
   void vcycle(System &S, int k);
+  void pcg_iteration(System &S, int ktop);
   int pcg(System &S, int ktop, const double *b, double *x);
   int solve_compact(System &S, int ktop, const double *b, double *x);
   int solve(Amg &A, System &S, int J, const double *g, double *dir);
@@ -563,6 +581,17 @@ std::unique_ptr<System> build_system(mgbx_handle *h, Amg &A, bool condensed) {
       Lv.T = upload_csr(pool, Tk, s);
       Lv.Tt = upload_csr(pool, Ttk, s);
       Lv.AT = upload_csr(pool, ATp, s, false);
+      if (!Lv.T_identity) {
+        GatherPlan g1 = product_plan(cur, Tk, ATp, true);
+        GatherPlan g2 = product_plan(Ttk, ATp, nxt, false);
+        Lv.g1ptr = pool.upload<int64_t>(g1.ptr.data(), g1.ptr.size(), s);
+        Lv.g1src = pool.upload<int64_t>(g1.src.data(), g1.src.size(), s);
+        Lv.g1w = pool.upload<double>(g1.w.data(), g1.w.size(), s);
+        Lv.g2ptr = pool.upload<int64_t>(g2.ptr.data(), g2.ptr.size(), s);
+        Lv.g2src = pool.upload<int64_t>(g2.src.data(), g2.src.size(), s);
+        Lv.g2w = pool.upload<double>(g2.w.data(), g2.w.size(), s);
+        CK(cudaStreamSynchronize(s));
+      }
       cur = std::move(nxt);
     }
   }
@@ -641,8 +670,8 @@ void Engine::setup_hierarchy(Amg &A, System &S, int ktop) {
     if (Lv.T_identity) {
       copy(Lc.A.val, Lv.A.val, Lv.A.nnz);
     } else {
-      LAUNCH(KC_SPGEMM, k_spgemm_numeric<<<nblk(Lv.AT.rows), 256, 0, s>>>(Lv.A, Lv.T, Lv.AT));
-      LAUNCH(KC_SPGEMM, k_spgemm_numeric<<<nblk(Lc.A.rows), 256, 0, s>>>(Lv.Tt, Lv.AT, Lc.A));
+      LAUNCH(KC_SPGEMM, k_csr_gather<<<nblk(Lv.AT.nnz), 256, 0, s>>>(Lv.AT.nnz, Lv.g1ptr, Lv.g1src, Lv.g1w, Lv.A.val, Lv.AT.val));
+      LAUNCH(KC_SPGEMM, k_csr_gather<<<nblk(Lc.A.nnz), 256, 0, s>>>(Lc.A.nnz, Lv.g2ptr, Lv.g2src, Lv.g2w, Lv.AT.val, Lc.A.val));
     }
   }
   if (direct) {
@@ -711,8 +740,14 @@ void Engine::vcycle(System &S, int k) {
   const int nu = bottom ? 30 : std::max(1, h->cfg.smoother_sweeps);
   // pre-smoothing from x = 0
   double *xa = Lv.x, *xb = Lv.x2;
-  jacobi(Lv, Lv.b, nullptr, xa);
-  for (int it = 1; it < nu; ++it) {
+  int done = 1;
+  if (nu >= 2) {
+    jacobi2(Lv, Lv.b, xa);      // two sweeps from x = 0 in one kernel
+    done = 2;
+  } else {
+    jacobi(Lv, Lv.b, nullptr, xa);
+  }
+  for (int it = done; it < nu; ++it) {
     jacobi(Lv, Lv.b, xa, xb);
     std::swap(xa, xb);
   }
@@ -731,44 +766,92 @@ void Engine::vcycle(System &S, int k) {
 }
 
 // Preconditioned CG on lev[ktop]; returns the iteration count (negative: breakdown)
+// One PCG iteration on fixed buffers (capturable into a CUDA graph):
+//   z = M^{-1} r (V-cycle);  rz_new = r.z;  beta = rz_new/rz;  p = z + beta p;  Ap = A p;  alpha = rz/pAp;
+//   x += alpha p;  r -= alpha Ap;  rr = r.r;  scalars -> pinned host
+void Engine::pcg_iteration(System &S, int ktop) {
+  SysLevel &Lv = S.lev[ktop];
+  const int64_t m = Lv.m;
+  double *r = S.pc_r, *p = S.pc_p, *Ap = S.pc_Ap, *x = S.pc_x;
+  double *scal = h->dscal + 8;   // {rz, pAp, rr, rz_new, beta}
+  const unsigned int rg = red_grid(m);
+  copy(Lv.b, r, m);
+  vcycle(S, ktop);
+  const double *zz = Lv.x;
+  LAUNCH(KC_VEC, k_dot<<<rg, kRedThreads, 0, s>>>(m, r, zz, h->partials, h->ticket, scal + 3));
+  LAUNCH(KC_VEC, k_pcg_beta<<<1, 1, 0, s>>>(scal));
+  LAUNCH(KC_VEC, k_pcg_dir<<<nblk(m), 256, 0, s>>>(m, scal, zz, p));
+  spmv(Lv.A, p, nullptr, 1.0, Ap, Lv.spmv_group);
+  LAUNCH(KC_VEC, k_dot<<<rg, kRedThreads, 0, s>>>(m, p, Ap, h->partials, h->ticket, scal + 1));
+  LAUNCH(KC_VEC, k_pcg_update<<<rg, kRedThreads, 0, s>>>(m, scal, p, Ap, x, r, h->partials, h->ticket));
+  CK(cudaMemcpyAsync(h->hscal + 8, scal, sizeof(double) * 5, cudaMemcpyDeviceToHost, s));
+}
+
+// Preconditioned CG on lev[ktop]; returns the iteration count (negative: breakdown)
 int Engine::pcg(System &S, int ktop, const double *b, double *x) {
   SysLevel &Lv = S.lev[ktop];
   const int64_t m = Lv.m;
-  double *r = S.pc_r, *z = S.pc_z, *p = S.pc_p, *Ap = S.pc_Ap;
-  double *scal = h->dscal + 8;   // {rz, pAp, rr, rz_new, beta}
+  double *r = S.pc_r, *p = S.pc_p;
+  double *scal = h->dscal + 8;
   const unsigned int rg = red_grid(m);
-  zero(x, m);
+  zero(S.pc_x, m);
+  zero(p, m);
   copy(r, b, m);
   LAUNCH(KC_VEC, k_dot<<<rg, kRedThreads, 0, s>>>(m, r, r, h->partials, h->ticket, scal + 2));
+  LAUNCH(KC_VEC, k_pcg_init<<<1, 1, 0, s>>>(scal));
   CK(cudaMemcpyAsync(h->hscal + 8, scal, sizeof(double) * 5, cudaMemcpyDeviceToHost, s));
   sync();
   const double bb = h->hscal[10];
-  if (!(bb > 0.0) || !std::isfinite(bb)) return 0;
+  if (!(bb > 0.0) || !std::isfinite(bb)) {
+    zero(x, m);
+    return 0;
+  }
   const double target = h->cfg.pcg_rtol * h->cfg.pcg_rtol * bb;
+  // the iteration body is captured once per (system, top level) and replayed as a CUDA graph
+  cudaGraphExec_t gexec = nullptr;
+  const bool use_graph = h->cfg.use_graphs && !h->cfg.profile;
+  if (use_graph) {
+    auto it = S.graphs.find(ktop);
+    if (it == S.graphs.end()) {
+      cudaGraph_t graph = nullptr;
+      CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      const int64_t l0 = h->launches;
+      try {
+        pcg_iteration(S, ktop);
+      } catch (...) {
+        cudaStreamEndCapture(s, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        throw;
+      }
+      S.graph_launches[ktop] = h->launches - l0;
+      h->launches = l0;
+      CK(cudaStreamEndCapture(s, &graph));
+      CK(cudaGraphInstantiate(&gexec, graph, 0));
+      cudaGraphDestroy(graph);
+      S.graphs[ktop] = gexec;
+    } else {
+      gexec = it->second;
+    }
+  }
   int it = 0;
   double best = bb;
   int since_best = 0;
-  for (; it < h->cfg.pcg_maxit;) {
-    copy(Lv.b, r, m);
-    vcycle(S, ktop);
-    const double *zz = Lv.x;
-    if (it == 0) {
-      LAUNCH(KC_VEC, k_dot<<<rg, kRedThreads, 0, s>>>(m, r, zz, h->partials, h->ticket, scal + 0));
-      copy(p, zz, m);
+  int status = 1;
+  while (it < h->cfg.pcg_maxit) {
+    if (gexec) {
+      CK(cudaGraphLaunch(gexec, s));
+      h->launches += S.graph_launches[ktop];
+      h->kc_launches[KC_VEC] += 0;
     } else {
-      LAUNCH(KC_VEC, k_dot<<<rg, kRedThreads, 0, s>>>(m, r, zz, h->partials, h->ticket, scal + 3));
-      LAUNCH(KC_VEC, k_pcg_beta<<<1, 1, 0, s>>>(scal));
-      LAUNCH(KC_VEC, k_pcg_dir<<<nblk(m), 256, 0, s>>>(m, scal, zz, p));
+      pcg_iteration(S, ktop);
     }
-    (void)z;
-    spmv(Lv.A, p, nullptr, 1.0, Ap, Lv.spmv_group);
-    LAUNCH(KC_VEC, k_dot<<<rg, kRedThreads, 0, s>>>(m, p, Ap, h->partials, h->ticket, scal + 1));
-    LAUNCH(KC_VEC, k_pcg_update<<<rg, kRedThreads, 0, s>>>(m, scal, p, Ap, x, r, h->partials, h->ticket));
     ++it;
-    CK(cudaMemcpyAsync(h->hscal + 8, scal, sizeof(double) * 5, cudaMemcpyDeviceToHost, s));
     sync();
     const double rr = h->hscal[10];
-    if (!std::isfinite(rr) || !(h->hscal[9] > 0.0)) return -it;   // breakdown (indefinite or non-finite)
+    if (!std::isfinite(rr) || !(h->hscal[9] > 0.0)) {   // breakdown (indefinite or non-finite)
+      status = -1;
+      break;
+    }
     if (rr <= target) break;
     if (rr < best * 0.999) {
       best = rr;
@@ -777,7 +860,8 @@ int Engine::pcg(System &S, int ktop, const double *b, double *x) {
       break;   // stagnation at the attainable accuracy
     }
   }
-  return it;
+  copy(x, S.pc_x, m);
+  return status * it;
 }
 
 int Engine::solve_compact(System &S, int ktop, const double *b, double *x) {
@@ -1179,7 +1263,7 @@ extern "C" {
 
 void mgbx_default_config(mgbx_config *c) {
   c->dense_direct_max = 2048;
-  c->coarse_max = 512;
+  c->coarse_max = 128;
   c->pcg_maxit = 400;
   c->pcg_rtol = 1e-11;
   c->smoother_sweeps = 2;
@@ -1187,6 +1271,7 @@ void mgbx_default_config(mgbx_config *c) {
   c->device = -1;
   c->verbose = 0;
   c->profile = 0;
+  c->use_graphs = 1;
 }
 
 void mgbx_default_step_opts(mgbx_step_opts *o, int64_t n) {
@@ -1281,6 +1366,10 @@ int mgbx_create(const mgbx_problem *prob, const mgbx_config *cfg, mgbx_handle **
 void mgbx_destroy(mgbx_handle *h) {
   if (!h) return;
   if (h->stream) cudaStreamSynchronize(h->stream);
+  for (int w = 0; w < 2; ++w)
+    for (System *S : {h->amg[w].sys_cond.get(), h->amg[w].sys_full.get()})
+      if (S)
+        for (auto &kv : S->graphs) cudaGraphExecDestroy(kv.second);
   h->pool.release();
   if (h->hscal) cudaFreeHost(h->hscal);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -1528,8 +1617,12 @@ int mgbx_hessian_values(mgbx_handle *h, int which, int level, double t, const do
       for (int k = 0; k < ktop; ++k) {
         SysLevel &Lv = S.lev[k];
         SysLevel &Lc = S.lev[k + 1];
-        E_LAUNCH(KC_SPGEMM, k_spgemm_numeric<<<nblk(Lv.AT.rows), 256, 0, h->stream>>>(Lv.A, Lv.T, Lv.AT));
-        E_LAUNCH(KC_SPGEMM, k_spgemm_numeric<<<nblk(Lc.A.rows), 256, 0, h->stream>>>(Lv.Tt, Lv.AT, Lc.A));
+        if (Lv.T_identity) {
+          E.copy(Lc.A.val, Lv.A.val, Lv.A.nnz);
+          continue;
+        }
+        E_LAUNCH(KC_SPGEMM, k_csr_gather<<<nblk(Lv.AT.nnz), 256, 0, h->stream>>>(Lv.AT.nnz, Lv.g1ptr, Lv.g1src, Lv.g1w, Lv.A.val, Lv.AT.val));
+        E_LAUNCH(KC_SPGEMM, k_csr_gather<<<nblk(Lc.A.nnz), 256, 0, h->stream>>>(Lc.A.nnz, Lv.g2ptr, Lv.g2src, Lv.g2w, Lv.AT.val, Lc.A.val));
       }
       SysLevel &Lv = S.lev[ktop];
       CK(cudaMemcpyAsync(val, Lv.A.val, sizeof(double) * Lv.A.nnz, cudaMemcpyDeviceToHost, h->stream));

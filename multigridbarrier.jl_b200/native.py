@@ -55,7 +55,7 @@ class Problem(C.Structure):
 class Config(C.Structure):
     _fields_ = [("dense_direct_max", C.c_int32), ("coarse_max", C.c_int32), ("pcg_maxit", C.c_int32),
                 ("pcg_rtol", C.c_double), ("smoother_sweeps", C.c_int32), ("condense", C.c_int32),
-                ("device", C.c_int32), ("verbose", C.c_int32), ("profile", C.c_int32)]
+                ("device", C.c_int32), ("verbose", C.c_int32), ("use_graphs", C.c_int32), ("profile", C.c_int32)]
 
 
 class StepOpts(C.Structure):

@@ -37,7 +37,7 @@ def test_parabolic_golden(name, geom):
 @pytest.mark.parametrize("name,geom,p", [c for c in SOLVE_CASES if c[1] in ("fem2d_P1_L2", "fem3d_k1_L2", "fem2d_P2_L2")])
 def test_golden_with_pcg_forced(name, geom, p):
     """Same goldens with every Newton system solved by V-cycle PCG (no direct dense solve at the top)."""
-    sol = solver.mgb_solve(default_problem(geom, p), config=dict(dense_direct_max=8, coarse_max=8))
+    sol = solver.mgb_solve(default_problem(geom, p), config=dict(dense_direct_max=0, coarse_max=0))
     assert np.linalg.norm(sol["z"] - gold(name)) < TOL
     assert sol["stats"]["pcg_iters"] > 0
 
@@ -83,7 +83,7 @@ def _obstacle_problem():
     lin = P.convex_linear(mg, idx=(0,), A_grid=np.tile([1.0, -1.0], (n, 1)),
                           b_grid=np.stack([3.0 + 0 * x[:, 0], 3.0 + x[:, 0] ** 2], axis=1))
     ep = P.convex_Euclidian_power(mg, idx=(1, 2, 3), p_grid=np.where(x[:, 0] > 0, 1.5, 3.0))
-    sel = np.stack([np.ones(n), (x[:, 1] > -0.5).astype(float)], axis=1)
+    sel = np.stack([(x[:, 1] > -0.5).astype(float), np.ones(n)], axis=1)   # obstacle only on part of the domain
     Q = P.convex_piecewise(mg, [lin, ep], select_grid=sel)
     return P.assemble(mg, Q=Q, p=1.5)
 
