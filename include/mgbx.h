@@ -11,6 +11,7 @@
  *   mgbx_step          <- mgb_step (+ newton, line search, f0/f1/f2, R'HR, solve)   src/mgb.jl:16-82, src/newton.jl:227-287
  *   mgbx_scalars       <- the scalars mgb_core / mgb_driver read between t-steps   src/mgb.jl:135-136,454,526-527
  *   mgbx_phase1_init   <- feasibility probe + slack initialisation    src/mgb.jl:417-448
+ *   mgbx_attach_feasibility <- M[2] of native_to_device, moved only if phase I runs   src/mgb.jl:449-452
  *   mgbx_set_feasibility_box <- _feasibility_convex(Q, b, R, ...)     src/mgb.jl:217-287,504
  *   mgbx_handoff       <- z2 = SOL_feas.z[1:len]                      src/mgb.jl:566
  *   mgbx_matched_t     <- _matched_t                                  src/mgb.jl:307-330
@@ -98,7 +99,8 @@ typedef struct {
   const double *const *op_data;  /* nops arrays p x p x N (BlockDiag.data) */
   const int32_t *D_var;    /* nD: state variable of D row k */
   const int32_t *D_op;     /* nD: operator id, -1 = identity */
-  const mgbx_csr *R_fine;  /* L matrices (nu*n) x m_l */
+  const mgbx_csr *R_fine;  /* L entries; only R_fine[L-1] ((nu*n) x m_L) is read: the coarser ones are
+                              R_fine[l] = R_fine[l+1]*T[l] and may be left zero-initialised */
   const mgbx_csr *T;       /* L-1 level transfers m_{l+1} x m_l with R_fine[l] = R_fine[l+1]*T[l] */
   const int64_t *var_offsets;    /* L x (nu+1): first column of variable k at level l */
 } mgbx_amg;
@@ -114,7 +116,7 @@ typedef struct {
 
 typedef struct {
   int32_t dense_direct_max;  /* Newton systems with <= this many unknowns: dense Cholesky (default 2048) */
-  int32_t coarse_max;        /* V-cycle is cut at the first level with <= this many unknowns (default 128) */
+  int32_t coarse_max;        /* V-cycle is cut at the first level with <= this many unknowns (default 128 = the maximum) */
   int32_t pcg_maxit;         /* default 400 */
   double pcg_rtol;           /* relative residual, default 1e-11 */
   int32_t smoother_sweeps;   /* l1-Jacobi / Chebyshev pre+post sweeps, default 2 */
@@ -123,6 +125,9 @@ typedef struct {
   int32_t verbose;
   int32_t use_graphs;        /* 1 (default): replay each PCG iteration (V-cycle + vector updates) as one CUDA graph */
   int32_t profile;           /* 1: time every kernel launch with CUDA events on the handle's stream (mgbx_kernel_stats) */
+  int32_t persistent;        /* 1 (default): each PCG solve is ONE cooperative persistent kernel (one CTA per SM, grid barriers) */
+  int32_t tail_max;          /* V-cycle levels with <= this many unknowns run inside CTA 0 of that kernel (default 1200) */
+  double pcg_rtol_final;     /* relative residual during the finalize pass (stopping_exact), default 1e-13 */
 } mgbx_config;
 
 /* options of one mgb_step (src/mgb.jl:16-30; defaults src/mgb.jl:360-363) */
@@ -173,6 +178,9 @@ int mgbx_scalars(mgbx_handle *h, int which, mgbx_scalars_out *out);
 
 /* phase I (src/mgb.jl:417-566) */
 int mgbx_phase1_init(mgbx_handle *h, int32_t *needs_phase1, double *b, double *zabsmax);
+/* the feasibility AMG may be given at create time (amg[1]) or attached only when mgbx_phase1_init reports that
+ * phase I is needed (saves its upload for feasible starts); after attaching, call mgbx_phase1_init again */
+int mgbx_attach_feasibility(mgbx_handle *h, const mgbx_amg *feas);
 int mgbx_set_feasibility_box(mgbx_handle *h, double b, double Rbox);
 int mgbx_reset_feasibility_state(mgbx_handle *h);    /* z_feas <- (z_main, initial slack): no warm start between box rounds */
 int mgbx_handoff(mgbx_handle *h);                    /* z_main <- leading block of z_feas */

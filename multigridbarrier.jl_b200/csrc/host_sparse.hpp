@@ -144,6 +144,22 @@ inline HostCsr spgemm_symbolic(const HostCsr &A, const HostCsr &B) {
   return C;
 }
 
+// A*B with values (sorted columns per row); used once at setup to compose R_fine[l] = R_fine[l+1]*T[l]
+inline HostCsr spgemm_numeric_host(const HostCsr &A, const HostCsr &B) {
+  HostCsr C = spgemm_symbolic(A, B);
+  C.val.assign(C.idx.size(), 0.0);
+  std::vector<int64_t> posmap(B.cols, -1);
+  for (int64_t i = 0; i < A.rows; ++i) {
+    for (int64_t k = C.ptr[i]; k < C.ptr[i + 1]; ++k) posmap[C.idx[k]] = k;
+    for (int64_t k = A.ptr[i]; k < A.ptr[i + 1]; ++k) {
+      const int64_t a = A.idx[k];
+      const double av = A.val[k];
+      for (int64_t q = B.ptr[a]; q < B.ptr[a + 1]; ++q) C.val[posmap[B.idx[q]]] += av * B.val[q];
+    }
+  }
+  return C;
+}
+
 inline int64_t find_in_row(const HostCsr &A, int64_t row, int32_t col) {
   const int32_t *b = A.idx.data() + A.ptr[row], *e = A.idx.data() + A.ptr[row + 1];
   const int32_t *it = std::lower_bound(b, e, col);

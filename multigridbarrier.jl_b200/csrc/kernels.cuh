@@ -289,12 +289,13 @@ __device__ __forceinline__ void spd_inverse(double *M, int m) {
     }
 }
 
-template <int MODE>
+// NDT >= nD bounds the per-thread arrays (y, F1, F2 = NDT^2 doubles) so that they stay in registers / L1
+template <int MODE, int NDT>
 __global__ void __launch_bounds__(kRedThreads) k_node(NodeParams P) {
   double red[4] = {0.0, 0.0, 0.0, -INFINITY};
   const int op[4] = {0, 0, 0, 1};
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += (int64_t)gridDim.x * blockDim.x) {
-    double y[MGBX_MAX_ND];
+    double y[NDT];
     node_Dz(P, i, y);
     if (MODE == NODE_SLACK) {
       const double s = node_slack(P.cd, P.n, i, y);
@@ -305,7 +306,7 @@ __global__ void __launch_bounds__(kRedThreads) k_node(NodeParams P) {
     const int nD = P.nD;
     const double bwi = P.bw ? P.bw[i] : 1.0;
     const bool active = !(P.bw && bwi == 0.0);
-    double F1[MGBX_MAX_ND];
+    double F1[NDT];
     if (MODE == NODE_F01) {
       double F0 = 0.0;
       if (active) F0 = node_eval(P.cd, P.n, i, y, 1, F1, nullptr);
@@ -323,7 +324,7 @@ __global__ void __launch_bounds__(kRedThreads) k_node(NodeParams P) {
       red[1] += wi * lin;
       if (!isfinite(F0)) red[2] += 1.0;
     } else {   // NODE_F2
-      double F2[MGBX_MAX_ND * MGBX_MAX_ND];
+      double F2[NDT * NDT];
       const double sc = P.bw ? bwi : P.inv_n;
       if (active) {
         node_eval(P.cd, P.n, i, y, 2, F1, F2);
@@ -337,7 +338,7 @@ __global__ void __launch_bounds__(kRedThreads) k_node(NodeParams P) {
         for (int a = 0; a < nK; ++a)
           for (int b = a; b < nK; ++b, ++q) P.Hn[i + (int64_t)q * P.n] = F2[P.Krow[a] * nD + P.Krow[b]];
       } else {
-        double hEE[16], hKE[MGBX_MAX_ND * 4];
+        double hEE[16], hKE[NDT * 4];
         for (int k = 0; k < nE * nE; ++k) hEE[k] = 0.0;
         for (int k = 0; k < nK * nE; ++k) hKE[k] = 0.0;
         for (int j = 0; j < nD; ++j) {

@@ -13,6 +13,7 @@
 // they only exchange scalars with this library.
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -24,6 +25,7 @@
 
 #include "host_sparse.hpp"
 #include "kernels.cuh"
+#include "solver_kernels.cuh"
 
 using namespace mgbx;
 
@@ -39,9 +41,10 @@ static thread_local std::string g_last_error;
 
 // kernel classes for the optional per-class device timing (cfg.profile) and launch statistics
 enum KClass { KC_NODE_F01 = 0, KC_NODE_F2, KC_BLOCKGRAD, KC_BLOCKHESS, KC_GATHER, KC_SPMV, KC_JACOBI, KC_SPGEMM, KC_VEC, KC_COND,
-              KC_DENSE, KC_COUNT };
+              KC_DENSE, KC_PCG, KC_COUNT };
 static const char *kKClassNames[KC_COUNT] = {"node_f01", "node_f2", "blockgrad", "blockhess", "csr_gather", "spmv", "jacobi",
-                                             "spgemm", "vector", "condense", "dense"};
+                                             "spgemm", "vector", "condense", "dense", "pcg_persistent"};
+enum { STAGE_F01 = -1, STAGE_F2 = -2, STAGE_SOLVE = -3 };
 #define LAUNCH(kc, ...)   \
   do {                    \
     pre_launch(kc);       \
@@ -59,6 +62,16 @@ namespace {
 
 struct ArgError : std::runtime_error {
   using std::runtime_error::runtime_error;
+};
+
+struct HostTimer {
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  double lap() {
+    auto t1 = std::chrono::steady_clock::now();
+    double s = std::chrono::duration<double>(t1 - t0).count();
+    t0 = t1;
+    return s;
+  }
 };
 
 inline unsigned int nblk(int64_t work, int threads = 256) { return (unsigned int)((work + threads - 1) / threads); }
@@ -109,6 +122,74 @@ DevCsr upload_csr(Pool &pool, const HostCsr &H, cudaStream_t s, bool with_values
   return D;
 }
 
+
+// Host term lists (CSR-like: ptr over outputs, 64-bit sources, optional weights) -> sliced-ELL on the device.
+SellPlan upload_sell(Pool &pool, const std::vector<int64_t> &ptr, const std::vector<int64_t> &src, const std::vector<double> *w,
+                     cudaStream_t s) {
+  SellPlan P;
+  P.nout = (int64_t)ptr.size() - 1;
+  P.nslices = (P.nout + 31) / 32;
+  P.nterms = ptr.back();
+  std::vector<int64_t> sptr(P.nslices + 1, 0);
+  std::vector<int32_t> cnt(P.nout);
+  for (int64_t sl = 0; sl < P.nslices; ++sl) {
+    int64_t wmax = 0;
+    for (int64_t nz = sl * 32; nz < std::min(P.nout, sl * 32 + 32); ++nz) {
+      cnt[nz] = (int32_t)(ptr[nz + 1] - ptr[nz]);
+      wmax = std::max<int64_t>(wmax, cnt[nz]);
+    }
+    sptr[sl + 1] = sptr[sl] + 32 * wmax;
+  }
+  const int64_t total = sptr[P.nslices];
+  std::vector<int32_t> hs(total, 0);
+  std::vector<double> hw(w ? total : 0, 0.0);
+  for (int64_t nz = 0; nz < P.nout; ++nz) {
+    const int64_t off = sptr[nz >> 5] + (nz & 31);
+    for (int64_t k = ptr[nz]; k < ptr[nz + 1]; ++k) {
+      if (src[k] > INT32_MAX) throw std::runtime_error("gather plan: source index exceeds 32 bits");
+      hs[off + 32 * (k - ptr[nz])] = (int32_t)src[k];
+      if (w) hw[off + 32 * (k - ptr[nz])] = (*w)[k];
+    }
+  }
+  P.sptr = pool.upload<int64_t>(sptr.data(), sptr.size(), s);
+  P.cnt = pool.upload<int32_t>(cnt.data(), cnt.size(), s);
+  P.src = pool.upload<int32_t>(hs.data(), hs.size(), s);
+  P.w = w ? pool.upload<double>(hw.data(), hw.size(), s) : nullptr;
+  CK(cudaStreamSynchronize(s));
+  return P;
+}
+
+// Term list of the sparse product C = Lm * Rm, built on the device (one thread per non-zero of C; two passes).
+SellPlan device_product_plan(Pool &pool, const DevCsr &Lm, const DevCsr &Rm, const DevCsr &C, bool variable_left, cudaStream_t s) {
+  SellPlan P;
+  P.nout = C.nnz;
+  P.nslices = (P.nout + 31) / 32;
+  if (Lm.nnz > INT32_MAX || Rm.nnz > INT32_MAX || C.rows > INT32_MAX) throw std::runtime_error("product plan: index exceeds 32 bits");
+  if (P.nout == 0) return P;
+  int32_t *rowof = nullptr, *width = nullptr;
+  CK(cudaMalloc(&rowof, sizeof(int32_t) * P.nout));
+  CK(cudaMalloc(&width, sizeof(int32_t) * P.nslices));
+  P.cnt = pool.alloc<int32_t>(P.nout);
+  k_csr_rows<<<nblk(C.rows), 256, 0, s>>>(C, rowof);
+  k_prod_plan<0><<<nblk(P.nslices * 32), 256, 0, s>>>(Lm, Rm, C, rowof, variable_left ? 1 : 0, P, width);
+  std::vector<int32_t> hwid(P.nslices);
+  CK(cudaMemcpyAsync(hwid.data(), width, sizeof(int32_t) * P.nslices, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  std::vector<int64_t> sptr(P.nslices + 1, 0);
+  for (int64_t sl = 0; sl < P.nslices; ++sl) sptr[sl + 1] = sptr[sl] + 32 * (int64_t)hwid[sl];
+  const int64_t total = sptr[P.nslices];
+  P.nterms = total;
+  P.sptr = pool.upload<int64_t>(sptr.data(), sptr.size(), s);
+  P.src = pool.zeros<int32_t>(total, s);
+  P.w = pool.zeros<double>(total, s);
+  k_prod_plan<1><<<nblk(P.nslices * 32), 256, 0, s>>>(Lm, Rm, C, rowof, variable_left ? 1 : 0, P, width);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(s));
+  cudaFree(rowof);
+  cudaFree(width);
+  return P;
+}
+
 // ------------------------------------------------------------------------------------------------
 // linear systems: top-level assembly plan + Galerkin hierarchy
 // ------------------------------------------------------------------------------------------------
@@ -116,9 +197,8 @@ struct SysLevel {
   int64_t m = 0;
   DevCsr A;
   DevCsr T, Tt, AT;          // T: this level (rows) <- next coarser level (cols)
-  // Galerkin gather plans: AT = A*T  and  A_coarse = T'*AT, one fixed-order gather kernel each
-  int64_t *g1ptr = nullptr, *g1src = nullptr, *g2ptr = nullptr, *g2src = nullptr;
-  double *g1w = nullptr, *g2w = nullptr;
+  // Galerkin gather plans: AT = A*T  and  A_coarse = T'*AT, one fixed-order sliced-ELL gather each
+  SellPlan s1, s2;
   bool has_coarser = false, T_identity = false;
   double *dinv = nullptr, *diag = nullptr;
   double *b = nullptr, *x = nullptr, *x2 = nullptr, *r = nullptr;   // V-cycle work
@@ -129,20 +209,28 @@ struct SysLevel {
 
 struct System {
   bool condensed = false;
+  int ltop = 0;                      // AMG level of lev[0]
   std::vector<int> kept, elim;       // state variable ids
-  std::vector<SysLevel> lev;         // lev[k] <-> AMG level L-1-k
+  std::vector<SysLevel> lev;         // lev[k] <-> AMG level ltop-k
   PairList pl;
   int nK = 0, nE = 0;
   int Krow[MGBX_MAX_ND], Erow[MGBX_MAX_ND];
-  int64_t *gptr = nullptr, *gidx = nullptr;
-  double *gw = nullptr;
+  SellPlan top;                      // element blocks -> top-level CSR values
   double *Hblk = nullptr;
   int64_t hblk_size = 0;
   int cut = -1;                      // V-cycle bottom (dense inverse) level index, -1: none
   // PCG work at the largest size
   double *pc_r = nullptr, *pc_z = nullptr, *pc_p = nullptr, *pc_Ap = nullptr, *pc_x = nullptr, *pc_b = nullptr;
-  std::map<int, cudaGraphExec_t> graphs;        // captured PCG iteration per top level
+  std::map<int, cudaGraphExec_t> graphs;        // captured PCG iteration per top level (non-persistent path)
   std::map<int, int64_t> graph_launches;
+  // persistent solve kernel: one plan per top level
+  struct PcgDev {
+    PcgPlan host;
+    PcgPlan *dev = nullptr;
+  };
+  std::map<int, PcgDev> pplans;
+  double *pc_p2 = nullptr, *pcg_partials = nullptr, *pcg_out = nullptr;
+  unsigned int *pcg_bar = nullptr;
 };
 
 struct Amg {
@@ -164,7 +252,7 @@ struct Amg {
   std::vector<double *> chain2;
   double *x = nullptr, *xn = nullptr, *g = nullptr, *gn = nullptr, *dir = nullptr, *rhs = nullptr, *tmp = nullptr, *xbest = nullptr,
          *gbest = nullptr;
-  std::unique_ptr<System> sys_cond, sys_full;
+  std::unique_ptr<System> sys_cond, sys_coarse, sys_hook;   // fine-level (condensed), levels < L-1, parity hooks
   double fb = 0.0, fR = 0.0;
 };
 
@@ -203,9 +291,21 @@ struct mgbx_handle {
   };
   std::vector<Pending> ev_pending;
   cudaEvent_t ev_cur = nullptr;
+  int pcg_grid = 0;
+  double cur_rtol2 = 1e-22;
 };
 
 namespace {
+
+
+// per-node kernel, instantiated for array bounds NDT in {4, 6, 8, 12}
+template <int MODE>
+void launch_node(const NodeParams &P, unsigned int grid, cudaStream_t s) {
+  if (P.nD <= 4) k_node<MODE, 4><<<grid, kRedThreads, 0, s>>>(P);
+  else if (P.nD <= 6) k_node<MODE, 6><<<grid, kRedThreads, 0, s>>>(P);
+  else if (P.nD <= 8) k_node<MODE, 8><<<grid, kRedThreads, 0, s>>>(P);
+  else k_node<MODE, MGBX_MAX_ND><<<grid, kRedThreads, 0, s>>>(P);
+}
 
 struct Engine {
   mgbx_handle *h;
@@ -218,12 +318,28 @@ struct Engine {
       for (auto &p : h->ev_pending) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, p.a, p.b);
-        h->kc_ms[p.kc] += ms;
+        if (p.kc >= 0) h->kc_ms[p.kc] += ms;
+        else if (h->res) {   // stage timers of the current mgbx_step
+          if (p.kc == STAGE_F01) h->res->ms_f01 += ms;
+          else if (p.kc == STAGE_F2) h->res->ms_f2 += ms;
+          else if (p.kc == STAGE_SOLVE) h->res->ms_solve += ms;
+        }
         h->ev_free.push_back(p.a);
         h->ev_free.push_back(p.b);
       }
       h->ev_pending.clear();
     }
+  }
+  // stage timing without extra host synchronisation: the event pair is resolved at the next sync()
+  cudaEvent_t stage_begin() {
+    cudaEvent_t e = get_event();
+    cudaEventRecord(e, s);
+    return e;
+  }
+  void stage_end(int stage, cudaEvent_t a) {
+    cudaEvent_t b = get_event();
+    cudaEventRecord(b, s);
+    h->ev_pending.push_back({stage, a, b});
   }
   cudaEvent_t get_event() {
     if (!h->ev_free.empty()) {
@@ -368,23 +484,18 @@ struct Engine {
   // ---------------------------------------------------------------- f0 + f1 at level J
   // zbase: broken state the level correction is added to; x: level-J coefficients; gout: level-J gradient
   EvalOut eval_f01(Amg &A, int J, double t, const double *zbase, const double *x, double *gout, bool use_bw = true) {
-    cudaEventRecord(h->ev0, s);
+    cudaEvent_t st = stage_begin();
     prolong_to_fine(A, J, x, zbase, A.zf);
     NodeParams P = node_params(A, t);
     if (!use_bw) P.bw = nullptr;
-    LAUNCH(KC_NODE_F01, k_node<NODE_F01><<<red_grid(A.n), kRedThreads, 0, s>>>(P));
+    LAUNCH(KC_NODE_F01, launch_node<NODE_F01>(P, red_grid(A.n), s));
     ElemParams E = elem_params(A);
     LAUNCH(KC_BLOCKGRAD, k_blockgrad<<<nblk((int64_t)A.nu * A.n), 256, 0, s>>>(E, A.G, A.gb, A.nu));
     restrict_from_fine(A, J, A.gb, gout);
     LAUNCH(KC_VEC, k_dot2<<<red_grid(A.m[J]), kRedThreads, 0, s>>>(A.m[J], gout, nullptr, h->partials, h->ticket, h->dscal + 4));
-    cudaEventRecord(h->ev1, s);
+    stage_end(STAGE_F01, st);
     fetch(8);
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
-    if (h->res) {
-      h->res->ms_f01 += ms;
-      h->res->f01_evals++;
-    }
+    if (h->res) h->res->f01_evals++;
     EvalOut o;
     const double bar = (use_bw && A.bw) ? h->hscal[0] : h->hscal[0] * (1.0 / (double)A.n);
     o.lin = h->hscal[1];
@@ -403,6 +514,8 @@ struct Engine {
   void dense_apply(SysLevel &Lv, const double *b, double *x);      // x = A^{-1} b via factor (direct)
   void vcycle(System &S, int k);
   void pcg_iteration(System &S, int ktop);
+  System::PcgDev &pcg_plan(System &S, int ktop);
+  int pcg_persistent(System &S, int ktop, const double *b, double *x);
   int pcg(System &S, int ktop, const double *b, double *x);
   int solve_compact(System &S, int ktop, const double *b, double *x);
   int solve(Amg &A, System &S, int J, const double *g, double *dir);
@@ -427,12 +540,26 @@ struct Engine {
 // -------------------------------------------------------------------------------------------------
 // host-side plan construction
 // -------------------------------------------------------------------------------------------------
-std::unique_ptr<System> build_system(mgbx_handle *h, Amg &A, bool condensed) {
+// Build the index plans of one linear-system family.  ltop: the AMG level the top matrix lives on.  The top
+// matrix is assembled directly from the element blocks with R_top = R_fine[ltop] (= R_fine[L-1] * T[L-2] ... T[ltop]),
+// every coarser level by Galerkin gather plans.
+std::unique_ptr<System> build_system(mgbx_handle *h, Amg &A, bool condensed, int ltop) {
   auto S = std::make_unique<System>();
   Pool &pool = h->pool;
   cudaStream_t s = h->stream;
-  const int L = A.L;
+  const int L = ltop + 1;            // levels 0..ltop take part
   S->condensed = condensed;
+  S->ltop = ltop;
+  if (condensed && ltop != A.L - 1) throw std::runtime_error("internal: condensation only at the fine level");
+  // prolongation from the top level of this system to the broken fine space
+  HostCsr Rtop_store;
+  const HostCsr *Rtop_p = &A.hRL;
+  if (ltop != A.L - 1) {
+    Rtop_store = A.hRL;
+    for (int l = A.L - 2; l >= ltop; --l) Rtop_store = spgemm_numeric_host(Rtop_store, A.hT[l]);
+    Rtop_p = &Rtop_store;
+  }
+  const HostCsr &Rtop = *Rtop_p;
   // which variables can be eliminated node-locally at the fine level: R block == identity and every D row is :id
   std::vector<char> is_elim(A.nu, 0);
   if (condensed) {
@@ -446,7 +573,7 @@ std::unique_ptr<System> build_system(mgbx_handle *h, Amg &A, bool condensed) {
           if (A.D_op[j] >= 0) idonly = false;
         }
       if (!any || !idonly) continue;
-      HostCsr blk = submatrix(A.hRL, (int64_t)v * A.n, (int64_t)(v + 1) * A.n, c0, c1);
+      HostCsr blk = submatrix(Rtop, (int64_t)v * A.n, (int64_t)(v + 1) * A.n, c0, c1);
       if (is_identity(blk)) is_elim[v] = 1;
     }
     int ne = 0;
@@ -502,8 +629,11 @@ std::unique_ptr<System> build_system(mgbx_handle *h, Amg &A, bool condensed) {
     const int v = S->kept[q];
     for (int64_t c = A.voff[L - 1][v]; c < A.voff[L - 1][v + 1]; ++c) colmap[c] = S->lev[0].off[q] + (c - A.voff[L - 1][v]);
   }
-  HostCsr Einc = element_incidence(A.hRL, A.N, A.p, used, A.n, colmap, mtop);
+  HostTimer tm;
+  const bool vb = h->cfg.verbose > 0;
+  HostCsr Einc = element_incidence(Rtop, A.N, A.p, used, A.n, colmap, mtop);
   HostCsr pat = plan_pattern(Einc);
+  if (vb) fprintf(stderr, "[mgbx] build_system(cond=%d): pattern m=%lld nnz=%lld %.3fs\n", (int)condensed, (long long)mtop, (long long)pat.nnz(), tm.lap());
   // gather lists: for each nz of the pattern, the Hblk entries (and weights) that sum into it
   const int p = A.p;
   const int64_t pp = (int64_t)p * p;
@@ -518,17 +648,17 @@ std::unique_ptr<System> build_system(mgbx_handle *h, Amg &A, bool condensed) {
         for (int64_t e = 0; e < A.N; ++e)
           for (int r = 0; r < p; ++r) {
             const int64_t ra = (int64_t)va * A.n + e * p + r;
-            for (int64_t ka = A.hRL.ptr[ra]; ka < A.hRL.ptr[ra + 1]; ++ka) {
-              const int64_t row = colmap[A.hRL.idx[ka]];
+            for (int64_t ka = Rtop.ptr[ra]; ka < Rtop.ptr[ra + 1]; ++ka) {
+              const int64_t row = colmap[Rtop.idx[ka]];
               if (row < 0) continue;
               for (int c = 0; c < p; ++c) {
                 const int64_t rb = (int64_t)vb * A.n + e * p + c;
-                for (int64_t kb = A.hRL.ptr[rb]; kb < A.hRL.ptr[rb + 1]; ++kb) {
-                  const int64_t col = colmap[A.hRL.idx[kb]];
+                for (int64_t kb = Rtop.ptr[rb]; kb < Rtop.ptr[rb + 1]; ++kb) {
+                  const int64_t col = colmap[Rtop.idx[kb]];
                   if (col < 0) continue;
                   const int64_t nz = find_in_row(pat, row, (int32_t)col);
                   if (nz < 0) throw std::runtime_error("internal: assembly pattern misses an entry");
-                  fn(nz, ((int64_t)pr * A.N + e) * pp + (int64_t)r * p + c, A.hRL.val[ka] * A.hRL.val[kb]);
+                  fn(nz, ((int64_t)pr * A.N + e) * pp + (int64_t)r * p + c, Rtop.val[ka] * Rtop.val[kb]);
                 }
               }
             }
@@ -548,18 +678,17 @@ std::unique_ptr<System> build_system(mgbx_handle *h, Amg &A, bool condensed) {
       gidx[q] = src;
       if (!unit) gw[q] = wgt;
     });
-    S->gptr = pool.upload<int64_t>(cnt.data(), cnt.size(), s);
-    S->gidx = pool.upload<int64_t>(gidx.data(), gidx.size(), s);
-    S->gw = unit ? nullptr : pool.upload<double>(gw.data(), gw.size(), s);
-    CK(cudaStreamSynchronize(s));
+    if (S->hblk_size > INT32_MAX) throw std::runtime_error("element block array exceeds 32-bit gather indices");
+    S->top = upload_sell(pool, cnt, gidx, unit ? nullptr : &gw, s);
   }
   S->Hblk = pool.alloc<double>(S->hblk_size);
+  if (vb) fprintf(stderr, "[mgbx]   gather lists %.3fs\n", tm.lap());
   // hierarchy patterns
   HostCsr cur = pat;
   for (int k = 0; k < nlev; ++k) {
     SysLevel &Lv = S->lev[k];
     const int l = L - 1 - k;
-    Lv.A = upload_csr(pool, cur, s, false);
+    if (k == 0) Lv.A = upload_csr(pool, cur, s, false);   // deeper levels were set by their parent below
     Lv.spmv_group = Engine::group_for(Lv.A);
     Lv.dinv = pool.alloc<double>(Lv.m);
     Lv.diag = pool.alloc<double>(Lv.m);
@@ -576,58 +705,67 @@ std::unique_ptr<System> build_system(mgbx_handle *h, Amg &A, bool condensed) {
       Lv.has_coarser = true;
       Lv.T_identity = is_identity(Tk);
       HostCsr Ttk = transpose(Tk);
-      HostCsr ATp = spgemm_symbolic(cur, Tk);
-      HostCsr nxt = spgemm_symbolic(Ttk, ATp);
       Lv.T = upload_csr(pool, Tk, s);
       Lv.Tt = upload_csr(pool, Ttk, s);
-      Lv.AT = upload_csr(pool, ATp, s, false);
-      if (!Lv.T_identity) {
-        GatherPlan g1 = product_plan(cur, Tk, ATp, true);
-        GatherPlan g2 = product_plan(Ttk, ATp, nxt, false);
-        Lv.g1ptr = pool.upload<int64_t>(g1.ptr.data(), g1.ptr.size(), s);
-        Lv.g1src = pool.upload<int64_t>(g1.src.data(), g1.src.size(), s);
-        Lv.g1w = pool.upload<double>(g1.w.data(), g1.w.size(), s);
-        Lv.g2ptr = pool.upload<int64_t>(g2.ptr.data(), g2.ptr.size(), s);
-        Lv.g2src = pool.upload<int64_t>(g2.src.data(), g2.src.size(), s);
-        Lv.g2w = pool.upload<double>(g2.w.data(), g2.w.size(), s);
-        CK(cudaStreamSynchronize(s));
+      if (Lv.T_identity) {
+        S->lev[k + 1].A = Lv.A;   // same matrix: the coarser level aliases this one
+      } else {
+        HostCsr ATp = spgemm_symbolic(cur, Tk);
+        HostCsr nxt = spgemm_symbolic(Ttk, ATp);
+        const double t_sym = tm.lap();
+        Lv.AT = upload_csr(pool, ATp, s, false);
+        S->lev[k + 1].A = upload_csr(pool, nxt, s, false);
+        Lv.s1 = device_product_plan(pool, Lv.A, Lv.T, Lv.AT, true, s);
+        Lv.s2 = device_product_plan(pool, Lv.Tt, Lv.AT, S->lev[k + 1].A, false, s);
+        cur = std::move(nxt);
+        if (vb)
+          fprintf(stderr, "[mgbx]   level %d: m=%lld -> %lld, nnz(A_c)=%lld, plan entries %lld + %lld, symbolic %.3fs plans %.3fs\n", k,
+                  (long long)Lv.m, (long long)S->lev[k + 1].m, (long long)cur.nnz(), (long long)Lv.s1.nterms, (long long)Lv.s2.nterms, t_sym,
+                  tm.lap());
       }
-      cur = std::move(nxt);
     }
   }
-  // V-cycle cut
+  // V-cycle cut: the first level small enough for the shared-memory dense inverse
   S->cut = -1;
   for (int k = 0; k < nlev; ++k)
     if (S->lev[k].m <= h->cfg.coarse_max) {
       S->cut = k;
       break;
     }
-  if (S->cut < 0 && S->lev[nlev - 1].m <= 4096) S->cut = nlev - 1;
   const int64_t mx = S->lev[0].m;
   S->pc_r = pool.alloc<double>(mx);
   S->pc_z = pool.alloc<double>(mx);
   S->pc_p = pool.alloc<double>(mx);
+  S->pc_p2 = pool.alloc<double>(mx);
   S->pc_Ap = pool.alloc<double>(mx);
   S->pc_x = pool.alloc<double>(mx);
   S->pc_b = pool.alloc<double>(mx);
+  S->pcg_partials = pool.zeros<double>(3 * (size_t)kPcgMaxGrid, s);
+  S->pcg_out = pool.zeros<double>(8, s);
+  S->pcg_bar = pool.zeros<unsigned int>(4, s);
   CK(cudaStreamSynchronize(s));
   return S;
 }
 
 System &Engine::system_for(Amg &A, int J) {
   const bool fine = (J == A.L - 1);
-  if (fine && h->cfg.condense) {
-    if (!A.sys_cond) A.sys_cond = build_system(h, A, true);
-    return *A.sys_cond;
+  if (fine) {
+    if (h->cfg.condense) {
+      if (!A.sys_cond) A.sys_cond = build_system(h, A, true, A.L - 1);
+      return *A.sys_cond;
+    }
+    if (!A.sys_hook) A.sys_hook = build_system(h, A, false, A.L - 1);
+    return *A.sys_hook;
   }
-  if (!A.sys_full) A.sys_full = build_system(h, A, false);
-  return *A.sys_full;
+  // coarse Newton levels (the recovery path of mgb_step): assembled directly at level L-2, Galerkin below
+  if (!A.sys_coarse) A.sys_coarse = build_system(h, A, false, A.L - 2);
+  return *A.sys_coarse;
 }
 
 // Evaluate the node Hessians at zbase + R_J x and fill the system matrices from the top level down to
 // level index ktop (= L-1-J), then the preconditioner hierarchy below it.
 void Engine::assemble(Amg &A, System &S, int J, double t, const double *zbase, const double *x) {
-  cudaEventRecord(h->ev0, s);
+  cudaEvent_t st = stage_begin();
   prolong_to_fine(A, J, x, zbase, A.zf);
   NodeParams P = node_params(A, t);
   P.nK = S.nK;
@@ -639,23 +777,17 @@ void Engine::assemble(Amg &A, System &S, int J, double t, const double *zbase, c
   P.Hn = A.Hn;
   P.hEEinv = A.hEEinv;
   P.hKE = A.hKE;
-  LAUNCH(KC_NODE_F2, k_node<NODE_F2><<<red_grid(A.n), kRedThreads, 0, s>>>(P));
+  LAUNCH(KC_NODE_F2, launch_node<NODE_F2>(P, red_grid(A.n), s));
   ElemParams E = elem_params(A);
   E.nK = S.nK;
   for (int j = 0; j < S.nK; ++j) E.Krow[j] = S.Krow[j];
   LAUNCH(KC_BLOCKHESS, k_blockhess<<<nblk(S.hblk_size), 256, 0, s>>>(E, S.pl, A.Hn, S.Hblk));
   SysLevel &top = S.lev[0];
-  LAUNCH(KC_GATHER, k_csr_gather<<<nblk(top.A.nnz), 256, 0, s>>>(top.A.nnz, S.gptr, S.gidx, S.gw, S.Hblk, top.A.val));
-  const int ktop = A.L - 1 - J;
+  LAUNCH(KC_GATHER, k_sell_gather<<<nblk(top.A.nnz), 256, 0, s>>>(S.top, S.Hblk, top.A.val));
+  const int ktop = S.ltop - J;
   setup_hierarchy(A, S, ktop);
-  cudaEventRecord(h->ev1, s);
-  sync();
-  float ms = 0.f;
-  cudaEventElapsedTime(&ms, h->ev0, h->ev1);
-  if (h->res) {
-    h->res->ms_f2 += ms;
-    h->res->f2_evals++;
-  }
+  stage_end(STAGE_F2, st);
+  if (h->res) h->res->f2_evals++;
 }
 
 void Engine::setup_hierarchy(Amg &A, System &S, int ktop) {
@@ -667,11 +799,9 @@ void Engine::setup_hierarchy(Amg &A, System &S, int ktop) {
   for (int k = 0; k < kend; ++k) {
     SysLevel &Lv = S.lev[k];
     SysLevel &Lc = S.lev[k + 1];
-    if (Lv.T_identity) {
-      copy(Lc.A.val, Lv.A.val, Lv.A.nnz);
-    } else {
-      LAUNCH(KC_SPGEMM, k_csr_gather<<<nblk(Lv.AT.nnz), 256, 0, s>>>(Lv.AT.nnz, Lv.g1ptr, Lv.g1src, Lv.g1w, Lv.A.val, Lv.AT.val));
-      LAUNCH(KC_SPGEMM, k_csr_gather<<<nblk(Lc.A.nnz), 256, 0, s>>>(Lc.A.nnz, Lv.g2ptr, Lv.g2src, Lv.g2w, Lv.AT.val, Lc.A.val));
+    if (!Lv.T_identity) {   // an identity transfer aliases the same matrix
+      LAUNCH(KC_SPGEMM, k_sell_gather<<<nblk(Lv.AT.nnz), 256, 0, s>>>(Lv.s1, Lv.A.val, Lv.AT.val));
+      LAUNCH(KC_SPGEMM, k_sell_gather<<<nblk(Lc.A.nnz), 256, 0, s>>>(Lv.s2, Lv.AT.val, Lc.A.val));
     }
   }
   if (direct) {
@@ -682,7 +812,12 @@ void Engine::setup_hierarchy(Amg &A, System &S, int ktop) {
     SysLevel &Lv = S.lev[k];
     LAUNCH(KC_VEC, k_l1diag<<<nblk(Lv.m), 256, 0, s>>>(Lv.A, Lv.dinv, Lv.diag));
   }
-  if (S.cut >= 0 && S.cut >= ktop) dense_factor(S, S.lev[S.cut], true);
+  if (S.cut >= 0 && S.cut >= ktop) {
+    SysLevel &Lc = S.lev[S.cut];
+    const int m = (int)Lc.m;
+    if (!Lc.dense_inv) Lc.dense_inv = h->pool.alloc<double>((size_t)m * m);
+    LAUNCH(KC_DENSE, k_coarse_inverse<<<1, 1024, coarse_inverse_smem(m), s>>>(Lc.A, Lc.dense_inv));
+  }
 }
 
 void Engine::dense_factor(System &S, SysLevel &Lv, bool want_inverse) {
@@ -692,7 +827,6 @@ void Engine::dense_factor(System &S, SysLevel &Lv, bool want_inverse) {
     Lv.dense = h->pool.alloc<double>((size_t)m * m);
     Lv.dscale = h->pool.alloc<double>(m);
   }
-  if (want_inverse && !Lv.dense_inv) Lv.dense_inv = h->pool.alloc<double>((size_t)m * m);
   zero(Lv.dense, (int64_t)m * m);
   LAUNCH(KC_DENSE, k_dense_scale_diag<<<nblk(m), 256, 0, s>>>(Lv.A, Lv.dscale));
   LAUNCH(KC_DENSE, k_csr_to_dense<<<nblk(m), 256, 0, s>>>(Lv.A, Lv.dscale, Lv.dense));
@@ -706,9 +840,7 @@ void Engine::dense_factor(System &S, SysLevel &Lv, bool want_inverse) {
       LAUNCH(KC_DENSE, k_chol_syrk<<<nt * (nt + 1) / 2, 256, 0, s>>>(Lv.dense, m, k0));
     }
   }
-  if (want_inverse) {
-    LAUNCH(KC_DENSE, k_chol_solve<<<m, 256, sizeof(double) * m, s>>>(Lv.dense, m, Lv.dense_inv, 1));
-  }
+  (void)want_inverse;
 }
 
 // x = A^{-1} b through the scaled Cholesky factor (one right-hand side), uses Lv.r as scratch
@@ -723,10 +855,8 @@ void Engine::vcycle(System &S, int k) {
   SysLevel &Lv = S.lev[k];
   const int nlev = (int)S.lev.size();
   if (k == S.cut) {
-    // x = D Minv D b
-    LAUNCH(KC_VEC, k_mul<<<nblk(Lv.m), 256, 0, s>>>(Lv.m, Lv.b, Lv.dscale, Lv.r));
-    LAUNCH(KC_DENSE, k_dense_symv<<<nblk(Lv.m * 32), 256, 0, s>>>(Lv.dense_inv, (int)Lv.m, Lv.r, Lv.x2));
-    LAUNCH(KC_VEC, k_mul<<<nblk(Lv.m), 256, 0, s>>>(Lv.m, Lv.x2, Lv.dscale, Lv.x));
+    // x = A^{-1} b through the explicit inverse (diagonal scaling already folded in by k_coarse_inverse)
+    LAUNCH(KC_DENSE, k_dense_symv<<<nblk(Lv.m * 32), 256, 0, s>>>(Lv.dense_inv, (int)Lv.m, Lv.b, Lv.x));
     return;
   }
   const bool bottom = (k == nlev - 1);
@@ -788,7 +918,88 @@ void Engine::pcg_iteration(System &S, int ktop) {
 }
 
 // Preconditioned CG on lev[ktop]; returns the iteration count (negative: breakdown)
+// plan of the persistent solve kernel for the hierarchy below lev[ktop] (built once, lives on the device)
+System::PcgDev &Engine::pcg_plan(System &S, int ktop) {
+  auto it = S.pplans.find(ktop);
+  if (it != S.pplans.end()) return it->second;
+  System::PcgDev &D = S.pplans[ktop];
+  PcgPlan &P = D.host;
+  memset(&P, 0, sizeof(P));
+  const int nlev = (int)S.lev.size();
+  const int kend = (S.cut >= 0) ? std::max(S.cut, ktop) : nlev - 1;
+  std::vector<int> act;
+  for (int k = ktop; k <= kend; ++k) {
+    if (k < kend && S.lev[k].T_identity) continue;   // same matrix as the next level
+    act.push_back(k);
+  }
+  P.nlev = (int)act.size();
+  P.nbig = 0;
+  for (int q = 0; q < P.nlev; ++q)
+    if (S.lev[act[q]].m > h->cfg.tail_max) P.nbig = q + 1;
+  P.nbig = std::max(P.nbig, 1);
+  P.bottom_dense = (S.cut >= 0 && act.back() == S.cut) ? 1 : 0;
+  P.nu = std::max(1, h->cfg.smoother_sweeps);
+  P.nu_bottom = 30;
+  P.maxit = h->cfg.pcg_maxit;
+  P.rtol2 = h->cfg.pcg_rtol * h->cfg.pcg_rtol;
+  for (int q = 0; q < P.nlev; ++q) {
+    SysLevel &Lv = S.lev[act[q]];
+    PLevel &pl = P.lev[q];
+    pl.m = Lv.m;
+    pl.A = Lv.A;
+    pl.dinv = Lv.dinv;
+    pl.b = Lv.b;
+    pl.x = Lv.x;
+    pl.x2 = Lv.x2;
+    pl.r = Lv.r;
+    pl.G = Lv.spmv_group;
+    if (q + 1 < P.nlev) {
+      pl.T = Lv.T;
+      pl.Tt = Lv.Tt;
+      pl.GT = group_for(Lv.T);
+      pl.GTt = group_for(Lv.Tt);
+    }
+  }
+  P.dense_inv = P.bottom_dense ? S.lev[S.cut].dense_inv : nullptr;
+  P.r = S.pc_r;
+  P.p = S.pc_p;
+  P.p2 = S.pc_p2;
+  P.Ap = S.pc_Ap;
+  P.x = S.pc_x;
+  P.b = S.pc_b;
+  P.partials = S.pcg_partials;
+  P.bar = S.pcg_bar;
+  P.out = S.pcg_out;
+  D.dev = h->pool.upload<PcgPlan>(&P, 1, s);
+  CK(cudaStreamSynchronize(s));
+  if (h->cfg.verbose > 0)
+    fprintf(stderr, "[mgbx] persistent PCG plan: %d levels (%d grid-wide, %d in CTA 0), dense bottom %d, grid %d x %d\n", P.nlev, P.nbig,
+            P.nlev - P.nbig, P.bottom_dense, h->pcg_grid, kPcgThreads);
+  return D;
+}
+
+// The whole PCG solve in one cooperative launch; returns the iteration count (negative: breakdown)
+int Engine::pcg_persistent(System &S, int ktop, const double *b, double *x) {
+  SysLevel &Lv = S.lev[ktop];
+  const int64_t m = Lv.m;
+  // the dense bottom inverse must exist before the plan captures its pointer
+  System::PcgDev &D = pcg_plan(S, ktop);
+  if (b != S.pc_b) copy(S.pc_b, b, m);
+  const PcgPlan *dev = D.dev;
+  void *args[] = {(void *)&dev, (void *)&h->cur_rtol2, (void *)&h->cfg.pcg_maxit};
+  pre_launch(KC_PCG);
+  CK(cudaLaunchCooperativeKernel((const void *)k_pcg_persistent, dim3(h->pcg_grid), dim3(kPcgThreads), args, 0, s));
+  post_launch(KC_PCG);
+  CK(cudaMemcpyAsync(h->hscal + 8, S.pcg_out, sizeof(double) * 4, cudaMemcpyDeviceToHost, s));
+  sync();
+  const int it = (int)h->hscal[8];
+  const double status = h->hscal[10];
+  if (x != S.pc_x) copy(x, S.pc_x, m);
+  return status < 0 ? -std::max(it, 1) : it;
+}
+
 int Engine::pcg(System &S, int ktop, const double *b, double *x) {
+  if (h->cfg.persistent) return pcg_persistent(S, ktop, b, x);
   SysLevel &Lv = S.lev[ktop];
   const int64_t m = Lv.m;
   double *r = S.pc_r, *p = S.pc_p;
@@ -806,7 +1017,7 @@ int Engine::pcg(System &S, int ktop, const double *b, double *x) {
     zero(x, m);
     return 0;
   }
-  const double target = h->cfg.pcg_rtol * h->cfg.pcg_rtol * bb;
+  const double target = h->cur_rtol2 * bb;
   // the iteration body is captured once per (system, top level) and replayed as a CUDA graph
   cudaGraphExec_t gexec = nullptr;
   const bool use_graph = h->cfg.use_graphs && !h->cfg.profile;
@@ -880,8 +1091,8 @@ int Engine::solve_compact(System &S, int ktop, const double *b, double *x) {
 // dir = H_J^{-1} g  (full level-J vectors).  With a condensed system the node-local variables are
 // eliminated exactly first and recovered by back-substitution.
 int Engine::solve(Amg &A, System &S, int J, const double *g, double *dir) {
-  cudaEventRecord(h->ev0, s);
-  const int ktop = A.L - 1 - J;
+  cudaEvent_t st = stage_begin();
+  const int ktop = S.ltop - J;
   SysLevel &Lv = S.lev[ktop];
   int iters = 0;
   if (S.nE == 0) {
@@ -916,14 +1127,11 @@ int Engine::solve(Amg &A, System &S, int J, const double *g, double *dir) {
     NP.zf = A.gb;
     LAUNCH(KC_COND, k_backsubst<<<nblk(A.n), 256, 0, s>>>(C, NP, g, dir));
   }
-  cudaEventRecord(h->ev1, s);
+  stage_end(STAGE_SOLVE, st);
   // inc = g . dir, finiteness of dir
   LAUNCH(KC_VEC, k_dot2<<<red_grid(A.m[J]), kRedThreads, 0, s>>>(A.m[J], dir, g, h->partials, h->ticket, h->dscal + 4));
   fetch(8);
-  float ms = 0.f;
-  cudaEventElapsedTime(&ms, h->ev0, h->ev1);
   if (h->res) {
-    h->res->ms_solve += ms;
     h->res->linear_solves++;
     h->res->pcg_iters += iters > 0 ? iters : -iters;
   }
@@ -935,6 +1143,10 @@ Engine::NewtonOut Engine::newton(Amg &A, int J, double t, int maxit, int stop_ki
   NewtonOut out{false, 0, MGBX_OK, 0.0, 0.0, 0.0};
   const int64_t m = A.m[J];
   System &S = system_for(A, J);
+  // the finalize pass stops on floating-point stagnation (stopping_exact): give it directions converged to the
+  // attainable accuracy so that it stagnates where a direct solve would
+  const double rt = (stop_kind == 0) ? std::min(h->cfg.pcg_rtol, h->cfg.pcg_rtol_final) : h->cfg.pcg_rtol;
+  h->cur_rtol2 = rt * rt;
   zero(A.x, m);
   EvalOut e0 = eval_f01(A, J, t, A.z, A.x, A.g);
   if (!e0.finite) {
@@ -1038,13 +1250,10 @@ int Engine::step(int which, double t, const mgbx_step_opts &o, mgbx_step_result 
     converged = converged && foo;
   }
   r->converged = converged ? 1 : 0;
-  h->res = nullptr;
-  if (status != MGBX_OK || !converged) {
-    copy(A.z, A.zsave, (int64_t)A.nu * A.n);   // the caller discards a failed step (mgb.jl:147-163)
-    sync();
-    return status != MGBX_OK ? status : MGBX_NOT_CONVERGED;
-  }
+  if (status != MGBX_OK || !converged) copy(A.z, A.zsave, (int64_t)A.nu * A.n);   // the caller discards a failed step (mgb.jl:147-163)
   sync();
+  h->res = nullptr;
+  if (status != MGBX_OK || !converged) return status != MGBX_OK ? status : MGBX_NOT_CONVERGED;
   return MGBX_OK;
 }
 
@@ -1184,12 +1393,17 @@ void create_amg(mgbx_handle *h, const mgbx_amg &in, Amg &A) {
     A.voff[l].assign(in.var_offsets + (size_t)l * (in.nu + 1), in.var_offsets + (size_t)(l + 1) * (in.nu + 1));
     A.m[l] = A.voff[l][in.nu];
     if (A.voff[l][0] != 0) throw ArgError("amg: var_offsets must start at 0");
-    if (in.R_fine[l].cols != A.m[l] || in.R_fine[l].rows != (int64_t)in.nu * in.n)
+    if (l == in.L - 1 && (in.R_fine[l].cols != A.m[l] || in.R_fine[l].rows != (int64_t)in.nu * in.n))
       throw ArgError("amg: R_fine dimension mismatch (rows must be nu*n, cols must match var_offsets)");
   }
+  HostTimer tm;
+  const bool vb = h->cfg.verbose > 0;
+  if (vb) fprintf(stderr, "[mgbx] create_amg: operators + weights queued %.3fs\n", tm.lap());
   A.hRL = csr_from_abi(in.R_fine[in.L - 1]);
+  if (vb) fprintf(stderr, "[mgbx]   R_fine[L-1] checked/converted (nnz=%lld) %.3fs\n", (long long)A.hRL.nnz(), tm.lap());
   A.RL = upload_csr(pool, A.hRL, s);
   A.RLt = upload_csr(pool, transpose(A.hRL), s);
+  if (vb) fprintf(stderr, "[mgbx]   R, R' uploaded %.3fs\n", tm.lap());
   A.hT.resize(std::max(0, in.L - 1));
   A.T.resize(A.hT.size());
   A.Tt.resize(A.hT.size());
@@ -1200,6 +1414,7 @@ void create_amg(mgbx_handle *h, const mgbx_amg &in, Amg &A) {
     A.T[l] = upload_csr(pool, A.hT[l], s);
     A.Tt[l] = upload_csr(pool, transpose(A.hT[l]), s);
   }
+  if (vb) fprintf(stderr, "[mgbx]   level transfers %.3fs\n", tm.lap());
   const int64_t nun = (int64_t)in.nu * in.n;
   A.z = pool.zeros<double>(nun, s);
   A.zsave = pool.zeros<double>(nun, s);
@@ -1229,6 +1444,31 @@ void create_amg(mgbx_handle *h, const mgbx_amg &in, Amg &A) {
   A.tmp = pool.zeros<double>(mmax, s);
   A.xbest = pool.zeros<double>(mmax, s);
   A.gbest = pool.zeros<double>(mmax, s);
+  CK(cudaStreamSynchronize(s));
+  if (vb) fprintf(stderr, "[mgbx]   work vectors + sync %.3fs\n", tm.lap());
+}
+
+
+// feasibility AMG (src/multigrid.jl:522-536): state [user..., slack], rows [user D...; slack:id; each component:id]
+void attach_feasibility(mgbx_handle *h, const mgbx_amg &a1) {
+  Amg &A = h->amg[0];
+  if (h->has_feas) throw ArgError("feasibility AMG already attached");
+  if (a1.n != A.n || a1.nu != A.nu + 1 || a1.nD != A.nD + 1 + A.nu)
+    throw ArgError("feasibility AMG must have nu+1 state variables and nD+1+nu rows (src/multigrid.jl:522-536)");
+  create_amg(h, a1, h->amg[1]);
+  Amg &F = h->amg[1];
+  F.cd = A.cd;          // same grids, wrapped
+  F.cd.feas = 1;
+  F.cd.NC = A.nD + 1;
+  F.cd.NF = F.nD;
+  F.cd.fb = 1.0;
+  F.cd.fR = 10.0;
+  // phase-I cost: integral of the slack = row nD of D (0-based) (src/mgb.jl:446-448)
+  std::vector<double> c1((size_t)F.n * F.nD, 0.0);
+  for (int64_t i = 0; i < F.n; ++i) c1[(size_t)A.nD * F.n + i] = 1.0;
+  CK(cudaMemcpyAsync(F.f, c1.data(), sizeof(double) * c1.size(), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->has_feas = true;
 }
 
 int guarded(mgbx_handle *h, const std::function<int()> &fn) {
@@ -1272,6 +1512,9 @@ void mgbx_default_config(mgbx_config *c) {
   c->verbose = 0;
   c->profile = 0;
   c->use_graphs = 1;
+  c->persistent = 1;
+  c->tail_max = 1200;
+  c->pcg_rtol_final = 1e-13;
 }
 
 void mgbx_default_step_opts(mgbx_step_opts *o, int64_t n) {
@@ -1308,7 +1551,9 @@ int mgbx_create(const mgbx_problem *prob, const mgbx_config *cfg, mgbx_handle **
   if (cfg) h->cfg = *cfg;
   else mgbx_default_config(&h->cfg);
   if (h->cfg.dense_direct_max > 4096) h->cfg.dense_direct_max = 4096;
-  if (h->cfg.coarse_max > h->cfg.dense_direct_max) h->cfg.coarse_max = h->cfg.dense_direct_max;
+  if (h->cfg.coarse_max > kCoarseMaxDense) h->cfg.coarse_max = kCoarseMaxDense;
+  if (h->cfg.coarse_max < 0) h->cfg.coarse_max = 0;
+  h->cur_rtol2 = h->cfg.pcg_rtol * h->cfg.pcg_rtol;
   int rc = guarded(h, [&]() -> int {
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -1317,6 +1562,16 @@ int mgbx_create(const mgbx_problem *prob, const mgbx_config *cfg, mgbx_handle **
                                std::string(cudaGetErrorString(e)) + ")");
     if (h->cfg.device >= 0) CK(cudaSetDevice(h->cfg.device));
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    {
+      int dev = 0, nsm = 0, coop = 0, per_sm = 0;
+      CK(cudaGetDevice(&dev));
+      CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+      CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_persistent, kPcgThreads, 0));
+      if (!coop || per_sm < 1) throw std::runtime_error("CUDA device cannot run the cooperative persistent solve kernel");
+      h->pcg_grid = std::min(nsm, kPcgMaxGrid);   // one CTA per SM
+      CK(cudaFuncSetAttribute(k_coarse_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coarse_inverse_smem(kCoarseMaxDense)));
+    }
     CK(cudaEventCreate(&h->ev0));
     CK(cudaEventCreate(&h->ev1));
     h->partials = h->pool.zeros<double>((size_t)kRedBlocks * 8, h->stream);
@@ -1331,26 +1586,10 @@ int mgbx_create(const mgbx_problem *prob, const mgbx_config *cfg, mgbx_handle **
     CK(cudaMemcpyAsync(A.z, prob->g_grid, sizeof(double) * A.n * A.nu, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(A.zinit, prob->g_grid, sizeof(double) * A.n * A.nu, cudaMemcpyHostToDevice, h->stream));
     if (prob->barrier_weights) A.bw = h->pool.upload<double>(prob->barrier_weights, A.n, h->stream);
+    HostTimer tq;
     upload_convex(h, prob->Q, A.n, A.nD, A.cd);
-    if (prob->amg[1].n > 0) {
-      const mgbx_amg &a1 = prob->amg[1];
-      if (a1.n != a0.n || a1.nu != a0.nu + 1 || a1.nD != a0.nD + 1 + a0.nu)
-        throw ArgError("feasibility AMG must have nu+1 state variables and nD+1+nu rows (src/multigrid.jl:522-536)");
-      create_amg(h, a1, h->amg[1]);
-      Amg &F = h->amg[1];
-      F.cd = A.cd;          // same grids, wrapped
-      F.cd.feas = 1;
-      F.cd.NC = A.nD + 1;
-      F.cd.NF = F.nD;
-      F.cd.fb = 1.0;
-      F.cd.fR = 10.0;
-      // phase-I cost: integral of the slack = row nD of D (0-based) (src/mgb.jl:446-448)
-      std::vector<double> c1((size_t)F.n * F.nD, 0.0);
-      for (int64_t i = 0; i < F.n; ++i) c1[(size_t)A.nD * F.n + i] = 1.0;
-      CK(cudaMemcpyAsync(F.f, c1.data(), sizeof(double) * c1.size(), cudaMemcpyHostToDevice, h->stream));
-      CK(cudaStreamSynchronize(h->stream));
-      h->has_feas = true;
-    }
+    if (h->cfg.verbose > 0) fprintf(stderr, "[mgbx] convex set scanned + uploaded %.3fs\n", tq.lap());
+    if (prob->amg[1].n > 0) attach_feasibility(h, prob->amg[1]);
     CK(cudaStreamSynchronize(h->stream));
     return MGBX_OK;
   });
@@ -1367,7 +1606,7 @@ void mgbx_destroy(mgbx_handle *h) {
   if (!h) return;
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (int w = 0; w < 2; ++w)
-    for (System *S : {h->amg[w].sys_cond.get(), h->amg[w].sys_full.get()})
+    for (System *S : {h->amg[w].sys_cond.get(), h->amg[w].sys_coarse.get(), h->amg[w].sys_hook.get()})
       if (S)
         for (auto &kv : S->graphs) cudaGraphExecDestroy(kv.second);
   h->pool.release();
@@ -1385,7 +1624,7 @@ void mgbx_destroy(mgbx_handle *h) {
 
 int mgbx_step(mgbx_handle *h, int which, double t, const mgbx_step_opts *o, mgbx_step_result *r) {
   if (!h || !o || !r) return MGBX_ERR_ARG;
-  return guarded(h, [&]() -> int {
+  const int rc = guarded(h, [&]() -> int {
     if (which < 0 || which > 1 || (which == 1 && !h->has_feas)) throw ArgError("mgbx_step: no such AMG");
     if (o->line_search != 0) {
       h->err = "line_search = illinois is not implemented yet";
@@ -1394,6 +1633,8 @@ int mgbx_step(mgbx_handle *h, int which, double t, const mgbx_step_opts *o, mgbx
     Engine E(h);
     return E.step(which, t, *o, r);
   });
+  h->res = nullptr;
+  return rc;
 }
 
 int mgbx_scalars(mgbx_handle *h, int which, mgbx_scalars_out *out) {
@@ -1437,11 +1678,11 @@ int mgbx_phase1_init(mgbx_handle *h, int32_t *needs_phase1, double *b, double *z
     *zabsmax = zmax;
     *b = 0.0;
     if (*needs_phase1) {
-      if (!h->has_feas) throw ArgError("phase I needed but the problem carries no feasibility AMG");
+      if (!h->has_feas) return MGBX_OK;   // the host attaches the feasibility AMG (mgbx_attach_feasibility) and calls again
       Amg &F = h->amg[1];
       // slack_i = 2*max(slack_fn(D z0), 1);  b = 2*max(1, max slack)   (src/mgb.jl:437-445)
       NodeParams P = E.node_params(A, 0.0);   // A.zf holds z0 from the probe
-      E_LAUNCH(KC_NODE_F01, k_node<NODE_SLACK><<<E.red_grid(A.n), kRedThreads, 0, h->stream>>>(P));
+      E_LAUNCH(KC_NODE_F01, launch_node<NODE_SLACK>(P, E.red_grid(A.n), h->stream));
       E_LAUNCH(KC_VEC, k_phase1_slack<<<nblk(A.n), 256, 0, h->stream>>>(A.n, A.slack, F.zinit + (int64_t)A.nu * A.n));
       E.copy(F.zinit, A.z, (int64_t)A.nu * A.n);
       E.copy(F.z, F.zinit, (int64_t)F.nu * F.n);
@@ -1449,6 +1690,14 @@ int mgbx_phase1_init(mgbx_handle *h, int32_t *needs_phase1, double *b, double *z
       E.fetch(3);
       *b = 2.0 * std::max(1.0, h->hscal[0]);
     }
+    return MGBX_OK;
+  });
+}
+
+int mgbx_attach_feasibility(mgbx_handle *h, const mgbx_amg *feas) {
+  if (!h || !feas) return MGBX_ERR_ARG;
+  return guarded(h, [&]() -> int {
+    attach_feasibility(h, *feas);
     return MGBX_OK;
   });
 }
@@ -1576,8 +1825,8 @@ int mgbx_hessian_pattern(mgbx_handle *h, int which, int level, int64_t *nnz, int
     if (which < 0 || which > 1 || (which == 1 && !h->has_feas)) throw ArgError("no such AMG");
     Amg &A = h->amg[which];
     if (level < 0 || level >= A.L) throw ArgError("no such level");
-    if (!A.sys_full) A.sys_full = build_system(h, A, false);
-    SysLevel &Lv = A.sys_full->lev[A.L - 1 - level];
+    if (!A.sys_hook) A.sys_hook = build_system(h, A, false, A.L - 1);
+    SysLevel &Lv = A.sys_hook->lev[A.L - 1 - level];
     *nnz = Lv.A.nnz;
     if (rowptr) CK(cudaMemcpy(rowptr, Lv.A.ptr, sizeof(int64_t) * (Lv.m + 1), cudaMemcpyDeviceToHost));
     if (colind) {
@@ -1596,8 +1845,8 @@ int mgbx_hessian_values(mgbx_handle *h, int which, int level, double t, const do
     Amg &A = h->amg[which];
     if (level < 0 || level >= A.L) throw ArgError("no such level");
     Engine E(h);
-    if (!A.sys_full) A.sys_full = build_system(h, A, false);
-    System &S = *A.sys_full;
+    if (!A.sys_hook) A.sys_hook = build_system(h, A, false, A.L - 1);
+    System &S = *A.sys_hook;
     CK(cudaMemcpyAsync(A.xn, s, sizeof(double) * A.m[level], cudaMemcpyHostToDevice, h->stream));
     {
       E.prolong_to_fine(A, level, A.xn, A.z, A.zf);
@@ -1609,20 +1858,17 @@ int mgbx_hessian_values(mgbx_handle *h, int which, int level, double t, const do
         P.Erow[j] = -1;
       }
       P.Hn = A.Hn;
-      E_LAUNCH(KC_NODE_F2, k_node<NODE_F2><<<E.red_grid(A.n), kRedThreads, 0, h->stream>>>(P));
+      E_LAUNCH(KC_NODE_F2, launch_node<NODE_F2>(P, E.red_grid(A.n), h->stream));
       ElemParams EP = E.elem_params(A);
       E_LAUNCH(KC_BLOCKHESS, k_blockhess<<<nblk(S.hblk_size), 256, 0, h->stream>>>(EP, S.pl, A.Hn, S.Hblk));
-      E_LAUNCH(KC_GATHER, k_csr_gather<<<nblk(S.lev[0].A.nnz), 256, 0, h->stream>>>(S.lev[0].A.nnz, S.gptr, S.gidx, S.gw, S.Hblk, S.lev[0].A.val));
+      E_LAUNCH(KC_GATHER, k_sell_gather<<<nblk(S.lev[0].A.nnz), 256, 0, h->stream>>>(S.top, S.Hblk, S.lev[0].A.val));
       const int ktop = A.L - 1 - level;
       for (int k = 0; k < ktop; ++k) {
         SysLevel &Lv = S.lev[k];
         SysLevel &Lc = S.lev[k + 1];
-        if (Lv.T_identity) {
-          E.copy(Lc.A.val, Lv.A.val, Lv.A.nnz);
-          continue;
-        }
-        E_LAUNCH(KC_SPGEMM, k_csr_gather<<<nblk(Lv.AT.nnz), 256, 0, h->stream>>>(Lv.AT.nnz, Lv.g1ptr, Lv.g1src, Lv.g1w, Lv.A.val, Lv.AT.val));
-        E_LAUNCH(KC_SPGEMM, k_csr_gather<<<nblk(Lc.A.nnz), 256, 0, h->stream>>>(Lc.A.nnz, Lv.g2ptr, Lv.g2src, Lv.g2w, Lv.AT.val, Lc.A.val));
+        if (Lv.T_identity) continue;   // aliased
+        E_LAUNCH(KC_SPGEMM, k_sell_gather<<<nblk(Lv.AT.nnz), 256, 0, h->stream>>>(Lv.s1, Lv.A.val, Lv.AT.val));
+        E_LAUNCH(KC_SPGEMM, k_sell_gather<<<nblk(Lc.A.nnz), 256, 0, h->stream>>>(Lv.s2, Lv.AT.val, Lc.A.val));
       }
       SysLevel &Lv = S.lev[ktop];
       CK(cudaMemcpyAsync(val, Lv.A.val, sizeof(double) * Lv.A.nnz, cudaMemcpyDeviceToHost, h->stream));

@@ -45,30 +45,31 @@ MGBX_HD double Log(double x) { return x <= 0.0 ? -INFINITY : log(x); }
 MGBX_HD double safe_pow(double s, double a) { return exp(a * Log(s)); }
 
 // One piece.  y: node inputs; F1 (ny) and F2 (ny x ny, row stride ny) are accumulated into.
+// The Hessian of the piece in its own coordinates z = A y[idx] + b is never stored: entry (r, s) is formed on
+// the fly from a handful of scalars (EP: 4 z_r z_s / rho^2 + 2 delta_rs / rho, the coupling column and the
+// slack corner; LINEAR: diag(1/z^2)), so the common identity-A case touches no local array beyond z and g.
 MGBX_HD double piece_eval(const PieceDev &pc, int64_t n, int64_t i, const double *y, int ny, int order,
                           bool cob, double slack, int slackpos, double *F1, double *F2) {
   const int ni = pc.ni, nc = pc.nc;
-  double yi[MGBX_MAX_NI];
   double z[MGBX_MAX_NC];
+  double gz[MGBX_MAX_NC];
   double Al[MGBX_MAX_NC * MGBX_MAX_NI];
-  for (int c = 0; c < ni; ++c) yi[c] = y[pc.idx[c]];
   const bool Aid = (pc.A == nullptr);
   if (!Aid)
     for (int c = 0; c < ni; ++c)
       for (int r = 0; r < nc; ++r) Al[r + c * nc] = pc.A[i + (int64_t)(c * nc + r) * n];
   for (int r = 0; r < nc; ++r) {
     double acc = 0.0;
-    if (Aid) acc = yi[r];
+    if (Aid) acc = y[pc.idx[r]];
     else
-      for (int c = 0; c < ni; ++c) acc += Al[r + c * nc] * yi[c];
+      for (int c = 0; c < ni; ++c) acc += Al[r + c * nc] * y[pc.idx[c]];
     z[r] = acc + (pc.b ? pc.b[i + (int64_t)r * n] : 0.0);
   }
   double f0;
-  double gz[MGBX_MAX_NC];
-  double Hz[MGBX_MAX_NC * MGBX_MAX_NC];   // EP: full; LINEAR: only the diagonal entries are used
   const bool ep = (pc.kind == MGBX_PIECE_EP);
+  const int nq = nc - 1;
+  double inv_r = 0.0, inv_r2 = 0.0, coef = 0.0, hss = 0.0;
   if (ep) {
-    const int nq = nc - 1;
     if (cob) z[nq] += slack;
     const double s = z[nq];
     const double p = pc.p ? pc.p[i] : pc.p_uniform;
@@ -76,26 +77,24 @@ MGBX_HD double piece_eval(const PieceDev &pc, int64_t n, int64_t i, const double
     const double al = 2.0 / p;
     double qsq = 0.0;
     for (int k = 0; k < nq; ++k) qsq += z[k] * z[k];
-    const double sa = safe_pow(s, al);
+    // one log and one exp serve every power of s on the interior (s > 0): s^(a-1) = s^a / s, s^(a-2) = s^(a-1) / s,
+    // s^(2a-2) = (s^(a-1))^2; outside the domain the reference's _safe_pow values are formed as written there
+    const double ls = Log(s);
+    const double sa = exp(al * ls);
     const double r = sa - qsq;
-    f0 = -Log(r) - mu * Log(s);
+    f0 = -Log(r) - mu * ls;
     if (order >= 1) {
-      const double inv_r = 1.0 / r;
-      const double sam1 = safe_pow(s, al - 1.0);
+      inv_r = 1.0 / r;
+      const bool in = s > 0.0;
+      const double sam1 = in ? sa / s : safe_pow(s, al - 1.0);
       for (int k = 0; k < nq; ++k) gz[k] = 2.0 * inv_r * z[k];
       gz[nq] = -al * sam1 * inv_r - mu / s;
       if (order >= 2) {
-        const double inv_r2 = inv_r * inv_r;
-        const double coef = -2.0 * al * sam1 * inv_r2;
-        const double sam2 = safe_pow(s, al - 2.0);
-        const double s2am2 = safe_pow(s, 2.0 * al - 2.0);
-        const double hss = -al * (al - 1.0) * sam2 * inv_r + al * al * s2am2 * inv_r2 + mu / (s * s);
-        for (int a = 0; a < nq; ++a) {
-          for (int b = 0; b < nq; ++b) Hz[a * nc + b] = 4.0 * z[a] * z[b] * inv_r2 + (a == b ? 2.0 * inv_r : 0.0);
-          Hz[a * nc + nq] = coef * z[a];
-          Hz[nq * nc + a] = coef * z[a];
-        }
-        Hz[nq * nc + nq] = hss;
+        inv_r2 = inv_r * inv_r;
+        coef = -2.0 * al * sam1 * inv_r2;
+        const double sam2 = in ? sam1 / s : safe_pow(s, al - 2.0);
+        const double s2am2 = in ? sam1 * sam1 : safe_pow(s, 2.0 * al - 2.0);
+        hss = -al * (al - 1.0) * sam2 * inv_r + al * al * s2am2 * inv_r2 + mu / (s * s);
       }
     }
   } else {
@@ -104,9 +103,17 @@ MGBX_HD double piece_eval(const PieceDev &pc, int64_t n, int64_t i, const double
       if (cob) z[r] += slack;
       f0 -= Log(z[r]);
       if (order >= 1) gz[r] = -1.0 / z[r];
-      if (order >= 2) Hz[r * nc + r] = 1.0 / (z[r] * z[r]);
     }
   }
+  // Hessian entry (r, s) in piece coordinates
+  auto hz = [&](int r, int s2) -> double {
+    if (ep) {
+      if (r < nq && s2 < nq) return 4.0 * z[r] * z[s2] * inv_r2 + (r == s2 ? 2.0 * inv_r : 0.0);
+      if (r == nq && s2 == nq) return hss;
+      return coef * z[r < s2 ? r : s2];
+    }
+    return r == s2 ? 1.0 / (z[r] * z[r]) : 0.0;
+  };
   if (order >= 1) {
     for (int c = 0; c < ni; ++c) {
       double acc = 0.0;
@@ -117,36 +124,25 @@ MGBX_HD double piece_eval(const PieceDev &pc, int64_t n, int64_t i, const double
     }
     if (cob) {
       double acc = 0.0;
-      if (ep) acc = gz[nc - 1];
+      if (ep) acc = gz[nq];
       else
         for (int r = 0; r < nc; ++r) acc += gz[r];
       F1[slackpos] += acc;
     }
   }
   if (order >= 2) {
-    // HA[r][b] = sum_s Hz[r][s] A[s][b]
-    double HA[MGBX_MAX_NC * MGBX_MAX_NI];
-    for (int r = 0; r < nc; ++r)
-      for (int b = 0; b < ni; ++b) {
-        double acc;
-        if (ep) {
-          if (Aid) acc = Hz[r * nc + b];
-          else {
-            acc = 0.0;
-            for (int s2 = 0; s2 < nc; ++s2) acc += Hz[r * nc + s2] * Al[s2 + b * nc];
-          }
-        } else {
-          acc = Hz[r * nc + r] * (Aid ? (r == b ? 1.0 : 0.0) : Al[r + b * nc]);
-        }
-        HA[r * ni + b] = acc;
-      }
     for (int a = 0; a < ni; ++a)
       for (int b = 0; b < ni; ++b) {
-        double acc;
-        if (Aid) acc = HA[a * ni + b];
-        else {
-          acc = 0.0;
-          for (int r = 0; r < nc; ++r) acc += Al[r + a * nc] * HA[r * ni + b];
+        double acc = 0.0;
+        if (Aid) acc = hz(a, b);
+        else if (ep) {
+          for (int r = 0; r < nc; ++r) {
+            double t = 0.0;
+            for (int s2 = 0; s2 < nc; ++s2) t += hz(r, s2) * Al[s2 + b * nc];
+            acc += Al[r + a * nc] * t;
+          }
+        } else {
+          for (int r = 0; r < nc; ++r) acc += Al[r + a * nc] * hz(r, r) * Al[r + b * nc];
         }
         F2[pc.idx[a] * ny + pc.idx[b]] += acc;
       }
@@ -155,15 +151,15 @@ MGBX_HD double piece_eval(const PieceDev &pc, int64_t n, int64_t i, const double
       double corner = 0.0;
       for (int a = 0; a < ni; ++a) {
         double acc = 0.0;
-        if (Aid) acc = ep ? Hz[a * nc + (nc - 1)] : Hz[a * nc + a];
+        if (Aid) acc = ep ? hz(a, nq) : hz(a, a);
         else
-          for (int r = 0; r < nc; ++r) acc += Al[r + a * nc] * (ep ? Hz[r * nc + (nc - 1)] : Hz[r * nc + r]);
+          for (int r = 0; r < nc; ++r) acc += Al[r + a * nc] * (ep ? hz(r, nq) : hz(r, r));
         F2[pc.idx[a] * ny + slackpos] += acc;
         F2[slackpos * ny + pc.idx[a]] += acc;
       }
-      if (ep) corner = Hz[(nc - 1) * nc + (nc - 1)];
+      if (ep) corner = hss;
       else
-        for (int r = 0; r < nc; ++r) corner += Hz[r * nc + r];
+        for (int r = 0; r < nc; ++r) corner += hz(r, r);
       F2[slackpos * ny + slackpos] += corner;
     }
   }

@@ -1,0 +1,535 @@
+// solver_kernels.cuh -- the Newton-system solve as ONE persistent cooperative kernel, the Galerkin
+// gather plans (sliced-ELL) and the coarse dense inverse.
+//
+// What this replaces in the reference (paths under /root/reference):
+//   k_pcg_persistent   solve(Symmetric(H), g)  src/utils.jl:142-145 (CHOLMOD) and the CUDA extension's cuDSS
+//                      analysis/factor/solve (ext/MultiGridBarrierCUDAExt/cudss_solver.jl:264-381): a whole
+//                      V-cycle-preconditioned CG solve -- every smoother sweep, residual, grid transfer, dot
+//                      product and the convergence test -- runs in one launch with one CTA per SM; phases are
+//                      separated by a grid barrier (release/acquire on one counter), levels below `nbig`
+//                      are handled by CTA 0 alone with __syncthreads.  Only {iterations, |r|^2, status}
+//                      return to the host.
+//   k_sell_gather      the numeric Galerkin products A_c = T'(A T) (north-star item 3) and the R'HR scatter
+//                      of src/BlockMatrices.jl:506-555, as fixed-order gathers over a sliced-ELL term list
+//                      (coalesced index/weight streams, deterministic; the reference CUDA ext uses FP64 atomics,
+//                      block_ops.jl:229-249).
+//   k_prod_count/fill  build those term lists on the device (setup, once per system).
+//   k_coarse_inverse   dense Cholesky + explicit inverse of the coarsest level in shared memory (one CTA).
+#pragma once
+#include "kernels.cuh"
+
+namespace mgbx {
+
+// ------------------------------------------------------------------------------------------------
+// sliced-ELL gather:  out[nz] = sum_{k < cnt[nz]} w[off + 32k] * in[src[off + 32k]],  off = sptr[nz/32] + nz%32
+// ------------------------------------------------------------------------------------------------
+struct SellPlan {
+  int64_t nout = 0, nslices = 0, nterms = 0;   // nterms: real (unpadded) terms
+  int64_t *sptr = nullptr;                      // nslices + 1 entry offsets
+  int32_t *cnt = nullptr;                       // nout
+  int32_t *src = nullptr;                       // padded entries
+  double *w = nullptr;                          // padded entries, or nullptr (all weights 1)
+};
+
+__global__ void __launch_bounds__(256) k_sell_gather(SellPlan P, const double *__restrict__ in, double *__restrict__ out) {
+  const int64_t nz = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (nz >= P.nout) return;
+  const int64_t off = P.sptr[nz >> 5] + (nz & 31);
+  const int c = P.cnt[nz];
+  double acc = 0.0;
+  if (P.w) {
+    for (int k = 0; k < c; ++k) acc += P.w[off + 32 * (int64_t)k] * in[P.src[off + 32 * (int64_t)k]];
+  } else {
+    for (int k = 0; k < c; ++k) acc += in[P.src[off + 32 * (int64_t)k]];
+  }
+  out[nz] = acc;
+}
+
+// row index of every non-zero of a CSR pattern
+__global__ void k_csr_rows(DevCsr A, int32_t *rowof) {
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= A.rows) return;
+  for (int64_t k = A.ptr[row]; k < A.ptr[row + 1]; ++k) rowof[k] = (int32_t)row;
+}
+
+__device__ __forceinline__ int64_t csr_find(const DevCsr &A, int64_t row, int32_t col) {
+  int64_t lo = A.ptr[row], hi = A.ptr[row + 1];
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    const int32_t c = A.idx[mid];
+    if (c < col) lo = mid + 1;
+    else if (c > col) hi = mid;
+    else return mid;
+  }
+  return -1;
+}
+
+// Term list of C = Lm * Rm into the fixed pattern C.  variable_left: the values of Lm change between
+// uses (source = nz of Lm, weight = value of Rm), otherwise the values of Rm change.  One thread per
+// non-zero of C walks row i of Lm and looks column c up in the rows of Rm: no atomics, fixed order.
+// FILL == 0: cnt[nz] and per-slice width;  FILL == 1: write src / w.
+template <int FILL>
+__global__ void __launch_bounds__(256) k_prod_plan(DevCsr Lm, DevCsr Rm, DevCsr C, const int32_t *__restrict__ rowof, int variable_left,
+                                                    SellPlan P, int32_t *width) {
+  const int64_t nz = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int count = 0;
+  if (nz < C.nnz) {
+    const int64_t i = rowof[nz];
+    const int32_t c = C.idx[nz];
+    const int64_t off = FILL ? P.sptr[nz >> 5] + (nz & 31) : 0;
+    for (int64_t a = Lm.ptr[i]; a < Lm.ptr[i + 1]; ++a) {
+      const int64_t b = csr_find(Rm, Lm.idx[a], c);
+      if (b < 0) continue;
+      if (FILL) {
+        P.src[off + 32 * (int64_t)count] = (int32_t)(variable_left ? a : b);
+        P.w[off + 32 * (int64_t)count] = variable_left ? Rm.val[b] : Lm.val[a];
+      }
+      ++count;
+    }
+    if (!FILL) P.cnt[nz] = count;
+  }
+  if (!FILL) {
+    int wmax = count;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+    if ((threadIdx.x & 31) == 0 && nz < C.nnz) width[nz >> 5] = wmax;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// coarse dense inverse: Minv = (D A D)^{-1} with D = diag(a_ii)^{-1/2} folded back in, so that
+// x = Minv_out * b solves A x = b.  One CTA, everything in shared memory, m <= kCoarseMaxDense.
+//   shared layout: S[m][m+1] (scaled matrix -> Cholesky factor L), Li[m(m+1)/2] (packed inverse of L), d[m]
+// ------------------------------------------------------------------------------------------------
+constexpr int kCoarseMaxDense = 128;
+inline size_t coarse_inverse_smem(int m) { return sizeof(double) * ((size_t)m * (m + 1) + (size_t)m * (m + 1) / 2 + m); }
+
+__global__ void __launch_bounds__(1024) k_coarse_inverse(DevCsr A, double *Minv) {
+  extern __shared__ double sm[];
+  const int m = (int)A.rows;
+  const int ld = m + 1;
+  double *S = sm;
+  double *Li = S + (size_t)m * ld;
+  double *d = Li + (size_t)m * (m + 1) / 2;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int t = tid; t < m * ld; t += nt) S[t] = 0.0;
+  __syncthreads();
+  for (int row = tid; row < m; row += nt) {
+    double dg = 0.0;
+    for (int64_t k = A.ptr[row]; k < A.ptr[row + 1]; ++k)
+      if (A.idx[k] == row) dg = A.val[k];
+    d[row] = dg > 0.0 ? 1.0 / sqrt(dg) : 1.0;
+  }
+  __syncthreads();
+  for (int row = tid; row < m; row += nt)
+    for (int64_t k = A.ptr[row]; k < A.ptr[row + 1]; ++k) S[row * ld + A.idx[k]] = A.val[k] * d[row] * d[A.idx[k]];
+  __syncthreads();
+  // right-looking Cholesky on the lower triangle
+  for (int j = 0; j < m; ++j) {
+    if (tid == 0) S[j * ld + j] = sqrt(S[j * ld + j]);
+    __syncthreads();
+    const double piv = S[j * ld + j];
+    for (int i = j + 1 + tid; i < m; i += nt) S[i * ld + j] /= piv;
+    __syncthreads();
+    const int rem = m - j - 1;
+    for (int t = tid; t < rem * rem; t += nt) {
+      const int i = j + 1 + t / rem, k = j + 1 + t % rem;
+      if (k <= i) S[i * ld + k] -= S[i * ld + j] * S[k * ld + j];
+    }
+    __syncthreads();
+  }
+  // Li = L^{-1}, one warp per column c: x_c = 1/L_cc, x_i = -(sum_{k=c}^{i-1} L_ik x_k)/L_ii
+  const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+  for (int c = wid; c < m; c += nw) {
+    if (lane == 0) Li[(size_t)c * (c + 1) / 2 + c] = 1.0 / S[c * ld + c];
+    __syncwarp();
+    for (int i = c + 1; i < m; ++i) {
+      double s = 0.0;
+      for (int k = c + lane; k < i; k += 32) s += S[i * ld + k] * Li[(size_t)k * (k + 1) / 2 + c];
+      s = warp_sum(s);
+      if (lane == 0) Li[(size_t)i * (i + 1) / 2 + c] = -s / S[i * ld + i];
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // Minv[i][j] = d_i d_j sum_{k >= max(i,j)} Li[k][i] Li[k][j]
+  for (int t = tid; t < m * m; t += nt) {
+    const int i = t / m, j = t % m;
+    double s = 0.0;
+    for (int k = (i > j ? i : j); k < m; ++k) s += Li[(size_t)k * (k + 1) / 2 + i] * Li[(size_t)k * (k + 1) / 2 + j];
+    Minv[t] = s * d[i] * d[j];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// persistent PCG
+// ------------------------------------------------------------------------------------------------
+constexpr int kPcgThreads = 1024;
+constexpr int kPcgMaxGrid = 1024;   // partial slots per reduction
+
+struct PLevel {
+  int64_t m;
+  DevCsr A, T, Tt;       // T: this level <- next coarser active level; Tt its transpose
+  const double *dinv;
+  double *b, *x, *x2, *r;
+  int G, GT, GTt;        // lanes per row
+};
+
+struct PcgPlan {
+  int nlev, nbig;        // active levels: [0, nbig) by the whole grid, [nbig, nlev) by CTA 0 alone
+  int bottom_dense;      // the last level is applied through dense_inv
+  int nu, nu_bottom;     // smoother sweeps (pre = post = nu), sweeps on an iterated bottom level
+  int maxit;
+  double rtol2;
+  PLevel lev[MGBX_MAX_LEVELS];
+  const double *dense_inv;
+  double *r, *p, *p2, *Ap, *x;
+  const double *b;
+  double *partials;      // 3 x kPcgMaxGrid
+  unsigned int *bar;
+  double *out;           // [0] iterations, [1] |r|^2, [2] status (1 converged/stagnated, -1 breakdown), [3] |b|^2
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned int *bar) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int nb = 1;
+    if (blockIdx.x == 0) nb = 0x80000000u - (gridDim.x - 1);
+    unsigned int old, cur;
+    asm volatile("atom.add.release.gpu.u32 %0,[%1],%2;" : "=r"(old) : "l"(bar), "r"(nb) : "memory");
+    int spins = 0;
+    do {
+      asm volatile("ld.acquire.gpu.u32 %0,[%1];" : "=r"(cur) : "l"(bar) : "memory");
+      if (++spins > 64) __nanosleep(40);
+    } while (((old ^ cur) & 0x80000000u) == 0);
+  }
+  __syncthreads();
+}
+
+// scope of a phase: the whole grid (GRID) or one CTA
+template <bool GRID>
+struct Scope {
+  int64_t tid, nthr;
+  unsigned int *bar;
+  __device__ __forceinline__ void sync() const {
+    if (GRID) grid_barrier(bar);
+    else __syncthreads();
+  }
+};
+
+template <int G>
+__device__ __forceinline__ double row_dot(const DevCsr &A, int64_t row, int sub, bool valid, const double *x) {
+  double acc = 0.0;
+  if (valid) {
+    const int64_t b = A.ptr[row], e = A.ptr[row + 1];
+    for (int64_t k = b + sub; k < e; k += G) acc += A.val[k] * x[A.idx[k]];
+  }
+  if (G > 1) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, G);
+  }
+  return acc;
+}
+
+// y = alpha * A x + (y0 ? y0 : 0)     (y may alias y0; y must not alias x)
+template <int G, class SC>
+__device__ void ph_spmv(const SC &sc, const DevCsr &A, const double *x, const double *y0, double alpha, double *y) {
+  const int64_t step = sc.nthr / G;
+  const int sub = (int)(sc.tid % G);
+  for (int64_t base = 0; base < A.rows; base += step) {
+    const int64_t row = base + sc.tid / G;
+    const bool valid = row < A.rows;
+    const double acc = row_dot<G>(A, row, sub, valid, x);
+    if (valid && sub == 0) y[row] = alpha * acc + (y0 ? y0[row] : 0.0);
+  }
+}
+
+// two l1-Jacobi sweeps from x = 0:  x1 = dinv b;  x = x1 + dinv (b - A x1)
+template <int G, class SC>
+__device__ void ph_jacobi_first2(const SC &sc, const DevCsr &A, const double *dinv, const double *b, double *xnew) {
+  const int64_t step = sc.nthr / G;
+  const int sub = (int)(sc.tid % G);
+  for (int64_t base = 0; base < A.rows; base += step) {
+    const int64_t row = base + sc.tid / G;
+    const bool valid = row < A.rows;
+    double acc = 0.0;
+    if (valid) {
+      const int64_t bb = A.ptr[row], e = A.ptr[row + 1];
+      for (int64_t k = bb + sub; k < e; k += G) {
+        const int32_t j = A.idx[k];
+        acc += A.val[k] * (dinv[j] * b[j]);
+      }
+    }
+    if (G > 1) {
+#pragma unroll
+      for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, G);
+    }
+    if (valid && sub == 0) {
+      const double d = dinv[row], bi = b[row];
+      const double x1 = d * bi;
+      xnew[row] = x1 + d * (bi - acc);
+    }
+  }
+}
+
+// xnew = x + dinv (b - A x); returns this thread's share of sum_i dotw[i] * xnew[i] (0 if dotw == nullptr)
+template <int G, class SC>
+__device__ double ph_jacobi(const SC &sc, const DevCsr &A, const double *dinv, const double *b, const double *x, double *xnew,
+                            const double *dotw) {
+  const int64_t step = sc.nthr / G;
+  const int sub = (int)(sc.tid % G);
+  double part = 0.0;
+  for (int64_t base = 0; base < A.rows; base += step) {
+    const int64_t row = base + sc.tid / G;
+    const bool valid = row < A.rows;
+    const double acc = row_dot<G>(A, row, sub, valid, x);
+    if (valid && sub == 0) {
+      const double v = x[row] + dinv[row] * (b[row] - acc);
+      xnew[row] = v;
+      if (dotw) part += dotw[row] * v;
+    }
+  }
+  return part;
+}
+
+#define MGBX_G_DISPATCH(G, CALL) \
+  do {                            \
+    if ((G) == 32) { constexpr int GG = 32; CALL; } \
+    else if ((G) == 4) { constexpr int GG = 4; CALL; } \
+    else { constexpr int GG = 1; CALL; } \
+  } while (0)
+
+// x = dense_inv * b, one warp per row
+template <class SC>
+__device__ void ph_dense_apply(const SC &sc, const double *Minv, int m, const double *b, double *x) {
+  const int lane = (int)(sc.tid & 31);
+  const int64_t nw = sc.nthr >> 5;
+  for (int64_t row = sc.tid >> 5; row < m; row += nw) {
+    const double *r = Minv + (size_t)row * m;
+    double s = 0.0;
+    for (int j = lane; j < m; j += 32) s += r[j] * b[j];
+    s = warp_sum(s);
+    if (lane == 0) x[row] = s;
+  }
+}
+
+// block-wide sum, result broadcast to every thread (fixed order)
+__device__ __forceinline__ double block_sum_bcast(double v) {
+  __shared__ double wsum[32];
+  __shared__ double total;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();   // protects wsum / total from the previous call
+  if (lane == 0) wsum[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    double x = lane < nw ? wsum[lane] : 0.0;
+    x = warp_sum(x);
+    if (lane == 0) total = x;
+  }
+  __syncthreads();
+  return total;
+}
+
+// deposit this CTA's partial, grid barrier, then every CTA sums all partials in the same fixed order
+__device__ __forceinline__ double grid_sum(double part, double *slot, unsigned int *bar) {
+  const double bs = block_sum_bcast(part);
+  if (threadIdx.x == 0) slot[blockIdx.x] = bs;
+  grid_barrier(bar);
+  double v = 0.0;
+  for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) v += slot[b];
+  return block_sum_bcast(v);
+}
+
+// V-cycle over the active levels [k0, k1) in scope `sc`; btop: right-hand side of level k0.  After the
+// down-sweep of level k1-1 the coarser levels (if any) are run by CTA 0 alone (GRID scope only).  The
+// result is in lev[k0].x: the ping-pong between x and x2 starts on the buffer that makes the last sweep
+// land in x, so no pointer is ever swapped and every CTA agrees on where results live.
+// dot_top != nullptr: returns this thread's share of sum dot_top[i] * x[i] on level k0, and the barrier after
+// the last sweep is left to the caller's grid_sum.
+template <bool GRID>
+__device__ double vcycle_levels(const PcgPlan &P, const Scope<GRID> &sc, int k0, int k1, const double *btop, const double *dot_top) {
+  double part = 0.0;
+  // ---- down
+  for (int k = k0; k < k1; ++k) {
+    const PLevel &Lv = P.lev[k];
+    const double *bk = (k == k0) ? btop : Lv.b;
+    const bool last = (k == P.nlev - 1);
+    if (last && P.bottom_dense) {
+      ph_dense_apply(sc, P.dense_inv, (int)Lv.m, bk, Lv.x);
+      sc.sync();
+      continue;
+    }
+    const int want = last ? P.nu_bottom : P.nu;
+    const int done = (want >= 2) ? 2 : 1;
+    const int npre = want - done, npost = last ? 0 : P.nu;
+    double *cur = ((npre + npost) & 1) ? Lv.x2 : Lv.x, *oth = ((npre + npost) & 1) ? Lv.x : Lv.x2;
+    if (done == 2) {
+      MGBX_G_DISPATCH(Lv.G, (ph_jacobi_first2<GG>(sc, Lv.A, Lv.dinv, bk, cur)));
+    } else {
+      for (int64_t i = sc.tid; i < Lv.m; i += sc.nthr) cur[i] = Lv.dinv[i] * bk[i];
+    }
+    sc.sync();
+    for (int it = 0; it < npre; ++it) {
+      MGBX_G_DISPATCH(Lv.G, (ph_jacobi<GG>(sc, Lv.A, Lv.dinv, bk, cur, oth, nullptr)));
+      sc.sync();
+      double *t = cur;
+      cur = oth;
+      oth = t;
+    }
+    if (!last) {
+      MGBX_G_DISPATCH(Lv.G, (ph_spmv<GG>(sc, Lv.A, cur, bk, -1.0, Lv.r)));
+      sc.sync();
+      MGBX_G_DISPATCH(Lv.GTt, (ph_spmv<GG>(sc, Lv.Tt, Lv.r, nullptr, 1.0, P.lev[k + 1].b)));
+      sc.sync();
+    }
+  }
+  // ---- coarser levels by CTA 0 alone
+  if (GRID && k1 < P.nlev) {
+    if (blockIdx.x == 0) {
+      Scope<false> cta{(int64_t)threadIdx.x, (int64_t)blockDim.x, nullptr};
+      vcycle_levels<false>(P, cta, k1, P.nlev, P.lev[k1].b, nullptr);
+    }
+    sc.sync();
+  }
+  // ---- up
+  for (int k = k1 - 1; k >= k0; --k) {
+    if (k == P.nlev - 1) continue;   // bottom level: nothing coarser
+    const PLevel &Lv = P.lev[k];
+    const double *bk = (k == k0) ? btop : Lv.b;
+    const int want = P.nu;
+    const int done = (want >= 2) ? 2 : 1;
+    const int npre = want - done, npost = P.nu;
+    // buffer holding the pre-smoothed iterate: start buffer advanced by npre swaps
+    const bool start_x2 = ((npre + npost) & 1) != 0;
+    const bool cur_x2 = start_x2 != ((npre & 1) != 0);
+    double *cur = cur_x2 ? Lv.x2 : Lv.x, *oth = cur_x2 ? Lv.x : Lv.x2;
+    MGBX_G_DISPATCH(Lv.GT, (ph_spmv<GG>(sc, Lv.T, P.lev[k + 1].x, cur, 1.0, cur)));   // x += T xc (row-local)
+    sc.sync();
+    for (int it = 0; it < npost; ++it) {
+      const bool fin = (it == npost - 1) && (k == k0) && (dot_top != nullptr);
+      double pp = 0.0;
+      MGBX_G_DISPATCH(Lv.G, (pp = ph_jacobi<GG>(sc, Lv.A, Lv.dinv, bk, cur, oth, fin ? dot_top : nullptr)));
+      part += pp;
+      if (!fin) sc.sync();
+      double *t = cur;
+      cur = oth;
+      oth = t;
+    }
+  }
+  return part;
+}
+
+__global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_persistent(const PcgPlan *plan_g, double rtol2, int maxit) {
+  __shared__ PcgPlan P;
+  {
+    const uint64_t *src = reinterpret_cast<const uint64_t *>(plan_g);
+    uint64_t *dst = reinterpret_cast<uint64_t *>(&P);
+    for (int i = threadIdx.x; i < (int)(sizeof(PcgPlan) / sizeof(uint64_t)); i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+  Scope<true> sc{tid, nthr, P.bar};
+  const int64_t m = P.lev[0].m;
+  double *slot0 = P.partials, *slot1 = P.partials + kPcgMaxGrid, *slot2 = P.partials + 2 * kPcgMaxGrid;
+
+  // the plan in shared memory is read-only from here on; the p / p2 ping-pong lives in registers
+  double *pv = P.p, *pv2 = P.p2;
+  // x = 0, p = 0, r = b, |b|^2
+  double part = 0.0;
+  for (int64_t i = tid; i < m; i += nthr) {
+    const double bi = P.b[i];
+    P.x[i] = 0.0;
+    pv[i] = 0.0;
+    P.r[i] = bi;
+    part += bi * bi;
+  }
+  const double bb = grid_sum(part, slot0, P.bar);
+  int it = 0;
+  double rr = bb, status = 1.0;
+  if (bb > 0.0 && isfinite(bb)) {
+    const double target = rtol2 * bb;
+    double rz_old = 1.0, best = bb;
+    int since_best = 0;
+    const PLevel &top = P.lev[0];
+    while (it < maxit) {
+      // z = M^{-1} r, with r.z accumulated in the last smoothing sweep of the top level
+      const bool single = (P.nlev == 1);
+      double prz = vcycle_levels<true>(P, sc, 0, P.nbig, P.r, single ? nullptr : P.r);
+      const double *z = P.lev[0].x;
+      if (single) {   // one-level "hierarchy": no up-sweep ran, take the dot here
+        prz = 0.0;
+        for (int64_t i = tid; i < m; i += nthr) prz += P.r[i] * z[i];
+      }
+      const double rz = grid_sum(prz, slot1, P.bar);
+      const double beta = rz / rz_old;
+      rz_old = rz;
+      // p2 = z + beta p;  Ap = A p2 (neighbour values formed on the fly);  p2.Ap
+      double ppap = 0.0;
+      {
+        const int G = top.G;
+        const int64_t step = nthr / G;
+        const int sub = (int)(tid % G);
+        for (int64_t base = 0; base < m; base += step) {
+          const int64_t row = base + tid / G;
+          const bool valid = row < m;
+          double acc = 0.0;
+          if (valid) {
+            const int64_t b0 = top.A.ptr[row], e0 = top.A.ptr[row + 1];
+            for (int64_t k = b0 + sub; k < e0; k += G) {
+              const int32_t j = top.A.idx[k];
+              acc += top.A.val[k] * (z[j] + beta * pv[j]);
+            }
+          }
+          for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, G);
+          if (valid && sub == 0) {
+            const double pn = z[row] + beta * pv[row];
+            pv2[row] = pn;
+            P.Ap[row] = acc;
+            ppap += pn * acc;
+          }
+        }
+      }
+      const double pAp = grid_sum(ppap, slot2, P.bar);
+      {
+        double *t = pv;
+        pv = pv2;
+        pv2 = t;
+      }
+      ++it;
+      if (!(pAp > 0.0) || !isfinite(pAp)) {
+        status = -1.0;
+        break;
+      }
+      const double alpha = rz / pAp;
+      double prr = 0.0;
+      for (int64_t i = tid; i < m; i += nthr) {
+        P.x[i] += alpha * pv[i];
+        const double ri = P.r[i] - alpha * P.Ap[i];
+        P.r[i] = ri;
+        prr += ri * ri;
+      }
+      rr = grid_sum(prr, slot0, P.bar);
+      if (!isfinite(rr)) {
+        status = -1.0;
+        break;
+      }
+      if (rr <= target) break;
+      if (rr < best * 0.999) {
+        best = rr;
+        since_best = 0;
+      } else if (++since_best >= 25) {
+        break;   // stagnation at the attainable accuracy
+      }
+    }
+  }
+  if (tid == 0) {
+    P.out[0] = (double)it;
+    P.out[1] = rr;
+    P.out[2] = status;
+    P.out[3] = bb;
+  }
+}
+
+}  // namespace mgbx

@@ -55,7 +55,8 @@ class Problem(C.Structure):
 class Config(C.Structure):
     _fields_ = [("dense_direct_max", C.c_int32), ("coarse_max", C.c_int32), ("pcg_maxit", C.c_int32),
                 ("pcg_rtol", C.c_double), ("smoother_sweeps", C.c_int32), ("condense", C.c_int32),
-                ("device", C.c_int32), ("verbose", C.c_int32), ("use_graphs", C.c_int32), ("profile", C.c_int32)]
+                ("device", C.c_int32), ("verbose", C.c_int32), ("use_graphs", C.c_int32), ("profile", C.c_int32),
+                ("persistent", C.c_int32), ("tail_max", C.c_int32), ("pcg_rtol_final", C.c_double)]
 
 
 class StepOpts(C.Structure):
@@ -80,7 +81,7 @@ class ScalarsOut(C.Structure):
 EXPORTS = [
     "mgbx_default_config", "mgbx_default_step_opts", "mgbx_abi_version", "mgbx_device_count",
     "mgbx_create", "mgbx_destroy", "mgbx_last_error", "mgbx_step", "mgbx_scalars",
-    "mgbx_phase1_init", "mgbx_set_feasibility_box", "mgbx_reset_feasibility_state", "mgbx_handoff",
+    "mgbx_phase1_init", "mgbx_attach_feasibility", "mgbx_set_feasibility_box", "mgbx_reset_feasibility_state", "mgbx_handoff",
     "mgbx_matched_t", "mgbx_get_z", "mgbx_set_z", "mgbx_set_grids", "mgbx_level_size",
     "mgbx_barrier_eval", "mgbx_hessian_pattern", "mgbx_hessian_values", "mgbx_solve_newton_system",
     "mgbx_plan_pattern", "mgbx_launch_count", "mgbx_kernel_stats", "mgbx_set_profile",
@@ -119,6 +120,7 @@ def lib():
     L.mgbx_step.argtypes = [H, C.c_int, C.c_double, C.POINTER(StepOpts), C.POINTER(StepResult)]
     L.mgbx_scalars.argtypes = [H, C.c_int, C.POINTER(ScalarsOut)]
     L.mgbx_phase1_init.argtypes = [H, c_i32p, c_f64p, c_f64p]
+    L.mgbx_attach_feasibility.argtypes = [H, C.POINTER(Amg)]
     L.mgbx_set_feasibility_box.argtypes = [H, C.c_double, C.c_double]
     L.mgbx_reset_feasibility_state.argtypes = [H]
     L.mgbx_handoff.argtypes = [H]
@@ -181,9 +183,10 @@ class _Keep:
         return _ptr(a, c_i32p)
 
     def csr(self, M) -> Csr:
-        M = sp.csr_matrix(M)
-        M.sum_duplicates()
-        M.sort_indices()
+        if not (sp.isspmatrix_csr(M) and M.has_canonical_format):
+            M = sp.csr_matrix(M)
+            M.sum_duplicates()
+            M.sort_indices()
         return Csr(M.shape[0], M.shape[1], self.i64(M.indptr), self.i64(M.indices), self.f64(M.data))
 
 
@@ -208,7 +211,8 @@ def _pack_amg(keep: _Keep, M) -> Amg:
         ops[k] = keep.f64(np.ascontiguousarray(geom.operators[nm].transpose(0, 2, 1)))
     keep.bufs.append(ops)
     L = len(M.R_fine)
-    Rs = (Csr * L)(*[keep.csr(R) for R in M.R_fine])
+    # only R_fine[L-1] crosses the boundary with data: the library composes the coarser ones from T (mgbx.h)
+    Rs = (Csr * L)(*([Csr(R.shape[0], R.shape[1], None, None, None) for R in M.R_fine[:-1]] + [keep.csr(M.R_fine[-1])]))
     Ts = (Csr * max(1, L - 1))(*[keep.csr(T) for T in M.T])
     keep.bufs += [Rs, Ts]
     voff = np.asarray(M.var_offsets, dtype=np.int64).reshape(L, M.nu + 1)
@@ -252,8 +256,9 @@ class Handle:
         keep = _Keep()
         P = Problem()
         P.amg[0] = _pack_amg(keep, prob.M[0])
-        if with_feasibility and prob.M[1] is not None:
-            P.amg[1] = _pack_amg(keep, prob.M[1])
+        # the feasibility AMG is attached lazily, only when phase1_init reports that phase I must run
+        self._feas_M = prob.M[1] if with_feasibility else None
+        self._feas_attached = False
         n = prob.M[0].geometry.n
         P.f_grid = keep.colmajor(prob.f)
         P.g_grid = keep.colmajor(prob.g)
@@ -305,9 +310,22 @@ class Handle:
         return out
 
     # ---- phase I
+    def attach_feasibility(self):
+        if self._feas_attached:
+            return
+        if self._feas_M is None:
+            raise MgbxError(ERR_ARG, "phase I needed but the problem carries no feasibility AMG")
+        keep = _Keep()
+        a = _pack_amg(keep, self._feas_M)
+        self._check(lib().mgbx_attach_feasibility(self._h, C.byref(a)))
+        self._feas_attached = True
+
     def phase1_init(self):
         need, b, zmax = C.c_int32(), C.c_double(), C.c_double()
         self._check(lib().mgbx_phase1_init(self._h, C.byref(need), C.byref(b), C.byref(zmax)))
+        if need.value and not self._feas_attached:
+            self.attach_feasibility()
+            self._check(lib().mgbx_phase1_init(self._h, C.byref(need), C.byref(b), C.byref(zmax)))
         return bool(need.value), b.value, zmax.value
 
     def set_feasibility_box(self, b, R):
