@@ -119,7 +119,7 @@ typedef struct {
   int32_t coarse_max;        /* V-cycle is cut at the first level with <= this many unknowns (default 128 = the maximum) */
   int32_t pcg_maxit;         /* default 400 */
   double pcg_rtol;           /* relative residual, default 1e-11 */
-  int32_t smoother_sweeps;   /* l1-Jacobi / Chebyshev pre+post sweeps, default 2 */
+  int32_t smoother_sweeps;   /* pre = post smoothing sweeps (Chebyshev degree), default 2 */
   int32_t condense;          /* 1 (default): eliminate node-local :full variables exactly before PCG */
   int32_t device;            /* CUDA device ordinal, -1 = current */
   int32_t verbose;
@@ -128,6 +128,11 @@ typedef struct {
   int32_t persistent;        /* 1 (default): each PCG solve is ONE cooperative persistent kernel (one CTA per SM, grid barriers) */
   int32_t tail_max;          /* V-cycle levels with <= this many unknowns run inside CTA 0 of that kernel (default 1200) */
   double pcg_rtol_final;     /* relative residual during the finalize pass (stopping_exact), default 1e-13 */
+  int32_t fused;             /* 1 (default): fused element kernels (operator blocks staged once in shared memory);
+                                0: separate per-node and per-block kernels (always used when a block does not fit) */
+  int32_t smoother;          /* V-cycle smoother of the persistent kernel: 1 (default) Chebyshev of degree smoother_sweeps
+                                with diagonal scaling on [lam/cheb_ratio, lam], lam = Gershgorin bound; 0 l1-Jacobi */
+  double cheb_ratio;         /* default 4 */
 } mgbx_config;
 
 /* options of one mgb_step (src/mgb.jl:16-30; defaults src/mgb.jl:360-363) */
@@ -205,6 +210,17 @@ int mgbx_solve_newton_system(mgbx_handle *h, int which, int level, double t, con
 
 /* number of kernels launched through this handle so far (bench.py's gpu_launches) */
 int64_t mgbx_launch_count(const mgbx_handle *h);
+
+/* shape of the fine-level linear system and of the persistent solve kernel's plan (for roofline arithmetic);
+ * zero-filled until the first fine-level Newton system has been solved */
+typedef struct {
+  int32_t condensed, nlev, nbig, bottom_dense, grid, threads;
+  int64_t m[MGBX_MAX_LEVELS], nnz[MGBX_MAX_LEVELS], nnzT[MGBX_MAX_LEVELS];   /* active V-cycle levels, top first */
+  int64_t assembly_terms;     /* padded terms of the element-block -> CSR gather */
+  int64_t hblk_entries;       /* pairs * N * p * p */
+  int64_t galerkin_terms;     /* padded terms of all Galerkin product gathers */
+} mgbx_solver_info_t;
+int mgbx_solver_info(mgbx_handle *h, int which, mgbx_solver_info_t *out);
 
 /* per-kernel-class launch counts and (with profile on) summed device time in ms; names[k] are static strings.
  * Arrays must hold at least 16 entries. */

@@ -171,17 +171,26 @@ __global__ void __launch_bounds__(256) k_jacobi_first2(DevCsr A, const double *_
   }
 }
 
-// dinv = 1 / sum_k |a_ik|  (l1-Jacobi), diag = a_ii
-__global__ void k_l1diag(DevCsr A, double *dinv, double *diag) {
+// dinv = 1 / sum_k |a_ik|  (l1-Jacobi), diag = a_ii, and the Gershgorin bound of lambda_max(D^-1 A),
+// max_i sum_k |a_ik| / a_ii, folded with atomicMax on the bit pattern (non-negative doubles order like integers;
+// max is order-independent, so the result is deterministic).  *lam_bits must be zeroed before the launch.
+__global__ void __launch_bounds__(256) k_l1diag(DevCsr A, double *dinv, double *diag, unsigned long long *lam_bits) {
   const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= A.rows) return;
-  double s = 0.0, d = 0.0;
-  for (int64_t k = A.ptr[row]; k < A.ptr[row + 1]; ++k) {
-    s += fabs(A.val[k]);
-    if (A.idx[k] == row) d = A.val[k];
+  double ratio = 0.0;
+  if (row < A.rows) {
+    double s = 0.0, d = 0.0;
+    for (int64_t k = A.ptr[row]; k < A.ptr[row + 1]; ++k) {
+      s += fabs(A.val[k]);
+      if (A.idx[k] == row) d = A.val[k];
+    }
+    dinv[row] = s > 0.0 ? 1.0 / s : 0.0;
+    if (diag) diag[row] = d;
+    if (d > 0.0 && isfinite(s)) ratio = s / d;
   }
-  dinv[row] = s > 0.0 ? 1.0 / s : 0.0;
-  if (diag) diag[row] = d;
+  if (lam_bits) {
+    ratio = warp_max(ratio);
+    if ((threadIdx.x & 31) == 0 && ratio > 0.0) atomicMax(lam_bits, (unsigned long long)__double_as_longlong(ratio));
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -788,6 +797,211 @@ __global__ void __launch_bounds__(256) k_dense_symv(const double *__restrict__ M
   for (int j = lane; j < m; j += 32) s += r[j] * x[j];
   s = warp_sum(s);
   if (lane == 0) y[row] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused element kernels (north-star items 1 + 2): one pass per barrier evaluation.
+//   k_elem<NODE_F01>  apply_D -> F0/F1 -> (1/n) F1 + w.*c -> sum_k D_k' y_k      (k_node<F01> + k_blockgrad in one kernel)
+//   k_elem<NODE_F2>   apply_D -> F2 -> node-local Schur condensation -> sum_jk D_j' diag(h_jk) D_k   (k_node<F2> + k_blockhess)
+// A block owns `epb` whole elements per tile (one thread per broken node) and walks tiles grid-stride.  The
+// operator blocks of the tile are staged ONCE in shared memory (padded against bank conflicts) and serve both
+// the forward application D z and the adjoint / triple product; the per-node samples (G or the packed Hessian)
+// are exchanged through shared memory and never touch HBM.  Replaces, per evaluation, nD block matvecs +
+// map_rows + nD adjoint matvecs (src/convex.jl:155-179) resp. nD^2 block_fused_triple! calls each allocating
+// p x p x N (src/convex.jl:185-200, src/BlockMatrices.jl:170-212).
+// ------------------------------------------------------------------------------------------------
+struct ElemFused {
+  NodeParams np;
+  PairList pl;
+  double *Hblk;     // F2: pairs x N x p x p
+  double *gb;       // F01: nu x n
+  int64_t N;
+  int epb;          // elements per tile
+  int p1, ES;       // padded column stride and element stride of the staged operator blocks (doubles)
+  int nex;          // exchange rows
+  int nops;
+};
+
+inline size_t elem_fused_smem(int nops, int epb, int ES, int nu, int nex, int p) {
+  return sizeof(double) * ((size_t)nops * epb * ES + (size_t)(nu + nex) * epb * p);
+}
+
+template <int MODE, int NDT>
+__global__ void __launch_bounds__(256) k_elem(ElemFused Q) {
+  extern __shared__ double esm[];
+  const NodeParams &P = Q.np;
+  const int p = P.p, pp = p * p, p1 = Q.p1, ES = Q.ES, epb = Q.epb;
+  const int TM = epb * p;                       // node slots per tile
+  double *ops_s = esm;                          // [op][el][c][r] padded
+  double *zs = ops_s + (size_t)Q.nops * epb * ES;   // [var][slot]
+  double *ex = zs + (size_t)P.nu * TM;          // [row][slot]
+  const int tid = threadIdx.x;
+  double red[4] = {0.0, 0.0, 0.0, -INFINITY};
+  const int op4[4] = {0, 0, 0, 1};
+  const int64_t ntiles = (Q.N + epb - 1) / epb;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t e0 = tile * epb;
+    const int ne = (int)min((int64_t)epb, Q.N - e0);
+    const int T = ne * p;
+    const int64_t node0 = e0 * p;
+    __syncthreads();   // previous tile fully consumed
+    for (int o = 0; o < Q.nops; ++o) {
+      const double *src = P.ops[o] + e0 * (int64_t)pp;
+      double *dst = ops_s + (size_t)o * epb * ES;
+      for (int t = tid; t < ne * pp; t += blockDim.x) {
+        const int el = t / pp, rem = t - el * pp;
+        const int c = rem / p, r = rem - c * p;
+        dst[el * ES + c * p1 + r] = src[t];
+      }
+    }
+    for (int v = 0; v < P.nu; ++v)
+      for (int t = tid; t < T; t += blockDim.x) zs[v * TM + t] = P.zf[(int64_t)v * P.n + node0 + t];
+    __syncthreads();
+    const int el = tid / p, q = tid - el * p;
+    const bool on = tid < T;
+    const int64_t i = node0 + tid;
+    if (on) {
+      double y[NDT];
+      for (int j = 0; j < P.nD; ++j) {
+        const int v = P.D_var[j], o = P.D_op[j];
+        if (o < 0) y[j] = zs[v * TM + tid];
+        else {
+          const double *blk = ops_s + (size_t)o * epb * ES + el * ES + q;
+          const double *ze = zs + v * TM + el * p;
+          double acc = 0.0;
+          for (int c = 0; c < p; ++c) acc += blk[c * p1] * ze[c];
+          y[j] = acc;
+        }
+      }
+      const int nD = P.nD;
+      const double bwi = P.bw ? P.bw[i] : 1.0;
+      const bool active = !(P.bw && bwi == 0.0);
+      const double sc = P.bw ? bwi : P.inv_n;
+      double F1[NDT];
+      if (MODE == NODE_F01) {
+        double F0 = 0.0;
+        if (active) F0 = node_eval(P.cd, P.n, i, y, 1, F1, nullptr);
+        else
+          for (int j = 0; j < nD; ++j) F1[j] = 0.0;
+        const double wi = P.w[i];
+        double lin = 0.0;
+        for (int j = 0; j < nD; ++j) {
+          const double c = P.t * P.f[i + (int64_t)j * P.n];
+          lin += c * y[j];
+          ex[j * TM + tid] = (active ? sc * F1[j] : 0.0) + wi * c;
+        }
+        red[0] += active ? (P.bw ? bwi * F0 : F0) : 0.0;
+        red[1] += wi * lin;
+        if (!isfinite(F0)) red[2] += 1.0;
+      } else {
+        double F2[NDT * NDT];
+        if (active) {
+          node_eval(P.cd, P.n, i, y, 2, F1, F2);
+          for (int k = 0; k < nD * nD; ++k) F2[k] *= sc;
+        } else {
+          for (int k = 0; k < nD * nD; ++k) F2[k] = 0.0;
+        }
+        const int nK = P.nK, nE = P.nE;
+        if (nE == 0) {
+          int qq = 0;
+          for (int a = 0; a < nK; ++a)
+            for (int b = a; b < nK; ++b, ++qq) ex[qq * TM + tid] = F2[P.Krow[a] * nD + P.Krow[b]];
+        } else {
+          double hEE[16], hKE[NDT * 4];
+          for (int k = 0; k < nE * nE; ++k) hEE[k] = 0.0;
+          for (int k = 0; k < nK * nE; ++k) hKE[k] = 0.0;
+          for (int j = 0; j < nD; ++j) {
+            const int ej = P.Erow[j];
+            if (ej < 0) continue;
+            for (int k = 0; k < nD; ++k) {
+              const int ek = P.Erow[k];
+              if (ek >= 0) hEE[ej * nE + ek] += F2[j * nD + k];
+            }
+            for (int a = 0; a < nK; ++a) hKE[a * nE + ej] += F2[P.Krow[a] * nD + j];
+          }
+          spd_inverse(hEE, nE);
+          {
+            int qq = 0;
+            for (int a = 0; a < nE; ++a)
+              for (int b = a; b < nE; ++b, ++qq) P.hEEinv[i + (int64_t)qq * P.n] = hEE[a * nE + b];
+          }
+          for (int k = 0; k < nK * nE; ++k) P.hKE[i + (int64_t)k * P.n] = hKE[k];
+          int qq = 0;
+          for (int a = 0; a < nK; ++a)
+            for (int b = a; b < nK; ++b, ++qq) {
+              double s = F2[P.Krow[a] * nD + P.Krow[b]];
+              for (int ev = 0; ev < nE; ++ev) {
+                double wv = 0.0;
+                for (int ew = 0; ew < nE; ++ew) wv += hEE[ev * nE + ew] * hKE[b * nE + ew];
+                s -= hKE[a * nE + ev] * wv;
+              }
+              ex[qq * TM + tid] = s;
+            }
+        }
+      }
+    }
+    __syncthreads();
+    if (MODE == NODE_F01) {
+      // gb[v][node0 + (el, c)] = sum_{j in rows(v)} sum_q D_j[q][c] G_j[q]
+      if (on) {
+        const int c = q;
+        for (int v = 0; v < P.nu; ++v) {
+          double acc = 0.0;
+          for (int j = 0; j < P.nD; ++j) {
+            if (P.D_var[j] != v) continue;
+            const int o = P.D_op[j];
+            const double *g = ex + j * TM + el * p;
+            if (o < 0) acc += g[c];
+            else {
+              const double *blk = ops_s + (size_t)o * epb * ES + el * ES + c * p1;
+              for (int k = 0; k < p; ++k) acc += blk[k] * g[k];
+            }
+          }
+          Q.gb[(int64_t)v * P.n + i] = acc;
+        }
+      }
+    } else {
+      // Hblk[((pair*N + e)*p + r)*p + c] = sum_{ja in rows(va), kb in rows(vb)} sum_q D_ja[q][r] h[q] D_kb[q][c]
+      const int nK = P.nK;
+      const int per = ne * pp;
+      for (int pr = 0; pr < Q.pl.npairs; ++pr) {
+        const int va = Q.pl.va[pr], vb = Q.pl.vb[pr];
+        double *out = Q.Hblk + ((int64_t)pr * Q.N + e0) * pp;
+        for (int t = tid; t < per; t += blockDim.x) {
+          const int e2 = t / pp, rem = t - e2 * pp;
+          const int r = rem / p, c = rem - r * p;
+          double acc = 0.0;
+          for (int ja = 0; ja < nK; ++ja) {
+            const int j = P.Krow[ja];
+            if (P.D_var[j] != va) continue;
+            const int oj = P.D_op[j];
+            for (int kb = 0; kb < nK; ++kb) {
+              const int k = P.Krow[kb];
+              if (P.D_var[k] != vb) continue;
+              const int ok = P.D_op[k];
+              const int a = ja < kb ? ja : kb, b = ja < kb ? kb : ja;
+              const double *h = ex + (a * nK - (a * (a - 1)) / 2 + (b - a)) * TM + e2 * p;
+              if (oj < 0 && ok < 0) {
+                if (r == c) acc += h[r];
+              } else if (oj < 0) {
+                acc += h[r] * ops_s[(size_t)ok * epb * ES + e2 * ES + c * p1 + r];
+              } else if (ok < 0) {
+                acc += ops_s[(size_t)oj * epb * ES + e2 * ES + r * p1 + c] * h[c];
+              } else {
+                const double *dj = ops_s + (size_t)oj * epb * ES + e2 * ES + r * p1;
+                const double *dk = ops_s + (size_t)ok * epb * ES + e2 * ES + c * p1;
+                double s = 0.0;
+                for (int k2 = 0; k2 < p; ++k2) s += dj[k2] * h[k2] * dk[k2];
+                acc += s;
+              }
+            }
+          }
+          out[t] = acc;
+        }
+      }
+    }
+  }
+  if (MODE == NODE_F01) grid_reduce<4>(red, op4, P.partials, P.ticket, P.red_out);
 }
 
 }  // namespace mgbx

@@ -26,6 +26,7 @@
 #include "host_sparse.hpp"
 #include "kernels.cuh"
 #include "solver_kernels.cuh"
+#include "setup_kernels.cuh"
 
 using namespace mgbx;
 
@@ -41,9 +42,9 @@ static thread_local std::string g_last_error;
 
 // kernel classes for the optional per-class device timing (cfg.profile) and launch statistics
 enum KClass { KC_NODE_F01 = 0, KC_NODE_F2, KC_BLOCKGRAD, KC_BLOCKHESS, KC_GATHER, KC_SPMV, KC_JACOBI, KC_SPGEMM, KC_VEC, KC_COND,
-              KC_DENSE, KC_PCG, KC_COUNT };
+              KC_DENSE, KC_PCG, KC_ELEM_F01, KC_ELEM_F2, KC_COUNT };
 static const char *kKClassNames[KC_COUNT] = {"node_f01", "node_f2", "blockgrad", "blockhess", "csr_gather", "spmv", "jacobi",
-                                             "spgemm", "vector", "condense", "dense", "pcg_persistent"};
+                                             "spgemm", "vector", "condense", "dense", "pcg_persistent", "elem_f01", "elem_f2"};
 enum { STAGE_F01 = -1, STAGE_F2 = -2, STAGE_SOLVE = -3 };
 #define LAUNCH(kc, ...)   \
   do {                    \
@@ -82,11 +83,12 @@ inline unsigned int nblk(int64_t work, int threads = 256) { return (unsigned int
 struct Pool {
   std::vector<void *> ptrs;
   size_t bytes = 0;
+  cudaStream_t stream = nullptr;   // set at create: allocations are stream-ordered (cudaMallocAsync), cheap and reusable
   template <class T>
   T *alloc(size_t n) {
     if (n == 0) n = 1;
     void *p = nullptr;
-    cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+    cudaError_t e = cudaMallocAsync(&p, n * sizeof(T), stream);
     if (e != cudaSuccess) throw std::runtime_error(std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
     ptrs.push_back(p);
     bytes += n * sizeof(T);
@@ -105,8 +107,9 @@ struct Pool {
     return d;
   }
   void release() {
-    for (void *p : ptrs) cudaFree(p);
+    for (void *p : ptrs) cudaFreeAsync(p, stream);
     ptrs.clear();
+    if (stream) cudaStreamSynchronize(stream);
   }
 };
 
@@ -159,34 +162,143 @@ SellPlan upload_sell(Pool &pool, const std::vector<int64_t> &ptr, const std::vec
   return P;
 }
 
-// Term list of the sparse product C = Lm * Rm, built on the device (one thread per non-zero of C; two passes).
-SellPlan device_product_plan(Pool &pool, const DevCsr &Lm, const DevCsr &Rm, const DevCsr &C, bool variable_left, cudaStream_t s) {
+
+// temporary device CSR (plan construction only), freed explicitly
+struct TempCsr {
+  DevCsr d;
+  cudaStream_t s = nullptr;
+  void free_all() {
+    if (d.ptr) cudaFreeAsync(d.ptr, s);
+    if (d.idx) cudaFreeAsync(d.idx, s);
+    if (d.val) cudaFreeAsync(d.val, s);
+    d = DevCsr();
+  }
+};
+TempCsr upload_csr_temp(const HostCsr &H, cudaStream_t s, bool with_values) {
+  TempCsr T;
+  T.s = s;
+  T.d.rows = H.rows;
+  T.d.cols = H.cols;
+  T.d.nnz = H.nnz();
+  CK(cudaMallocAsync((void **)&T.d.ptr, sizeof(int64_t) * (H.rows + 1), s));
+  CK(cudaMallocAsync((void **)&T.d.idx, sizeof(int32_t) * std::max<int64_t>(1, H.nnz()), s));
+  CK(cudaMemcpyAsync(T.d.ptr, H.ptr.data(), sizeof(int64_t) * (H.rows + 1), cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(T.d.idx, H.idx.data(), sizeof(int32_t) * H.nnz(), cudaMemcpyHostToDevice, s));
+  if (with_values && !H.val.empty()) {
+    CK(cudaMallocAsync((void **)&T.d.val, sizeof(double) * std::max<int64_t>(1, H.nnz()), s));
+    CK(cudaMemcpyAsync(T.d.val, H.val.data(), sizeof(double) * H.nnz(), cudaMemcpyHostToDevice, s));
+  }
+  CK(cudaStreamSynchronize(s));
+  return T;
+}
+
+// stream-ordered scratch allocations for plan construction (no device-wide synchronisation, memory stays in the
+// device's default pool between handles: its release threshold is raised at mgbx_create)
+template <class T>
+T *tmp_alloc(size_t n, cudaStream_t s) {
+  void *p = nullptr;
+  CK(cudaMallocAsync(&p, std::max<size_t>(n, 1) * sizeof(T), s));
+  return (T *)p;
+}
+inline void tmp_free(void *p, cudaStream_t s) {
+  if (p) cudaFreeAsync(p, s);
+}
+
+// Sparsity pattern of A*B on the device: candidate keys (row << 32 | col) -> radix sort -> unique -> CSR.
+DevCsr device_symbolic(Pool &pool, const DevCsr &A, const DevCsr &B, cudaStream_t s) {
+  if (A.cols != B.rows) throw std::runtime_error("device_symbolic: inner dimensions differ");
+  DevCsr C;
+  C.rows = A.rows;
+  C.cols = B.cols;
+  int64_t *cand = tmp_alloc<int64_t>(A.rows + 1, s), *offs = tmp_alloc<int64_t>(A.rows + 1, s);
+  k_sym_count<<<nblk(A.rows + 1), 256, 0, s>>>(A, B, cand);
+  CK(cudaGetLastError());
+  size_t tmp_bytes = 0;
+  CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cand, offs, (int)(A.rows + 1), s));
+  char *tmp = tmp_alloc<char>(tmp_bytes, s);
+  CK(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, cand, offs, (int)(A.rows + 1), s));
+  int64_t total = 0;
+  CK(cudaMemcpyAsync(&total, offs + A.rows, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  tmp_free(tmp, s);
+  if (total > INT32_MAX) {
+    tmp_free(cand, s);
+    tmp_free(offs, s);
+    throw std::runtime_error("device_symbolic: more than 2^31 candidate entries");
+  }
+  unsigned long long *keys = tmp_alloc<unsigned long long>(total, s), *keys2 = tmp_alloc<unsigned long long>(total, s);
+  int *nsel = tmp_alloc<int>(1, s);
+  int nnz = 0;
+  if (total > 0) {
+    k_sym_fill<<<nblk(A.rows), 256, 0, s>>>(A, B, offs, keys);
+    CK(cudaGetLastError());
+    int end_bit = 33;
+    while (end_bit < 64 && ((unsigned long long)A.rows >> (end_bit - 32)) != 0) ++end_bit;
+    CK(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, keys, keys2, (int)total, 0, end_bit, s));
+    tmp = tmp_alloc<char>(tmp_bytes, s);
+    CK(cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, keys, keys2, (int)total, 0, end_bit, s));
+    tmp_free(tmp, s);
+    CK(cub::DeviceSelect::Unique(nullptr, tmp_bytes, keys2, keys, nsel, (int)total, s));
+    tmp = tmp_alloc<char>(tmp_bytes, s);
+    CK(cub::DeviceSelect::Unique(tmp, tmp_bytes, keys2, keys, nsel, (int)total, s));
+    tmp_free(tmp, s);
+    CK(cudaMemcpyAsync(&nnz, nsel, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  C.nnz = nnz;
+  C.ptr = pool.alloc<int64_t>(C.rows + 1);
+  C.idx = pool.alloc<int32_t>(C.nnz);
+  C.val = pool.zeros<double>(C.nnz, s);
+  k_sym_finish<<<nblk(std::max<int64_t>(C.nnz, C.rows + 1)), 256, 0, s>>>(keys, C.nnz, C.rows, C.ptr, C.idx);
+  CK(cudaGetLastError());
+  tmp_free(keys, s);
+  tmp_free(keys2, s);
+  tmp_free(nsel, s);
+  tmp_free(cand, s);
+  tmp_free(offs, s);
+  CK(cudaStreamSynchronize(s));
+  return C;
+}
+
+// two-pass sliced-ELL construction shared by the device plan builders: COUNT(P, width) then FILL(P)
+template <class CountFn, class FillFn>
+SellPlan build_sell_two_pass(Pool &pool, int64_t nout, bool with_weights, cudaStream_t s, CountFn count, FillFn fill) {
   SellPlan P;
-  P.nout = C.nnz;
-  P.nslices = (P.nout + 31) / 32;
-  if (Lm.nnz > INT32_MAX || Rm.nnz > INT32_MAX || C.rows > INT32_MAX) throw std::runtime_error("product plan: index exceeds 32 bits");
-  if (P.nout == 0) return P;
-  int32_t *rowof = nullptr, *width = nullptr;
-  CK(cudaMalloc(&rowof, sizeof(int32_t) * P.nout));
-  CK(cudaMalloc(&width, sizeof(int32_t) * P.nslices));
-  P.cnt = pool.alloc<int32_t>(P.nout);
-  k_csr_rows<<<nblk(C.rows), 256, 0, s>>>(C, rowof);
-  k_prod_plan<0><<<nblk(P.nslices * 32), 256, 0, s>>>(Lm, Rm, C, rowof, variable_left ? 1 : 0, P, width);
+  P.nout = nout;
+  P.nslices = (nout + 31) / 32;
+  if (nout == 0) return P;
+  int32_t *width = tmp_alloc<int32_t>(P.nslices, s);
+  P.cnt = pool.alloc<int32_t>(nout);
+  count(P, width);
+  CK(cudaGetLastError());
   std::vector<int32_t> hwid(P.nslices);
   CK(cudaMemcpyAsync(hwid.data(), width, sizeof(int32_t) * P.nslices, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   std::vector<int64_t> sptr(P.nslices + 1, 0);
   for (int64_t sl = 0; sl < P.nslices; ++sl) sptr[sl + 1] = sptr[sl] + 32 * (int64_t)hwid[sl];
-  const int64_t total = sptr[P.nslices];
-  P.nterms = total;
+  P.nterms = sptr[P.nslices];
   P.sptr = pool.upload<int64_t>(sptr.data(), sptr.size(), s);
-  P.src = pool.zeros<int32_t>(total, s);
-  P.w = pool.zeros<double>(total, s);
-  k_prod_plan<1><<<nblk(P.nslices * 32), 256, 0, s>>>(Lm, Rm, C, rowof, variable_left ? 1 : 0, P, width);
+  P.src = pool.zeros<int32_t>(P.nterms, s);
+  P.w = with_weights ? pool.zeros<double>(P.nterms, s) : nullptr;
+  fill(P, width);
   CK(cudaGetLastError());
+  tmp_free(width, s);
   CK(cudaStreamSynchronize(s));
-  cudaFree(rowof);
-  cudaFree(width);
+  return P;
+}
+
+// Term list of the sparse product C = Lm * Rm, built on the device (one thread per non-zero of C; two passes).
+SellPlan device_product_plan(Pool &pool, const DevCsr &Lm, const DevCsr &Rm, const DevCsr &C, bool variable_left, cudaStream_t s) {
+  if (Lm.nnz > INT32_MAX || Rm.nnz > INT32_MAX || C.rows > INT32_MAX) throw std::runtime_error("product plan: index exceeds 32 bits");
+  if (C.nnz == 0) return SellPlan();
+  int32_t *rowof = tmp_alloc<int32_t>(C.nnz, s);
+  k_csr_rows<<<nblk(C.rows), 256, 0, s>>>(C, rowof);
+  const unsigned int g = nblk(((C.nnz + 31) / 32) * 32);
+  const int vl = variable_left ? 1 : 0;
+  SellPlan P = build_sell_two_pass(
+      pool, C.nnz, true, s, [&](SellPlan &Q, int32_t *width) { k_prod_plan<0><<<g, 256, 0, s>>>(Lm, Rm, C, rowof, vl, Q, width); },
+      [&](SellPlan &Q, int32_t *width) { k_prod_plan<1><<<g, 256, 0, s>>>(Lm, Rm, C, rowof, vl, Q, width); });
+  tmp_free(rowof, s);
   return P;
 }
 
@@ -200,7 +312,7 @@ struct SysLevel {
   // Galerkin gather plans: AT = A*T  and  A_coarse = T'*AT, one fixed-order sliced-ELL gather each
   SellPlan s1, s2;
   bool has_coarser = false, T_identity = false;
-  double *dinv = nullptr, *diag = nullptr;
+  double *dinv = nullptr, *diag = nullptr, *lam = nullptr;   // lam: Gershgorin bound of lambda_max(D^-1 A) (device scalar)
   double *b = nullptr, *x = nullptr, *x2 = nullptr, *r = nullptr;   // V-cycle work
   double *dense = nullptr, *dense_inv = nullptr, *dscale = nullptr;
   int spmv_group = 1;
@@ -219,6 +331,7 @@ struct System {
   double *Hblk = nullptr;
   int64_t hblk_size = 0;
   int cut = -1;                      // V-cycle bottom (dense inverse) level index, -1: none
+  bool dense_elements = false;       // spectral-type geometry (one dense "element"): small systems are solved directly
   // PCG work at the largest size
   double *pc_r = nullptr, *pc_z = nullptr, *pc_p = nullptr, *pc_Ap = nullptr, *pc_x = nullptr, *pc_b = nullptr;
   std::map<int, cudaGraphExec_t> graphs;        // captured PCG iteration per top level (non-persistent path)
@@ -305,6 +418,24 @@ void launch_node(const NodeParams &P, unsigned int grid, cudaStream_t s) {
   else if (P.nD <= 6) k_node<MODE, 6><<<grid, kRedThreads, 0, s>>>(P);
   else if (P.nD <= 8) k_node<MODE, 8><<<grid, kRedThreads, 0, s>>>(P);
   else k_node<MODE, MGBX_MAX_ND><<<grid, kRedThreads, 0, s>>>(P);
+}
+
+// fused element kernel (k_elem), same NDT dispatch; the dynamic shared-memory limit is raised once per instantiation
+template <int MODE, int NDT>
+void launch_elem_inst(const ElemFused &Q, unsigned int grid, size_t smem, cudaStream_t s) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    CK(cudaFuncSetAttribute(k_elem<MODE, NDT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr_done = true;
+  }
+  k_elem<MODE, NDT><<<grid, 256, smem, s>>>(Q);
+}
+template <int MODE>
+void launch_elem(const ElemFused &Q, unsigned int grid, size_t smem, cudaStream_t s) {
+  if (Q.np.nD <= 4) launch_elem_inst<MODE, 4>(Q, grid, smem, s);
+  else if (Q.np.nD <= 6) launch_elem_inst<MODE, 6>(Q, grid, smem, s);
+  else if (Q.np.nD <= 8) launch_elem_inst<MODE, 8>(Q, grid, smem, s);
+  else launch_elem_inst<MODE, MGBX_MAX_ND>(Q, grid, smem, s);
 }
 
 struct Engine {
@@ -476,6 +607,28 @@ struct Engine {
     for (int j = 0; j < A.nD; ++j) P.Krow[j] = j;
     return P;
   }
+
+  // tile geometry of the fused element kernel; false: fall back to the separate node / block kernels
+  // (operator blocks too large for shared memory, e.g. the dense spectral "element")
+  bool elem_fused_setup(Amg &A, const NodeParams &NP, int nex, ElemFused &Q, size_t &smem, unsigned int &grid) {
+    if (!h->cfg.fused || A.p > 256) return false;
+    memset(&Q, 0, sizeof(Q));
+    Q.np = NP;
+    Q.N = A.N;
+    Q.nops = A.nops;
+    Q.p1 = A.p | 1;
+    Q.ES = (A.p * Q.p1) | 1;
+    Q.nex = nex;
+    int epb = std::max(1, 256 / A.p);
+    const size_t cap = 216 * 1024;
+    while (epb > 1 && elem_fused_smem(A.nops, epb, Q.ES, A.nu, nex, A.p) > cap) epb = (epb + 1) / 2;
+    smem = elem_fused_smem(A.nops, epb, Q.ES, A.nu, nex, A.p);
+    if (smem > cap) return false;
+    Q.epb = epb;
+    const int64_t ntiles = (A.N + epb - 1) / epb;
+    grid = (unsigned int)std::max<int64_t>(1, std::min<int64_t>(ntiles, kRedBlocks));
+    return true;
+  }
   unsigned int red_grid(int64_t work) {
     const int64_t b = (work + kRedThreads - 1) / kRedThreads;
     return (unsigned int)std::max<int64_t>(1, std::min<int64_t>(b, kRedBlocks));
@@ -488,9 +641,17 @@ struct Engine {
     prolong_to_fine(A, J, x, zbase, A.zf);
     NodeParams P = node_params(A, t);
     if (!use_bw) P.bw = nullptr;
-    LAUNCH(KC_NODE_F01, launch_node<NODE_F01>(P, red_grid(A.n), s));
-    ElemParams E = elem_params(A);
-    LAUNCH(KC_BLOCKGRAD, k_blockgrad<<<nblk((int64_t)A.nu * A.n), 256, 0, s>>>(E, A.G, A.gb, A.nu));
+    ElemFused Q;
+    size_t smem = 0;
+    unsigned int grid = 0;
+    if (elem_fused_setup(A, P, A.nD, Q, smem, grid)) {
+      Q.gb = A.gb;
+      LAUNCH(KC_ELEM_F01, launch_elem<NODE_F01>(Q, grid, smem, s));
+    } else {
+      LAUNCH(KC_NODE_F01, launch_node<NODE_F01>(P, red_grid(A.n), s));
+      ElemParams E = elem_params(A);
+      LAUNCH(KC_BLOCKGRAD, k_blockgrad<<<nblk((int64_t)A.nu * A.n), 256, 0, s>>>(E, A.G, A.gb, A.nu));
+    }
     restrict_from_fine(A, J, A.gb, gout);
     LAUNCH(KC_VEC, k_dot2<<<red_grid(A.m[J]), kRedThreads, 0, s>>>(A.m[J], gout, nullptr, h->partials, h->ticket, h->dscal + 4));
     stage_end(STAGE_F01, st);
@@ -508,6 +669,12 @@ struct Engine {
 
   // ---------------------------------------------------------------- system assembly
   System &system_for(Amg &A, int J);
+  // Dense Cholesky for tiny systems and for spectral (dense) discretisations; finite-element systems above the
+  // coarse size go through the V-cycle PCG, which is faster there than a dense factorisation per Newton step.
+  bool use_direct(const System &S, const SysLevel &Lv) const {
+    if (Lv.m > h->cfg.dense_direct_max) return false;
+    return Lv.m <= kCoarseMaxDense || S.dense_elements || S.lev.size() == 1;
+  }
   void assemble(Amg &A, System &S, int J, double t, const double *zbase, const double *x);
   void setup_hierarchy(Amg &A, System &S, int ktop);
   void dense_factor(System &S, SysLevel &Lv, bool want_inverse);
@@ -550,6 +717,7 @@ std::unique_ptr<System> build_system(mgbx_handle *h, Amg &A, bool condensed, int
   const int L = ltop + 1;            // levels 0..ltop take part
   S->condensed = condensed;
   S->ltop = ltop;
+  S->dense_elements = A.p > 64;
   if (condensed && ltop != A.L - 1) throw std::runtime_error("internal: condensation only at the fine level");
   // prolongation from the top level of this system to the broken fine space
   HostCsr Rtop_store;
@@ -634,64 +802,69 @@ std::unique_ptr<System> build_system(mgbx_handle *h, Amg &A, bool condensed, int
   HostCsr Einc = element_incidence(Rtop, A.N, A.p, used, A.n, colmap, mtop);
   HostCsr pat = plan_pattern(Einc);
   if (vb) fprintf(stderr, "[mgbx] build_system(cond=%d): pattern m=%lld nnz=%lld %.3fs\n", (int)condensed, (long long)mtop, (long long)pat.nnz(), tm.lap());
-  // gather lists: for each nz of the pattern, the Hblk entries (and weights) that sum into it
+  // gather plan, built on the device: for each nz of the pattern, the Hblk entries (and weights) that sum into it
   const int p = A.p;
   const int64_t pp = (int64_t)p * p;
   S->hblk_size = (int64_t)S->pl.npairs * A.N * pp;
+  if (S->hblk_size > INT32_MAX) throw std::runtime_error("element block array exceeds 32-bit gather indices");
+  S->lev[0].A = upload_csr(pool, pat, s, false);
   {
-    const int64_t nnz = pat.nnz();
-    std::vector<int64_t> cnt(nnz + 1, 0);
     bool unit = true;
-    auto visit = [&](auto &&fn) {
-      for (int pr = 0; pr < S->pl.npairs; ++pr) {
-        const int va = S->pl.va[pr], vb = S->pl.vb[pr];
-        for (int64_t e = 0; e < A.N; ++e)
-          for (int r = 0; r < p; ++r) {
-            const int64_t ra = (int64_t)va * A.n + e * p + r;
-            for (int64_t ka = Rtop.ptr[ra]; ka < Rtop.ptr[ra + 1]; ++ka) {
-              const int64_t row = colmap[Rtop.idx[ka]];
-              if (row < 0) continue;
-              for (int c = 0; c < p; ++c) {
-                const int64_t rb = (int64_t)vb * A.n + e * p + c;
-                for (int64_t kb = Rtop.ptr[rb]; kb < Rtop.ptr[rb + 1]; ++kb) {
-                  const int64_t col = colmap[Rtop.idx[kb]];
-                  if (col < 0) continue;
-                  const int64_t nz = find_in_row(pat, row, (int32_t)col);
-                  if (nz < 0) throw std::runtime_error("internal: assembly pattern misses an entry");
-                  fn(nz, ((int64_t)pr * A.N + e) * pp + (int64_t)r * p + c, Rtop.val[ka] * Rtop.val[kb]);
-                }
-              }
-            }
-          }
+    for (double v : Rtop.val)
+      if (v != 1.0) {
+        unit = false;
+        break;
       }
-    };
-    visit([&](int64_t nz, int64_t, double wgt) {
-      cnt[nz + 1]++;
-      if (wgt != 1.0) unit = false;
-    });
-    for (int64_t k = 0; k < nnz; ++k) cnt[k + 1] += cnt[k];
-    std::vector<int64_t> gidx(cnt[nnz]);
-    std::vector<double> gw(unit ? 0 : cnt[nnz]);
-    std::vector<int64_t> pos(cnt.begin(), cnt.end() - 1);
-    visit([&](int64_t nz, int64_t src, double wgt) {
-      const int64_t q = pos[nz]++;
-      gidx[q] = src;
-      if (!unit) gw[q] = wgt;
-    });
-    if (S->hblk_size > INT32_MAX) throw std::runtime_error("element block array exceeds 32-bit gather indices");
-    S->top = upload_sell(pool, cnt, gidx, unit ? nullptr : &gw, s);
+    TempCsr einct = upload_csr_temp(transpose(Einc), s, false);
+    TempCsr rtmp;
+    TopPlanParams Q;
+    memset(&Q, 0, sizeof(Q));
+    if (ltop == A.L - 1) Q.R = A.RL;
+    else {
+      rtmp = upload_csr_temp(Rtop, s, true);
+      Q.R = rtmp.d;
+    }
+    Q.EincT = einct.d;
+    Q.pat = S->lev[0].A;
+    Q.n = A.n;
+    Q.N = A.N;
+    Q.p = p;
+    Q.unit = unit ? 1 : 0;
+    Q.nkept = (int)S->kept.size();
+    for (int q = 0; q < Q.nkept; ++q) {
+      Q.kept[q] = S->kept[q];
+      Q.off[q] = S->lev[0].off[q];
+      Q.rcol0[q] = A.voff[L - 1][S->kept[q]];
+    }
+    Q.off[Q.nkept] = S->lev[0].off[Q.nkept];
+    for (int qa = 0; qa < Q.nkept; ++qa)
+      for (int qb = 0; qb < Q.nkept; ++qb) {
+        int pr = -1;
+        for (int k = 0; k < S->pl.npairs; ++k)
+          if (S->pl.va[k] == S->kept[qa] && S->pl.vb[k] == S->kept[qb]) pr = k;
+        Q.pair_of[qa * Q.nkept + qb] = pr;
+      }
+    int32_t *rowof = tmp_alloc<int32_t>(pat.nnz(), s);
+    k_csr_rows<<<nblk(pat.rows), 256, 0, s>>>(S->lev[0].A, rowof);
+    Q.rowof = rowof;
+    const unsigned int g = nblk(((pat.nnz() + 31) / 32) * 32);
+    S->top = build_sell_two_pass(
+        pool, pat.nnz(), !unit, s, [&](SellPlan &P, int32_t *width) { k_top_plan<0><<<g, 256, 0, s>>>(Q, P, width); },
+        [&](SellPlan &P, int32_t *width) { k_top_plan<1><<<g, 256, 0, s>>>(Q, P, width); });
+    tmp_free(rowof, s);
+    einct.free_all();
+    if (rtmp.d.ptr) rtmp.free_all();
   }
   S->Hblk = pool.alloc<double>(S->hblk_size);
-  if (vb) fprintf(stderr, "[mgbx]   gather lists %.3fs\n", tm.lap());
-  // hierarchy patterns
-  HostCsr cur = pat;
+  if (vb) fprintf(stderr, "[mgbx]   gather plan (%lld padded terms) %.3fs\n", (long long)S->top.nterms, tm.lap());
+  // hierarchy patterns (device symbolic products) and Galerkin gather plans
   for (int k = 0; k < nlev; ++k) {
     SysLevel &Lv = S->lev[k];
     const int l = L - 1 - k;
-    if (k == 0) Lv.A = upload_csr(pool, cur, s, false);   // deeper levels were set by their parent below
     Lv.spmv_group = Engine::group_for(Lv.A);
     Lv.dinv = pool.alloc<double>(Lv.m);
     Lv.diag = pool.alloc<double>(Lv.m);
+    Lv.lam = pool.zeros<double>(1, s);
     Lv.b = pool.alloc<double>(Lv.m);
     Lv.x = pool.alloc<double>(Lv.m);
     Lv.x2 = pool.alloc<double>(Lv.m);
@@ -710,18 +883,16 @@ std::unique_ptr<System> build_system(mgbx_handle *h, Amg &A, bool condensed, int
       if (Lv.T_identity) {
         S->lev[k + 1].A = Lv.A;   // same matrix: the coarser level aliases this one
       } else {
-        HostCsr ATp = spgemm_symbolic(cur, Tk);
-        HostCsr nxt = spgemm_symbolic(Ttk, ATp);
+        const double t_host = tm.lap();
+        Lv.AT = device_symbolic(pool, Lv.A, Lv.T, s);
+        S->lev[k + 1].A = device_symbolic(pool, Lv.Tt, Lv.AT, s);
         const double t_sym = tm.lap();
-        Lv.AT = upload_csr(pool, ATp, s, false);
-        S->lev[k + 1].A = upload_csr(pool, nxt, s, false);
         Lv.s1 = device_product_plan(pool, Lv.A, Lv.T, Lv.AT, true, s);
         Lv.s2 = device_product_plan(pool, Lv.Tt, Lv.AT, S->lev[k + 1].A, false, s);
-        cur = std::move(nxt);
         if (vb)
-          fprintf(stderr, "[mgbx]   level %d: m=%lld -> %lld, nnz(A_c)=%lld, plan entries %lld + %lld, symbolic %.3fs plans %.3fs\n", k,
-                  (long long)Lv.m, (long long)S->lev[k + 1].m, (long long)cur.nnz(), (long long)Lv.s1.nterms, (long long)Lv.s2.nterms, t_sym,
-                  tm.lap());
+          fprintf(stderr, "[mgbx]   level %d: m=%lld -> %lld, nnz(A_c)=%lld, plan entries %lld + %lld, host %.3fs symbolic %.3fs plans %.3fs\n", k,
+                  (long long)Lv.m, (long long)S->lev[k + 1].m, (long long)S->lev[k + 1].A.nnz, (long long)Lv.s1.nterms, (long long)Lv.s2.nterms,
+                  t_host, t_sym, tm.lap());
       }
     }
   }
@@ -777,11 +948,20 @@ void Engine::assemble(Amg &A, System &S, int J, double t, const double *zbase, c
   P.Hn = A.Hn;
   P.hEEinv = A.hEEinv;
   P.hKE = A.hKE;
-  LAUNCH(KC_NODE_F2, launch_node<NODE_F2>(P, red_grid(A.n), s));
-  ElemParams E = elem_params(A);
-  E.nK = S.nK;
-  for (int j = 0; j < S.nK; ++j) E.Krow[j] = S.Krow[j];
-  LAUNCH(KC_BLOCKHESS, k_blockhess<<<nblk(S.hblk_size), 256, 0, s>>>(E, S.pl, A.Hn, S.Hblk));
+  ElemFused Q;
+  size_t smem = 0;
+  unsigned int grid = 0;
+  if (elem_fused_setup(A, P, std::max(A.nD, S.nK * (S.nK + 1) / 2), Q, smem, grid)) {
+    Q.pl = S.pl;
+    Q.Hblk = S.Hblk;
+    LAUNCH(KC_ELEM_F2, launch_elem<NODE_F2>(Q, grid, smem, s));
+  } else {
+    LAUNCH(KC_NODE_F2, launch_node<NODE_F2>(P, red_grid(A.n), s));
+    ElemParams E = elem_params(A);
+    E.nK = S.nK;
+    for (int j = 0; j < S.nK; ++j) E.Krow[j] = S.Krow[j];
+    LAUNCH(KC_BLOCKHESS, k_blockhess<<<nblk(S.hblk_size), 256, 0, s>>>(E, S.pl, A.Hn, S.Hblk));
+  }
   SysLevel &top = S.lev[0];
   LAUNCH(KC_GATHER, k_sell_gather<<<nblk(top.A.nnz), 256, 0, s>>>(S.top, S.Hblk, top.A.val));
   const int ktop = S.ltop - J;
@@ -793,7 +973,7 @@ void Engine::assemble(Amg &A, System &S, int J, double t, const double *zbase, c
 void Engine::setup_hierarchy(Amg &A, System &S, int ktop) {
   const int nlev = (int)S.lev.size();
   SysLevel &Ltop = S.lev[ktop];
-  const bool direct = Ltop.m <= h->cfg.dense_direct_max;
+  const bool direct = use_direct(S, Ltop);
   int kend = ktop;
   if (!direct) kend = (S.cut >= 0) ? std::max(S.cut, ktop) : nlev - 1;
   for (int k = 0; k < kend; ++k) {
@@ -810,7 +990,8 @@ void Engine::setup_hierarchy(Amg &A, System &S, int ktop) {
   }
   for (int k = ktop; k <= kend; ++k) {
     SysLevel &Lv = S.lev[k];
-    LAUNCH(KC_VEC, k_l1diag<<<nblk(Lv.m), 256, 0, s>>>(Lv.A, Lv.dinv, Lv.diag));
+    CK(cudaMemsetAsync(Lv.lam, 0, sizeof(double), s));
+    LAUNCH(KC_VEC, k_l1diag<<<nblk(Lv.m), 256, 0, s>>>(Lv.A, Lv.dinv, Lv.diag, (unsigned long long *)Lv.lam));
   }
   if (S.cut >= 0 && S.cut >= ktop) {
     SysLevel &Lc = S.lev[S.cut];
@@ -940,6 +1121,8 @@ System::PcgDev &Engine::pcg_plan(System &S, int ktop) {
   P.bottom_dense = (S.cut >= 0 && act.back() == S.cut) ? 1 : 0;
   P.nu = std::max(1, h->cfg.smoother_sweeps);
   P.nu_bottom = 30;
+  P.smoother = h->cfg.smoother;
+  P.cheb_ratio = h->cfg.cheb_ratio > 1.0 ? h->cfg.cheb_ratio : 4.0;
   P.maxit = h->cfg.pcg_maxit;
   P.rtol2 = h->cfg.pcg_rtol * h->cfg.pcg_rtol;
   for (int q = 0; q < P.nlev; ++q) {
@@ -948,6 +1131,8 @@ System::PcgDev &Engine::pcg_plan(System &S, int ktop) {
     pl.m = Lv.m;
     pl.A = Lv.A;
     pl.dinv = Lv.dinv;
+    pl.diag = Lv.diag;
+    pl.lam = Lv.lam;
     pl.b = Lv.b;
     pl.x = Lv.x;
     pl.x2 = Lv.x2;
@@ -1077,7 +1262,7 @@ int Engine::pcg(System &S, int ktop, const double *b, double *x) {
 
 int Engine::solve_compact(System &S, int ktop, const double *b, double *x) {
   SysLevel &Lv = S.lev[ktop];
-  if (Lv.m <= h->cfg.dense_direct_max) {
+  if (use_direct(S, Lv)) {
     dense_apply(Lv, b, x);
     // one step of iterative refinement against the CSR operator
     spmv(Lv.A, x, b, -1.0, Lv.r, Lv.spmv_group);
@@ -1515,6 +1700,9 @@ void mgbx_default_config(mgbx_config *c) {
   c->persistent = 1;
   c->tail_max = 1200;
   c->pcg_rtol_final = 1e-13;
+  c->fused = 1;
+  c->smoother = 1;
+  c->cheb_ratio = 4.0;
 }
 
 void mgbx_default_step_opts(mgbx_step_opts *o, int64_t n) {
@@ -1562,9 +1750,14 @@ int mgbx_create(const mgbx_problem *prob, const mgbx_config *cfg, mgbx_handle **
                                std::string(cudaGetErrorString(e)) + ")");
     if (h->cfg.device >= 0) CK(cudaSetDevice(h->cfg.device));
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->pool.stream = h->stream;
     {
       int dev = 0, nsm = 0, coop = 0, per_sm = 0;
       CK(cudaGetDevice(&dev));
+      cudaMemPool_t mp = nullptr;
+      CK(cudaDeviceGetDefaultMemPool(&mp, dev));
+      uint64_t keep = UINT64_MAX;   // freed blocks stay cached in the pool: the next handle reuses them without driver calls
+      CK(cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep));
       CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
       CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_persistent, kPcgThreads, 0));
@@ -1772,6 +1965,35 @@ int mgbx_set_grids(mgbx_handle *h, const double *f_grid, const double *g_grid) {
 }
 
 int64_t mgbx_launch_count(const mgbx_handle *h) { return h ? h->launches : 0; }
+
+int mgbx_solver_info(mgbx_handle *h, int which, mgbx_solver_info_t *out) {
+  if (!h || !out || which < 0 || which > 1) return MGBX_ERR_ARG;
+  return guarded(h, [&]() -> int {
+    memset(out, 0, sizeof(*out));
+    Amg &A = h->amg[which];
+    System *S = h->cfg.condense ? A.sys_cond.get() : A.sys_hook.get();
+    if (!S) return MGBX_OK;   // no fine-level system built yet
+    out->condensed = S->condensed ? 1 : 0;
+    out->assembly_terms = S->top.nterms;
+    out->hblk_entries = S->hblk_size;
+    auto it = S->pplans.find(0);
+    if (it != S->pplans.end()) {
+      const PcgPlan &P = it->second.host;
+      out->nlev = P.nlev;
+      out->nbig = P.nbig;
+      out->bottom_dense = P.bottom_dense;
+      out->grid = h->pcg_grid;
+      out->threads = kPcgThreads;
+      for (int q = 0; q < P.nlev; ++q) {
+        out->m[q] = P.lev[q].m;
+        out->nnz[q] = P.lev[q].A.nnz;
+        out->nnzT[q] = (q + 1 < P.nlev) ? P.lev[q].T.nnz : 0;
+      }
+    }
+    for (auto &Lv : S->lev) out->galerkin_terms += Lv.s1.nterms + Lv.s2.nterms;
+    return MGBX_OK;
+  });
+}
 
 int mgbx_kernel_stats(mgbx_handle *h, int reset, int32_t *nclasses, const char **names, int64_t *launches, double *ms) {
   if (!h || !nclasses) return MGBX_ERR_ARG;

@@ -170,7 +170,9 @@ constexpr int kPcgMaxGrid = 1024;   // partial slots per reduction
 struct PLevel {
   int64_t m;
   DevCsr A, T, Tt;       // T: this level <- next coarser active level; Tt its transpose
-  const double *dinv;
+  const double *dinv;    // l1-Jacobi: 1 / sum_j |a_ij|
+  const double *diag;    // a_ii (Chebyshev)
+  const double *lam;     // Gershgorin bound of lambda_max(D^-1 A), refreshed with the matrix values
   double *b, *x, *x2, *r;
   int G, GT, GTt;        // lanes per row
 };
@@ -179,6 +181,8 @@ struct PcgPlan {
   int nlev, nbig;        // active levels: [0, nbig) by the whole grid, [nbig, nlev) by CTA 0 alone
   int bottom_dense;      // the last level is applied through dense_inv
   int nu, nu_bottom;     // smoother sweeps (pre = post = nu), sweeps on an iterated bottom level
+  int smoother;          // 0: l1-Jacobi, 1: Chebyshev of degree nu on [lam/cheb_ratio, lam] with diagonal scaling
+  double cheb_ratio;
   int maxit;
   double rtol2;
   PLevel lev[MGBX_MAX_LEVELS];
@@ -292,6 +296,85 @@ __device__ double ph_jacobi(const SC &sc, const DevCsr &A, const double *dinv, c
   return part;
 }
 
+
+// ---- Chebyshev smoothing (degree nu, diagonal preconditioning) -------------------------------------------
+// 3-term recurrence on [a, b] = [lam/ratio, lam]:  theta = (a+b)/2, delta = (b-a)/2, sigma = theta/delta,
+// rho_0 = 1/sigma, rho_k = 1/(2 sigma - rho_{k-1});  d_0 = D^-1 r_0 / theta,
+// d_k = rho_k rho_{k-1} d_{k-1} + (2 rho_k / delta) D^-1 r_k,  x_{k+1} = x_k + d_k.  The error propagator is a
+// polynomial in D^-1 A, hence A-self-adjoint: the same sweeps before and after the coarse correction keep the
+// V-cycle a symmetric preconditioner.
+struct Cheb {
+  double th_inv, sigma, delta;
+  __device__ __forceinline__ Cheb(double lam, double ratio) {
+    const double b = lam, a = lam / ratio;
+    const double theta = 0.5 * (a + b);
+    delta = 0.5 * (b - a);
+    sigma = theta / delta;
+    th_inv = 1.0 / theta;
+  }
+  // coefficients of step k >= 1 given rho_{k-1}; returns rho_k
+  __device__ __forceinline__ double step(double rho_prev, double &c_dd, double &c_dr) const {
+    const double rho = 1.0 / (2.0 * sigma - rho_prev);
+    c_dd = rho * rho_prev;
+    c_dr = 2.0 * rho / delta;
+    return rho;
+  }
+};
+
+// steps 0 and 1 from x = 0 in one pass: d0 = th_inv D^-1 b; r1 = b - A d0; d1 = c_dd d0 + c_dr D^-1 r1; x = d0 + d1
+template <int G, class SC>
+__device__ void ph_cheb_first2(const SC &sc, const DevCsr &A, const double *diag, const double *b, double *xnew, double *d,
+                               double th_inv, double c_dd, double c_dr) {
+  const int64_t step = sc.nthr / G;
+  const int sub = (int)(sc.tid % G);
+  for (int64_t base = 0; base < A.rows; base += step) {
+    const int64_t row = base + sc.tid / G;
+    const bool valid = row < A.rows;
+    double acc = 0.0;
+    if (valid) {
+      const int64_t bb = A.ptr[row], e = A.ptr[row + 1];
+      for (int64_t k = bb + sub; k < e; k += G) {
+        const int32_t j = A.idx[k];
+        acc += A.val[k] * (th_inv * b[j] / diag[j]);
+      }
+    }
+    if (G > 1) {
+#pragma unroll
+      for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, G);
+    }
+    if (valid && sub == 0) {
+      const double di = 1.0 / diag[row], bi = b[row];
+      const double d0 = th_inv * bi * di;
+      const double d1 = c_dd * d0 + c_dr * (bi - acc) * di;
+      xnew[row] = d0 + d1;
+      d[row] = d1;
+    }
+  }
+}
+
+// one step on an existing iterate: r = b - A x; d = (first ? th_inv D^-1 r : c_dd d + c_dr D^-1 r); xnew = x + d
+template <int G, class SC>
+__device__ double ph_cheb_step(const SC &sc, const DevCsr &A, const double *diag, const double *b, const double *x, double *xnew,
+                               double *d, bool first, double th_inv, double c_dd, double c_dr, const double *dotw) {
+  const int64_t step = sc.nthr / G;
+  const int sub = (int)(sc.tid % G);
+  double part = 0.0;
+  for (int64_t base = 0; base < A.rows; base += step) {
+    const int64_t row = base + sc.tid / G;
+    const bool valid = row < A.rows;
+    const double acc = row_dot<G>(A, row, sub, valid, x);
+    if (valid && sub == 0) {
+      const double rr = (b[row] - acc) / diag[row];
+      const double dn = first ? th_inv * rr : c_dd * d[row] + c_dr * rr;
+      const double v = x[row] + dn;
+      d[row] = dn;
+      xnew[row] = v;
+      if (dotw) part += dotw[row] * v;
+    }
+  }
+  return part;
+}
+
 #define MGBX_G_DISPATCH(G, CALL) \
   do {                            \
     if ((G) == 32) { constexpr int GG = 32; CALL; } \
@@ -360,22 +443,47 @@ __device__ double vcycle_levels(const PcgPlan &P, const Scope<GRID> &sc, int k0,
       sc.sync();
       continue;
     }
+    const bool cheb = (P.smoother == 1) && !last;   // an iterated bottom level keeps l1-Jacobi
     const int want = last ? P.nu_bottom : P.nu;
     const int done = (want >= 2) ? 2 : 1;
     const int npre = want - done, npost = last ? 0 : P.nu;
     double *cur = ((npre + npost) & 1) ? Lv.x2 : Lv.x, *oth = ((npre + npost) & 1) ? Lv.x : Lv.x2;
-    if (done == 2) {
-      MGBX_G_DISPATCH(Lv.G, (ph_jacobi_first2<GG>(sc, Lv.A, Lv.dinv, bk, cur)));
-    } else {
-      for (int64_t i = sc.tid; i < Lv.m; i += sc.nthr) cur[i] = Lv.dinv[i] * bk[i];
-    }
-    sc.sync();
-    for (int it = 0; it < npre; ++it) {
-      MGBX_G_DISPATCH(Lv.G, (ph_jacobi<GG>(sc, Lv.A, Lv.dinv, bk, cur, oth, nullptr)));
+    if (cheb) {
+      const Cheb C(*Lv.lam, P.cheb_ratio);
+      double rho = 1.0 / C.sigma, c_dd = 0.0, c_dr = 0.0;
+      if (done == 2) {
+        rho = C.step(rho, c_dd, c_dr);
+        MGBX_G_DISPATCH(Lv.G, (ph_cheb_first2<GG>(sc, Lv.A, Lv.diag, bk, cur, Lv.r, C.th_inv, c_dd, c_dr)));
+      } else {
+        for (int64_t i = sc.tid; i < Lv.m; i += sc.nthr) {
+          const double d0 = C.th_inv * bk[i] / Lv.diag[i];
+          cur[i] = d0;
+          Lv.r[i] = d0;
+        }
+      }
       sc.sync();
-      double *t = cur;
-      cur = oth;
-      oth = t;
+      for (int it = 0; it < npre; ++it) {
+        rho = C.step(rho, c_dd, c_dr);
+        MGBX_G_DISPATCH(Lv.G, (ph_cheb_step<GG>(sc, Lv.A, Lv.diag, bk, cur, oth, Lv.r, false, C.th_inv, c_dd, c_dr, nullptr)));
+        sc.sync();
+        double *t = cur;
+        cur = oth;
+        oth = t;
+      }
+    } else {
+      if (done == 2) {
+        MGBX_G_DISPATCH(Lv.G, (ph_jacobi_first2<GG>(sc, Lv.A, Lv.dinv, bk, cur)));
+      } else {
+        for (int64_t i = sc.tid; i < Lv.m; i += sc.nthr) cur[i] = Lv.dinv[i] * bk[i];
+      }
+      sc.sync();
+      for (int it = 0; it < npre; ++it) {
+        MGBX_G_DISPATCH(Lv.G, (ph_jacobi<GG>(sc, Lv.A, Lv.dinv, bk, cur, oth, nullptr)));
+        sc.sync();
+        double *t = cur;
+        cur = oth;
+        oth = t;
+      }
     }
     if (!last) {
       MGBX_G_DISPATCH(Lv.G, (ph_spmv<GG>(sc, Lv.A, cur, bk, -1.0, Lv.r)));
@@ -406,10 +514,19 @@ __device__ double vcycle_levels(const PcgPlan &P, const Scope<GRID> &sc, int k0,
     double *cur = cur_x2 ? Lv.x2 : Lv.x, *oth = cur_x2 ? Lv.x : Lv.x2;
     MGBX_G_DISPATCH(Lv.GT, (ph_spmv<GG>(sc, Lv.T, P.lev[k + 1].x, cur, 1.0, cur)));   // x += T xc (row-local)
     sc.sync();
+    const bool cheb = (P.smoother == 1);
+    const Cheb C(cheb ? *Lv.lam : 1.0, P.cheb_ratio);
+    double rho = 1.0 / C.sigma, c_dd = 0.0, c_dr = 0.0;
     for (int it = 0; it < npost; ++it) {
       const bool fin = (it == npost - 1) && (k == k0) && (dot_top != nullptr);
       double pp = 0.0;
-      MGBX_G_DISPATCH(Lv.G, (pp = ph_jacobi<GG>(sc, Lv.A, Lv.dinv, bk, cur, oth, fin ? dot_top : nullptr)));
+      if (cheb) {
+        if (it > 0) rho = C.step(rho, c_dd, c_dr);
+        MGBX_G_DISPATCH(Lv.G, (pp = ph_cheb_step<GG>(sc, Lv.A, Lv.diag, bk, cur, oth, Lv.r, it == 0, C.th_inv, c_dd, c_dr,
+                                                     fin ? dot_top : nullptr)));
+      } else {
+        MGBX_G_DISPATCH(Lv.G, (pp = ph_jacobi<GG>(sc, Lv.A, Lv.dinv, bk, cur, oth, fin ? dot_top : nullptr)));
+      }
       part += pp;
       if (!fin) sc.sync();
       double *t = cur;

@@ -56,7 +56,8 @@ class Config(C.Structure):
     _fields_ = [("dense_direct_max", C.c_int32), ("coarse_max", C.c_int32), ("pcg_maxit", C.c_int32),
                 ("pcg_rtol", C.c_double), ("smoother_sweeps", C.c_int32), ("condense", C.c_int32),
                 ("device", C.c_int32), ("verbose", C.c_int32), ("use_graphs", C.c_int32), ("profile", C.c_int32),
-                ("persistent", C.c_int32), ("tail_max", C.c_int32), ("pcg_rtol_final", C.c_double)]
+                ("persistent", C.c_int32), ("tail_max", C.c_int32), ("pcg_rtol_final", C.c_double),
+                ("fused", C.c_int32), ("smoother", C.c_int32), ("cheb_ratio", C.c_double)]
 
 
 class StepOpts(C.Structure):
@@ -78,13 +79,20 @@ class ScalarsOut(C.Structure):
                 ("var_absmax", C.c_double * MAX_ND), ("all_finite", C.c_int32)]
 
 
+class SolverInfo(C.Structure):
+    _fields_ = [("condensed", C.c_int32), ("nlev", C.c_int32), ("nbig", C.c_int32), ("bottom_dense", C.c_int32),
+                ("grid", C.c_int32), ("threads", C.c_int32), ("m", C.c_int64 * MAX_LEVELS),
+                ("nnz", C.c_int64 * MAX_LEVELS), ("nnzT", C.c_int64 * MAX_LEVELS), ("assembly_terms", C.c_int64),
+                ("hblk_entries", C.c_int64), ("galerkin_terms", C.c_int64)]
+
+
 EXPORTS = [
     "mgbx_default_config", "mgbx_default_step_opts", "mgbx_abi_version", "mgbx_device_count",
     "mgbx_create", "mgbx_destroy", "mgbx_last_error", "mgbx_step", "mgbx_scalars",
     "mgbx_phase1_init", "mgbx_attach_feasibility", "mgbx_set_feasibility_box", "mgbx_reset_feasibility_state", "mgbx_handoff",
     "mgbx_matched_t", "mgbx_get_z", "mgbx_set_z", "mgbx_set_grids", "mgbx_level_size",
     "mgbx_barrier_eval", "mgbx_hessian_pattern", "mgbx_hessian_values", "mgbx_solve_newton_system",
-    "mgbx_plan_pattern", "mgbx_launch_count", "mgbx_kernel_stats", "mgbx_set_profile",
+    "mgbx_plan_pattern", "mgbx_launch_count", "mgbx_kernel_stats", "mgbx_set_profile", "mgbx_solver_info",
 ]
 
 _lib = None
@@ -140,6 +148,7 @@ def lib():
     L.mgbx_launch_count.restype = C.c_int64
     L.mgbx_kernel_stats.argtypes = [H, C.c_int, c_i32p, C.POINTER(C.c_char_p), c_i64p, c_f64p]
     L.mgbx_set_profile.argtypes = [H, C.c_int]
+    L.mgbx_solver_info.argtypes = [H, C.c_int, C.POINTER(SolverInfo)]
     _lib = L
     return L
 
@@ -360,6 +369,14 @@ class Handle:
 
     def launch_count(self):
         return int(lib().mgbx_launch_count(self._h))
+
+    def solver_info(self, which=MAIN):
+        out = SolverInfo()
+        self._check(lib().mgbx_solver_info(self._h, which, C.byref(out)))
+        L = out.nlev
+        return dict(condensed=bool(out.condensed), nlev=L, nbig=out.nbig, bottom_dense=bool(out.bottom_dense),
+                    grid=out.grid, threads=out.threads, m=list(out.m[:L]), nnz=list(out.nnz[:L]), nnzT=list(out.nnzT[:L]),
+                    assembly_terms=out.assembly_terms, hblk_entries=out.hblk_entries, galerkin_terms=out.galerkin_terms)
 
     def set_profile(self, on):
         self._check(lib().mgbx_set_profile(self._h, int(on)))

@@ -218,7 +218,7 @@ def test_persistent_pcg_matches_multilaunch_pcg(tail_max):
     g = rng.normal(size=m)
     out = []
     for persistent in (0, 1):
-        h = native.Handle(prob, dense_direct_max=0, coarse_max=40, persistent=persistent, tail_max=tail_max)
+        h = native.Handle(prob, dense_direct_max=0, coarse_max=40, persistent=persistent, tail_max=tail_max, smoother=0)
         try:
             x, its = h.solve_newton_system(0, J, 2.0, s, g)
             Hm = h.hessian(0, J, 2.0, s)
