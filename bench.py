@@ -215,6 +215,19 @@ def main():
         info = h.solver_info()
         total_ms = max(1e-9, sum(v[1] for v in kstats.values()))
 
+        try:
+            ncu_tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        except Exception:
+            ncu_tr = {}
+
+        def traffic(cls, nl):
+            """DRAM bytes per launch from the committed `ncu --set full` capture of the same kernel on this workload."""
+            if cls == "pcg_persistent" and "k_pcg_persistent" in ncu_tr:
+                e = ncu_tr["k_pcg_persistent"]
+                return 1e6 * e["dram_mb_per_launch"] / e["pcg_iterations_in_launch"] * pstats["pcg_iters"] / nl
+            key = {"elem_f01": "k_elem_f01", "elem_f2": "k_elem_f2"}.get(cls)
+            return 1e6 * ncu_tr[key]["dram_mb_per_launch"] if key in ncu_tr else None
+
         def line(cls):
             nl, ms = kstats[cls]
             if not nl:
@@ -226,7 +239,7 @@ def main():
                 bpl = ab.get(cls)
             ach = bpl / (ms * 1e-3 / nl) / 1e9 if bpl else None
             return {"bound": "hbm", "kernel": cls, "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": (ach / peak) if ach else None, "traffic": None,
+                    "frac": (ach / peak) if ach else None, "traffic": traffic(cls, nl),
                     "algorithmic_bytes_per_launch": bpl, "launches": nl, "avg_launch_us": 1e3 * ms / nl,
                     "share_of_device_time": ms / total_ms}
         dom = max(kstats, key=lambda k: kstats[k][1])
@@ -267,7 +280,7 @@ def main():
     }
     if roof:
         out["roofline"] = roof
-        out["roofline_by_kernel"] = {k: {kk: v[kk] for kk in ("achieved", "frac", "avg_launch_us", "share_of_device_time", "algorithmic_bytes_per_launch")}
+        out["roofline_by_kernel"] = {k: {kk: v[kk] for kk in ("achieved", "frac", "traffic", "avg_launch_us", "share_of_device_time", "algorithmic_bytes_per_launch")}
                                      for k, v in roof_all.items() if v}
         out["solver_plan"] = info
         out["kernel_classes"] = {k: {"launches": v[0], "ms": round(v[1], 3)} for k, v in kstats.items()}

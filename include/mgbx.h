@@ -103,6 +103,11 @@ typedef struct {
                               R_fine[l] = R_fine[l+1]*T[l] and may be left zero-initialised */
   const mgbx_csr *T;       /* L-1 level transfers m_{l+1} x m_l with R_fine[l] = R_fine[l+1]*T[l] */
   const int64_t *var_offsets;    /* L x (nu+1): first column of variable k at level l */
+  /* multi-GPU element partition (zero / NULL for a single-rank problem): this rank holds a contiguous block of
+   * elements; n above is the LOCAL node count */
+  int64_t n_global;              /* nodes of the whole mesh (the 1/n of the barrier average, src/convex.jl:155-164) */
+  const int32_t *var_local;      /* nu flags: 1 = the variable's fine-level unknowns are node-local (`:full` space, R block
+                                    == identity) and live only on the owning rank; 0 = shared (replicated, all-reduced) */
 } mgbx_amg;
 
 /* MGBProblem (src/mgb.jl:666-674) */
@@ -176,6 +181,14 @@ int mgbx_device_count(void);
 int mgbx_create(const mgbx_problem *prob, const mgbx_config *cfg, mgbx_handle **out);
 void mgbx_destroy(mgbx_handle *h);
 const char *mgbx_last_error(const mgbx_handle *h);   /* h may be NULL: last create error */
+
+/* Multi-GPU, one handle per rank/GPU: elements are partitioned across ranks (the host slices the
+ * problem, multigridbarrier.jl_b200/partition.py); inside the library the partial sums over elements -- R'g, the assembled
+ * Hessian values, objective / line-search / duality-gap scalars -- are combined with NCCL all-reduces on the handle's stream,
+ * and every rank then runs the identical (deterministic) multigrid-PCG solve on the shared unknowns.  NCCL is loaded with
+ * dlopen("libnccl.so.2") only when mgbx_comm_init is called.  Rank 0 obtains an id and the host broadcasts it. */
+int mgbx_nccl_unique_id(char id[128]);
+int mgbx_comm_init(mgbx_handle *h, int rank, int nranks, const char id[128]);
 
 /* the hot path */
 int mgbx_step(mgbx_handle *h, int which, double t, const mgbx_step_opts *o, mgbx_step_result *r);

@@ -799,6 +799,54 @@ __global__ void __launch_bounds__(256) k_dense_symv(const double *__restrict__ M
   if (lane == 0) y[row] = s;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// multi-GPU (element partition): a level vector is a list of segments, one per state variable; `shared`
+// segments are replicated on every rank, `local` segments hold the rank's own node-local unknowns.  Reductions
+// over such vectors are split: the shared part is summed redundantly (identically) on every rank, the local
+// part is a partial sum completed by an all-reduce.
+// ------------------------------------------------------------------------------------------------
+struct SegList {
+  int n;
+  int64_t off[MGBX_MAX_ND + 1];   // segment q = [off[q], off[q+1])
+  int local[MGBX_MAX_ND];
+};
+__device__ __forceinline__ int seg_is_local(const SegList &S, int64_t i) {
+  int q = 0;
+  while (q + 1 < S.n && i >= S.off[q + 1]) ++q;
+  return S.local[q];
+}
+
+// out[0..2] = {a.b, a.a, #non-finite entries of a} over the LOCAL segments, out[3..5] the same over the SHARED ones
+__global__ void __launch_bounds__(kRedThreads) k_dot2_seg(SegList S, int64_t m, const double *__restrict__ a, const double *__restrict__ b,
+                                                           double *partials, unsigned int *ticket, double *out) {
+  double red[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  const int op[6] = {0, 0, 0, 0, 0, 0};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+    const double x = a[i];
+    const int o = seg_is_local(S, i) ? 0 : 3;
+    red[o] += x * (b ? b[i] : 0.0);
+    red[o + 1] += x * x;
+    if (!isfinite(x)) red[o + 2] += 1.0;
+  }
+  grid_reduce<6>(red, op, partials, ticket, out);
+}
+
+// xn = x - s*d;  out[0] = |xn - x|^2 over the SHARED segments, out[1] over the LOCAL ones
+__global__ void __launch_bounds__(kRedThreads) k_trial_seg(SegList S, int64_t m, const double *__restrict__ x, const double *__restrict__ d,
+                                                            double s, double *xn, double *partials, unsigned int *ticket, double *out) {
+  double red[2] = {0.0, 0.0};
+  const int op[2] = {0, 0};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+    const double xi = x[i];
+    const double v = xi - s * d[i];
+    xn[i] = v;
+    const double df = v - xi;
+    red[seg_is_local(S, i) ? 1 : 0] += df * df;
+  }
+  grid_reduce<2>(red, op, partials, ticket, out);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Fused element kernels (north-star items 1 + 2): one pass per barrier evaluation.
 //   k_elem<NODE_F01>  apply_D -> F0/F1 -> (1/n) F1 + w.*c -> sum_k D_k' y_k      (k_node<F01> + k_blockgrad in one kernel)

@@ -12,6 +12,7 @@
 // The t-ramp (mgb_core) and phase-I control flow (mgb_driver) stay on the host side of the ABI:
 // they only exchange scalars with this library.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <chrono>
 #include <cmath>
@@ -76,6 +77,57 @@ struct HostTimer {
 };
 
 inline unsigned int nblk(int64_t work, int threads = 256) { return (unsigned int)((work + threads - 1) / threads); }
+
+
+// ------------------------------------------------------------------------------------------------
+// NCCL, loaded on demand (multi-GPU runs only): the few entry points used, declared here so that the
+// library has no link-time dependency on NCCL.  Types follow nccl.h (2.x ABI).
+// ------------------------------------------------------------------------------------------------
+struct NcclUniqueId {
+  char internal[128];
+};
+struct NcclApi {
+  void *lib = nullptr;
+  int (*GetUniqueId)(NcclUniqueId *) = nullptr;
+  int (*CommInitRank)(void **, int, NcclUniqueId, int) = nullptr;
+  int (*CommDestroy)(void *) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+};
+enum { kNcclInt64 = 4, kNcclUint64 = 5, kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2 };
+NcclApi &nccl_api() {
+  static NcclApi api;
+  if (api.lib) return api;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char *nm : names) {
+    api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (api.lib) break;
+  }
+  if (!api.lib) throw std::runtime_error(std::string("cannot load NCCL (libnccl.so.2): ") + dlerror());
+  auto sym = [&](const char *n) {
+    void *p = dlsym(api.lib, n);
+    if (!p) throw std::runtime_error(std::string("NCCL symbol missing: ") + n);
+    return p;
+  };
+  api.GetUniqueId = (int (*)(NcclUniqueId *))sym("ncclGetUniqueId");
+  api.CommInitRank = (int (*)(void **, int, NcclUniqueId, int))sym("ncclCommInitRank");
+  api.CommDestroy = (int (*)(void *))sym("ncclCommDestroy");
+  api.AllReduce = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))sym("ncclAllReduce");
+  api.AllGather = (int (*)(const void *, void *, size_t, int, void *, cudaStream_t))sym("ncclAllGather");
+  api.GroupStart = (int (*)())sym("ncclGroupStart");
+  api.GroupEnd = (int (*)())sym("ncclGroupEnd");
+  api.GetErrorString = (const char *(*)(int))sym("ncclGetErrorString");
+  return api;
+}
+#define NCK(call)                                                                                        \
+  do {                                                                                                   \
+    int r_ = (call);                                                                                     \
+    if (r_ != 0) throw std::runtime_error(std::string("NCCL error: ") + nccl_api().GetErrorString(r_) + " at " + __FILE__ + ":" + \
+                                          std::to_string(__LINE__));                                     \
+  } while (0)
 
 // ------------------------------------------------------------------------------------------------
 // device memory pool (freed at destroy)
@@ -367,6 +419,9 @@ struct Amg {
          *gbest = nullptr;
   std::unique_ptr<System> sys_cond, sys_coarse, sys_hook;   // fine-level (condensed), levels < L-1, parity hooks
   double fb = 0.0, fR = 0.0;
+  int64_t n_global = 0;              // nodes of the whole mesh (== n on a single rank)
+  std::vector<char> var_local;       // per variable: node-local unknowns at the fine level (multi-GPU)
+  bool any_local = false;
 };
 
 struct EvalOut {
@@ -406,6 +461,9 @@ struct mgbx_handle {
   cudaEvent_t ev_cur = nullptr;
   int pcg_grid = 0;
   double cur_rtol2 = 1e-22;
+  // multi-GPU
+  int rank = 0, nranks = 1;
+  void *comm = nullptr;
 };
 
 namespace {
@@ -565,6 +623,52 @@ struct Engine {
     }
   }
 
+
+  // ---------------------------------------------------------------- multi-GPU helpers
+  bool dist() const { return h->nranks > 1; }
+  SegList seglist(Amg &A, int J) {
+    SegList S;
+    memset(&S, 0, sizeof(S));
+    if (J == A.L - 1) {
+      S.n = A.nu;
+      for (int v = 0; v < A.nu; ++v) {
+        S.off[v] = A.voff[J][v];
+        S.local[v] = A.var_local[v];
+      }
+      S.off[A.nu] = A.voff[J][A.nu];
+    } else {
+      S.n = 1;
+      S.off[0] = 0;
+      S.off[1] = A.m[J];
+    }
+    return S;
+  }
+  void allreduce(double *buf, int64_t count, int op = kNcclSum) {
+    if (count > 0) NCK(nccl_api().AllReduce(buf, buf, (size_t)count, kNcclFloat64, op, h->comm, s));
+  }
+  // sum the shared segments of a level-J vector over the ranks (the local segments are already complete)
+  void allreduce_shared(Amg &A, int J, double *v, double *extra = nullptr, int64_t nextra = 0) {
+    const SegList S = seglist(A, J);
+    NCK(nccl_api().GroupStart());
+    for (int q = 0; q < S.n; ++q)
+      if (!S.local[q]) allreduce(v + S.off[q], S.off[q + 1] - S.off[q]);
+    if (extra) allreduce(extra, nextra);
+    NCK(nccl_api().GroupEnd());
+  }
+  // hscal[4..6] = {a.b, a.a, #non-finite(a)} over a level-J vector (all ranks obtain the same values)
+  void dot2_fetch(Amg &A, int J, const double *a, const double *b) {
+    const int64_t m = A.m[J];
+    if (!dist()) {
+      LAUNCH(KC_VEC, k_dot2<<<red_grid(m), kRedThreads, 0, s>>>(m, a, b, h->partials, h->ticket, h->dscal + 4));
+      fetch(8);
+      return;
+    }
+    LAUNCH(KC_VEC, k_dot2_seg<<<red_grid(m), kRedThreads, 0, s>>>(seglist(A, J), m, a, b, h->partials, h->ticket, h->dscal + 44));
+    allreduce(h->dscal + 44, 3);
+    fetch(64);
+    for (int k = 0; k < 3; ++k) h->hscal[4 + k] = h->hscal[44 + k] + h->hscal[47 + k];
+  }
+
   NodeParams node_params(Amg &A, double t) {
     NodeParams P;
     memset(&P, 0, sizeof(P));
@@ -582,7 +686,7 @@ struct Engine {
     P.f = A.f;
     P.bw = A.bw;
     P.t = t;
-    P.inv_n = 1.0 / (double)A.n;
+    P.inv_n = 1.0 / (double)A.n_global;
     P.cd = A.cd;
     P.G = A.G;
     P.partials = h->partials;
@@ -641,6 +745,7 @@ struct Engine {
     prolong_to_fine(A, J, x, zbase, A.zf);
     NodeParams P = node_params(A, t);
     if (!use_bw) P.bw = nullptr;
+    if (dist()) P.red_out = h->dscal + 40;
     ElemFused Q;
     size_t smem = 0;
     unsigned int grid = 0;
@@ -653,12 +758,26 @@ struct Engine {
       LAUNCH(KC_BLOCKGRAD, k_blockgrad<<<nblk((int64_t)A.nu * A.n), 256, 0, s>>>(E, A.G, A.gb, A.nu));
     }
     restrict_from_fine(A, J, A.gb, gout);
-    LAUNCH(KC_VEC, k_dot2<<<red_grid(A.m[J]), kRedThreads, 0, s>>>(A.m[J], gout, nullptr, h->partials, h->ticket, h->dscal + 4));
-    stage_end(STAGE_F01, st);
-    fetch(8);
+    if (!dist()) {
+      LAUNCH(KC_VEC, k_dot2<<<red_grid(A.m[J]), kRedThreads, 0, s>>>(A.m[J], gout, nullptr, h->partials, h->ticket, h->dscal + 4));
+      stage_end(STAGE_F01, st);
+      fetch(8);
+    } else {
+      // partial sums over this rank's elements -> all ranks: the shared part of R'g, the objective scalars, and the
+      // local-part norms (one grouped all-reduce); the shared-part norm is then formed identically on every rank
+      const SegList SG = seglist(A, J);
+      LAUNCH(KC_VEC, k_dot2_seg<<<red_grid(A.m[J]), kRedThreads, 0, s>>>(SG, A.m[J], gout, nullptr, h->partials, h->ticket, h->dscal + 44));
+      allreduce_shared(A, J, gout, h->dscal + 39, 8);   // [39] trial norm (local part), [40..43] node sums, [44..46] local dot
+      LAUNCH(KC_VEC, k_dot2_seg<<<red_grid(A.m[J]), kRedThreads, 0, s>>>(SG, A.m[J], gout, nullptr, h->partials, h->ticket, h->dscal + 50));
+      stage_end(STAGE_F01, st);
+      fetch(64);
+      for (int k = 0; k < 4; ++k) h->hscal[k] = h->hscal[40 + k];
+      for (int k = 0; k < 3; ++k) h->hscal[4 + k] = h->hscal[44 + k] + h->hscal[53 + k];
+      h->hscal[7] = h->hscal[38] + h->hscal[39];
+    }
     if (h->res) h->res->f01_evals++;
     EvalOut o;
-    const double bar = (use_bw && A.bw) ? h->hscal[0] : h->hscal[0] * (1.0 / (double)A.n);
+    const double bar = (use_bw && A.bw) ? h->hscal[0] : h->hscal[0] * (1.0 / (double)A.n_global);
     o.lin = h->hscal[1];
     o.y = bar + h->hscal[1];
     o.nonfinite_nodes = h->hscal[2];
@@ -964,6 +1083,7 @@ void Engine::assemble(Amg &A, System &S, int J, double t, const double *zbase, c
   }
   SysLevel &top = S.lev[0];
   LAUNCH(KC_GATHER, k_sell_gather<<<nblk(top.A.nnz), 256, 0, s>>>(S.top, S.Hblk, top.A.val));
+  if (dist()) allreduce(top.A.val, top.A.nnz);   // sum of the ranks' element contributions (identical pattern on every rank)
   const int ktop = S.ltop - J;
   setup_hierarchy(A, S, ktop);
   stage_end(STAGE_F2, st);
@@ -1299,7 +1419,13 @@ int Engine::solve(Amg &A, System &S, int J, const double *g, double *dir) {
     E.nK = S.nK;
     for (int j = 0; j < S.nK; ++j) E.Krow[j] = S.Krow[j];
     LAUNCH(KC_BLOCKGRAD, k_blockgrad<<<nblk((int64_t)A.nu * A.n), 256, 0, s>>>(E, A.G, A.gb, A.nu));
-    spmv(A.RLt, A.gb, g, 1.0, A.tmp);                 // tmp = g + R' gb   (entries of eliminated variables unused)
+    if (!dist()) {
+      spmv(A.RLt, A.gb, g, 1.0, A.tmp);               // tmp = g + R' gb   (entries of eliminated variables unused)
+    } else {
+      spmv(A.RLt, A.gb, nullptr, 1.0, A.tmp);         // this rank's part of R' gb, summed over the ranks, then + g
+      allreduce_shared(A, J, A.tmp);
+      LAUNCH(KC_VEC, k_axpby<<<nblk(A.m[J]), 256, 0, s>>>(A.m[J], 1.0, A.tmp, 1.0, g, A.tmp));
+    }
     for (size_t q = 0; q < S.kept.size(); ++q)
       copy(S.pc_b + Lv.off[q], A.tmp + A.voff[A.L - 1][S.kept[q]], Lv.off[q + 1] - Lv.off[q]);
     iters = solve_compact(S, ktop, S.pc_b, S.pc_x);
@@ -1314,8 +1440,7 @@ int Engine::solve(Amg &A, System &S, int J, const double *g, double *dir) {
   }
   stage_end(STAGE_SOLVE, st);
   // inc = g . dir, finiteness of dir
-  LAUNCH(KC_VEC, k_dot2<<<red_grid(A.m[J]), kRedThreads, 0, s>>>(A.m[J], dir, g, h->partials, h->ticket, h->dscal + 4));
-  fetch(8);
+  dot2_fetch(A, J, dir, g);
   if (h->res) {
     h->res->linear_solves++;
     h->res->pcg_iters += iters > 0 ? iters : -iters;
@@ -1328,6 +1453,9 @@ Engine::NewtonOut Engine::newton(Amg &A, int J, double t, int maxit, int stop_ki
   NewtonOut out{false, 0, MGBX_OK, 0.0, 0.0, 0.0};
   const int64_t m = A.m[J];
   System &S = system_for(A, J);
+  if (dist() && J == A.L - 1)
+    for (int v : S.kept)
+      if (A.var_local[v]) throw std::runtime_error("multi-GPU: a node-local state variable could not be condensed out of the Newton system");
   // the finalize pass stops on floating-point stagnation (stopping_exact): give it directions converged to the
   // attainable accuracy so that it stagnates where a direct solve would
   const double rt = (stop_kind == 0) ? std::min(h->cfg.pcg_rtol, h->cfg.pcg_rtol_final) : h->cfg.pcg_rtol;
@@ -1347,11 +1475,12 @@ Engine::NewtonOut Engine::newton(Amg &A, int J, double t, int maxit, int stop_ki
   while (k < maxit && !converged) {
     ++k;
     assemble(A, S, J, t, A.z, A.x);
-    solve(A, S, J, A.g, A.dir);
+    const int pit = solve(A, S, J, A.g, A.dir);
     const double inc = h->hscal[4];
     const bool dir_finite = (h->hscal[6] == 0.0) && std::isfinite(h->hscal[5]) && std::isfinite(inc);
     out.inc = inc;
-    if (h->cfg.verbose > 1) fprintf(stderr, "[mgbx] newton J=%d k=%d y=%.17g |g|=%.6g lam2=%.6g\n", J, k, y, gnorm, inc);
+    if (h->cfg.verbose > 1)
+      fprintf(stderr, "[mgbx] newton J=%d m=%lld k=%d y=%.17g |g|=%.6g lam2=%.6g pcg=%d t=%g\n", J, (long long)m, k, y, gnorm, inc, pit, t);
     if (!dir_finite) {
       out.status = MGBX_NON_FINITE;
       break;
@@ -1365,7 +1494,8 @@ Engine::NewtonOut Engine::newton(Amg &A, int J, double t, int maxit, int stop_ki
     double yn = y, gnn = gnorm;
     bool have_trial = false;   // xbest/gbest hold the last finite trial
     while (sstep > 0.0) {
-      LAUNCH(KC_VEC, k_trial<<<red_grid(m), kRedThreads, 0, s>>>(m, A.x, A.dir, sstep, A.xn, h->partials, h->ticket, h->dscal + 7));
+      if (!dist()) LAUNCH(KC_VEC, k_trial<<<red_grid(m), kRedThreads, 0, s>>>(m, A.x, A.dir, sstep, A.xn, h->partials, h->ticket, h->dscal + 7));
+      else LAUNCH(KC_VEC, k_trial_seg<<<red_grid(m), kRedThreads, 0, s>>>(seglist(A, J), m, A.x, A.dir, sstep, A.xn, h->partials, h->ticket, h->dscal + 38));
       EvalOut et = eval_f01(A, J, t, A.z, A.xn, A.gn);
       const bool stalled = (h->hscal[7] == 0.0);
       if (et.finite) {
@@ -1457,10 +1587,11 @@ int Engine::matched_t(double t_default, double *t_out, double *tstar_out) {
   solve(A, S, J, A.g, A.dir);      // nphi
   solve(A, S, J, A.gn, A.xn);      // nc
   const double d = h->hscal[4];    // gc . nc
-  LAUNCH(KC_VEC, k_dot<<<red_grid(m), kRedThreads, 0, s>>>(m, A.g, A.xn, h->partials, h->ticket, h->dscal + 0));
-  LAUNCH(KC_VEC, k_dot<<<red_grid(m), kRedThreads, 0, s>>>(m, A.gn, A.dir, h->partials, h->ticket, h->dscal + 1));
-  fetch(2);
-  const double b = h->hscal[0] + h->hscal[1];
+  (void)m;
+  dot2_fetch(A, J, A.xn, A.g);
+  const double b1 = h->hscal[4];
+  dot2_fetch(A, J, A.dir, A.gn);
+  const double b = b1 + h->hscal[4];
   *tstar_out = NAN;
   *t_out = t_default;
   if (!(d > 0.0)) return MGBX_OK;
@@ -1563,6 +1694,11 @@ void create_amg(mgbx_handle *h, const mgbx_amg &in, Amg &A) {
   A.nD = in.nD;
   A.L = in.L;
   A.nops = in.nops;
+  A.n_global = in.n_global > 0 ? in.n_global : in.n;
+  A.var_local.assign(in.nu, 0);
+  for (int v = 0; v < in.nu; ++v) A.var_local[v] = (in.var_local && in.var_local[v]) ? 1 : 0;
+  A.any_local = false;
+  for (char c : A.var_local) A.any_local = A.any_local || c;
   for (int j = 0; j < in.nD; ++j) {
     A.D_var[j] = in.D_var[j];
     A.D_op[j] = in.D_op[j];
@@ -1769,8 +1905,8 @@ int mgbx_create(const mgbx_problem *prob, const mgbx_config *cfg, mgbx_handle **
     CK(cudaEventCreate(&h->ev1));
     h->partials = h->pool.zeros<double>((size_t)kRedBlocks * 8, h->stream);
     h->ticket = h->pool.zeros<unsigned int>(4, h->stream);
-    h->dscal = h->pool.zeros<double>(32, h->stream);
-    CK(cudaMallocHost((void **)&h->hscal, sizeof(double) * 32));
+    h->dscal = h->pool.zeros<double>(64, h->stream);
+    CK(cudaMallocHost((void **)&h->hscal, sizeof(double) * 64));
     const mgbx_amg &a0 = prob->amg[0];
     create_amg(h, a0, h->amg[0]);
     Amg &A = h->amg[0];

@@ -44,7 +44,8 @@ class Amg(C.Structure):
     _fields_ = [("n", C.c_int64), ("N", C.c_int64), ("p", C.c_int32), ("nu", C.c_int32),
                 ("nD", C.c_int32), ("L", C.c_int32), ("w", c_f64p), ("nops", C.c_int32),
                 ("op_data", C.POINTER(c_f64p)), ("D_var", c_i32p), ("D_op", c_i32p),
-                ("R_fine", C.POINTER(Csr)), ("T", C.POINTER(Csr)), ("var_offsets", c_i64p)]
+                ("R_fine", C.POINTER(Csr)), ("T", C.POINTER(Csr)), ("var_offsets", c_i64p),
+                ("n_global", C.c_int64), ("var_local", c_i32p)]
 
 
 class Problem(C.Structure):
@@ -89,6 +90,7 @@ class SolverInfo(C.Structure):
 EXPORTS = [
     "mgbx_default_config", "mgbx_default_step_opts", "mgbx_abi_version", "mgbx_device_count",
     "mgbx_create", "mgbx_destroy", "mgbx_last_error", "mgbx_step", "mgbx_scalars",
+    "mgbx_nccl_unique_id", "mgbx_comm_init",
     "mgbx_phase1_init", "mgbx_attach_feasibility", "mgbx_set_feasibility_box", "mgbx_reset_feasibility_state", "mgbx_handoff",
     "mgbx_matched_t", "mgbx_get_z", "mgbx_set_z", "mgbx_set_grids", "mgbx_level_size",
     "mgbx_barrier_eval", "mgbx_hessian_pattern", "mgbx_hessian_values", "mgbx_solve_newton_system",
@@ -121,6 +123,8 @@ def lib():
     L.mgbx_abi_version.restype = C.c_int
     L.mgbx_device_count.restype = C.c_int
     L.mgbx_create.argtypes = [C.POINTER(Problem), C.POINTER(Config), C.POINTER(H)]
+    L.mgbx_nccl_unique_id.argtypes = [C.c_char_p]
+    L.mgbx_comm_init.argtypes = [H, C.c_int, C.c_int, C.c_char_p]
     L.mgbx_destroy.argtypes = [H]
     L.mgbx_destroy.restype = None
     L.mgbx_last_error.argtypes = [H]
@@ -225,9 +229,11 @@ def _pack_amg(keep: _Keep, M) -> Amg:
     Ts = (Csr * max(1, L - 1))(*[keep.csr(T) for T in M.T])
     keep.bufs += [Rs, Ts]
     voff = np.asarray(M.var_offsets, dtype=np.int64).reshape(L, M.nu + 1)
+    vl = getattr(M, "var_local", None)
     return Amg(n, N, p, M.nu, M.nD, L, keep.f64(M.w), len(names),
                C.cast(ops, C.POINTER(c_f64p)), keep.i32(D_var), keep.i32(D_op),
-               C.cast(Rs, C.POINTER(Csr)), C.cast(Ts, C.POINTER(Csr)), keep.i64(voff))
+               C.cast(Rs, C.POINTER(Csr)), C.cast(Ts, C.POINTER(Csr)), keep.i64(voff),
+               int(getattr(M, "n_global", 0)), keep.i32(vl) if vl is not None else None)
 
 
 def _pack_convex(keep: _Keep, Q, n) -> Convex:
@@ -260,7 +266,7 @@ def default_config(**kw) -> Config:
 class Handle:
     """Device-resident problem (the result of native_to_device in the reference)."""
 
-    def __init__(self, prob, barrier_weights=None, with_feasibility=True, **cfg):
+    def __init__(self, prob, barrier_weights=None, with_feasibility=True, comm=None, **cfg):
         L = lib()
         keep = _Keep()
         P = Problem()
@@ -278,6 +284,9 @@ class Handle:
         rc = L.mgbx_create(C.byref(P), C.byref(self.cfg), C.byref(self._h))
         if rc != OK:
             raise MgbxError(rc, (L.mgbx_last_error(None) or b"").decode())
+        if comm is not None:
+            rank, world, uid = comm
+            self._check(L.mgbx_comm_init(self._h, int(rank), int(world), uid))
         self.n = n
         self.nu = [prob.M[0].nu, prob.M[1].nu if prob.M[1] is not None else 0]
         self.nD = [prob.M[0].nD, prob.M[1].nD if prob.M[1] is not None else 0]
@@ -425,6 +434,15 @@ class Handle:
         self._check(lib().mgbx_solve_newton_system(self._h, which, level, float(t), _ptr(s), _ptr(rhs),
                                                    _ptr(x), C.byref(it)))
         return x, it.value
+
+
+def nccl_unique_id() -> bytes:
+    """128-byte NCCL id (rank 0 creates it; broadcast it to the other ranks, e.g. with torch.distributed)."""
+    buf = C.create_string_buffer(128)
+    rc = lib().mgbx_nccl_unique_id(buf)
+    if rc != OK:
+        raise MgbxError(rc, (lib().mgbx_last_error(None) or b"").decode())
+    return buf.raw
 
 
 def plan_pattern(R, N, p, nu, D_var):
