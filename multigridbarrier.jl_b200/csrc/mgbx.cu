@@ -256,6 +256,75 @@ inline void tmp_free(void *p, cudaStream_t s) {
   if (p) cudaFreeAsync(p, s);
 }
 
+// (row << 32 | col) keys (unsorted, duplicates allowed) -> CSR pattern with sorted columns; consumes `keys`.
+// drop_sentinel: keys equal to ~0 (padding of the multi-GPU all-gather) are discarded.
+DevCsr csr_from_keys(Pool &pool, unsigned long long *keys, int64_t total, int64_t rows, int64_t cols, bool drop_sentinel, cudaStream_t s) {
+  DevCsr C;
+  C.rows = rows;
+  C.cols = cols;
+  if (total > INT32_MAX) throw std::runtime_error("csr_from_keys: more than 2^31 candidate entries");
+  unsigned long long *keys2 = tmp_alloc<unsigned long long>(total, s);
+  int *nsel = tmp_alloc<int>(1, s);
+  int nnz = 0;
+  if (total > 0) {
+    size_t tmp_bytes = 0;
+    const int end_bit = 64;
+    CK(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, keys, keys2, (int)total, 0, end_bit, s));
+    char *tmp = tmp_alloc<char>(tmp_bytes, s);
+    CK(cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, keys, keys2, (int)total, 0, end_bit, s));
+    tmp_free(tmp, s);
+    CK(cub::DeviceSelect::Unique(nullptr, tmp_bytes, keys2, keys, nsel, (int)total, s));
+    tmp = tmp_alloc<char>(tmp_bytes, s);
+    CK(cub::DeviceSelect::Unique(tmp, tmp_bytes, keys2, keys, nsel, (int)total, s));
+    tmp_free(tmp, s);
+    CK(cudaMemcpyAsync(&nnz, nsel, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (drop_sentinel && nnz > 0) {
+      unsigned long long last = 0;
+      CK(cudaMemcpyAsync(&last, keys + (nnz - 1), sizeof(last), cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+      if (last == ~0ull) --nnz;
+    }
+  }
+  C.nnz = nnz;
+  C.ptr = pool.alloc<int64_t>(C.rows + 1);
+  C.idx = pool.alloc<int32_t>(C.nnz);
+  C.val = pool.zeros<double>(C.nnz, s);
+  k_sym_finish<<<nblk(std::max<int64_t>(C.nnz, C.rows + 1)), 256, 0, s>>>(keys, C.nnz, C.rows, C.ptr, C.idx);
+  CK(cudaGetLastError());
+  tmp_free(keys, s);
+  tmp_free(keys2, s);
+  tmp_free(nsel, s);
+  CK(cudaStreamSynchronize(s));
+  return C;
+}
+
+// Multi-GPU: the union over the ranks of the local top-level patterns (each rank sees only its elements), so that
+// every rank assembles into the SAME CSR structure and the values can be all-reduced.
+DevCsr global_pattern(int nranks, void *comm, Pool &pool, const HostCsr &pat, cudaStream_t s) {
+  NcclApi &N = nccl_api();
+  const int64_t nloc = pat.nnz();
+  std::vector<unsigned long long> hk(nloc);
+  for (int64_t i = 0; i < pat.rows; ++i)
+    for (int64_t k = pat.ptr[i]; k < pat.ptr[i + 1]; ++k) hk[k] = ((unsigned long long)i << 32) | (unsigned int)pat.idx[k];
+  int64_t *dcnt = tmp_alloc<int64_t>(nranks + 1, s);
+  CK(cudaMemcpyAsync(dcnt + nranks, &nloc, sizeof(int64_t), cudaMemcpyHostToDevice, s));
+  NCK(N.AllGather(dcnt + nranks, dcnt, 1, kNcclInt64, comm, s));
+  std::vector<int64_t> cnt(nranks);
+  CK(cudaMemcpyAsync(cnt.data(), dcnt, sizeof(int64_t) * nranks, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  tmp_free(dcnt, s);
+  const int64_t maxc = *std::max_element(cnt.begin(), cnt.end());
+  unsigned long long *send = tmp_alloc<unsigned long long>(maxc, s);
+  unsigned long long *all = tmp_alloc<unsigned long long>(maxc * nranks, s);
+  CK(cudaMemsetAsync(send, 0xff, sizeof(unsigned long long) * std::max<int64_t>(1, maxc), s));
+  CK(cudaMemcpyAsync(send, hk.data(), sizeof(unsigned long long) * nloc, cudaMemcpyHostToDevice, s));
+  NCK(N.AllGather(send, all, (size_t)maxc, kNcclUint64, comm, s));
+  CK(cudaStreamSynchronize(s));
+  tmp_free(send, s);
+  return csr_from_keys(pool, all, maxc * nranks, pat.rows, pat.cols, true, s);
+}
+
 // Sparsity pattern of A*B on the device: candidate keys (row << 32 | col) -> radix sort -> unique -> CSR.
 DevCsr device_symbolic(Pool &pool, const DevCsr &A, const DevCsr &B, cudaStream_t s) {
   if (A.cols != B.rows) throw std::runtime_error("device_symbolic: inner dimensions differ");
@@ -278,38 +347,14 @@ DevCsr device_symbolic(Pool &pool, const DevCsr &A, const DevCsr &B, cudaStream_
     tmp_free(offs, s);
     throw std::runtime_error("device_symbolic: more than 2^31 candidate entries");
   }
-  unsigned long long *keys = tmp_alloc<unsigned long long>(total, s), *keys2 = tmp_alloc<unsigned long long>(total, s);
-  int *nsel = tmp_alloc<int>(1, s);
-  int nnz = 0;
+  unsigned long long *keys = tmp_alloc<unsigned long long>(total, s);
   if (total > 0) {
     k_sym_fill<<<nblk(A.rows), 256, 0, s>>>(A, B, offs, keys);
     CK(cudaGetLastError());
-    int end_bit = 33;
-    while (end_bit < 64 && ((unsigned long long)A.rows >> (end_bit - 32)) != 0) ++end_bit;
-    CK(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, keys, keys2, (int)total, 0, end_bit, s));
-    tmp = tmp_alloc<char>(tmp_bytes, s);
-    CK(cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, keys, keys2, (int)total, 0, end_bit, s));
-    tmp_free(tmp, s);
-    CK(cub::DeviceSelect::Unique(nullptr, tmp_bytes, keys2, keys, nsel, (int)total, s));
-    tmp = tmp_alloc<char>(tmp_bytes, s);
-    CK(cub::DeviceSelect::Unique(tmp, tmp_bytes, keys2, keys, nsel, (int)total, s));
-    tmp_free(tmp, s);
-    CK(cudaMemcpyAsync(&nnz, nsel, sizeof(int), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
   }
-  C.nnz = nnz;
-  C.ptr = pool.alloc<int64_t>(C.rows + 1);
-  C.idx = pool.alloc<int32_t>(C.nnz);
-  C.val = pool.zeros<double>(C.nnz, s);
-  k_sym_finish<<<nblk(std::max<int64_t>(C.nnz, C.rows + 1)), 256, 0, s>>>(keys, C.nnz, C.rows, C.ptr, C.idx);
-  CK(cudaGetLastError());
-  tmp_free(keys, s);
-  tmp_free(keys2, s);
-  tmp_free(nsel, s);
   tmp_free(cand, s);
   tmp_free(offs, s);
-  CK(cudaStreamSynchronize(s));
-  return C;
+  return csr_from_keys(pool, keys, total, C.rows, C.cols, false, s);
 }
 
 // two-pass sliced-ELL construction shared by the device plan builders: COUNT(P, width) then FILL(P)
@@ -774,6 +819,7 @@ struct Engine {
       for (int k = 0; k < 4; ++k) h->hscal[k] = h->hscal[40 + k];
       for (int k = 0; k < 3; ++k) h->hscal[4 + k] = h->hscal[44 + k] + h->hscal[53 + k];
       h->hscal[7] = h->hscal[38] + h->hscal[39];
+      CK(cudaMemsetAsync(h->dscal + 38, 0, 2 * sizeof(double), s));   // the trial norms are consumed
     }
     if (h->res) h->res->f01_evals++;
     EvalOut o;
@@ -920,13 +966,15 @@ std::unique_ptr<System> build_system(mgbx_handle *h, Amg &A, bool condensed, int
   const bool vb = h->cfg.verbose > 0;
   HostCsr Einc = element_incidence(Rtop, A.N, A.p, used, A.n, colmap, mtop);
   HostCsr pat = plan_pattern(Einc);
-  if (vb) fprintf(stderr, "[mgbx] build_system(cond=%d): pattern m=%lld nnz=%lld %.3fs\n", (int)condensed, (long long)mtop, (long long)pat.nnz(), tm.lap());
+  if (vb) fprintf(stderr, "[mgbx] build_system(cond=%d): pattern m=%lld nnz=%lld %.3fs\n", (int)condensed, (long long)mtop, (long long)pat.nnz(), tm.lap());   // (local pattern on a multi-GPU rank)
   // gather plan, built on the device: for each nz of the pattern, the Hblk entries (and weights) that sum into it
   const int p = A.p;
   const int64_t pp = (int64_t)p * p;
   S->hblk_size = (int64_t)S->pl.npairs * A.N * pp;
   if (S->hblk_size > INT32_MAX) throw std::runtime_error("element block array exceeds 32-bit gather indices");
-  S->lev[0].A = upload_csr(pool, pat, s, false);
+  // multi-GPU: each rank sees only its own elements; the CSR structure is the union over the ranks
+  S->lev[0].A = (h->nranks > 1) ? global_pattern(h->nranks, h->comm, pool, pat, s) : upload_csr(pool, pat, s, false);
+  const int64_t top_nnz = S->lev[0].A.nnz;
   {
     bool unit = true;
     for (double v : Rtop.val)
@@ -963,12 +1011,12 @@ std::unique_ptr<System> build_system(mgbx_handle *h, Amg &A, bool condensed, int
           if (S->pl.va[k] == S->kept[qa] && S->pl.vb[k] == S->kept[qb]) pr = k;
         Q.pair_of[qa * Q.nkept + qb] = pr;
       }
-    int32_t *rowof = tmp_alloc<int32_t>(pat.nnz(), s);
+    int32_t *rowof = tmp_alloc<int32_t>(top_nnz, s);
     k_csr_rows<<<nblk(pat.rows), 256, 0, s>>>(S->lev[0].A, rowof);
     Q.rowof = rowof;
-    const unsigned int g = nblk(((pat.nnz() + 31) / 32) * 32);
+    const unsigned int g = nblk(((top_nnz + 31) / 32) * 32);
     S->top = build_sell_two_pass(
-        pool, pat.nnz(), !unit, s, [&](SellPlan &P, int32_t *width) { k_top_plan<0><<<g, 256, 0, s>>>(Q, P, width); },
+        pool, top_nnz, !unit, s, [&](SellPlan &P, int32_t *width) { k_top_plan<0><<<g, 256, 0, s>>>(Q, P, width); },
         [&](SellPlan &P, int32_t *width) { k_top_plan<1><<<g, 256, 0, s>>>(Q, P, width); });
     tmp_free(rowof, s);
     einct.free_all();
@@ -1939,6 +1987,7 @@ void mgbx_destroy(mgbx_handle *h) {
       if (S)
         for (auto &kv : S->graphs) cudaGraphExecDestroy(kv.second);
   h->pool.release();
+  if (h->comm) nccl_api().CommDestroy(h->comm);
   if (h->hscal) cudaFreeHost(h->hscal);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -1949,6 +1998,34 @@ void mgbx_destroy(mgbx_handle *h) {
   }
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
+}
+
+int mgbx_nccl_unique_id(char id[128]) {
+  if (!id) return MGBX_ERR_ARG;
+  return guarded(nullptr, [&]() -> int {
+    NcclUniqueId u;
+    NCK(nccl_api().GetUniqueId(&u));
+    memcpy(id, u.internal, 128);
+    return MGBX_OK;
+  });
+}
+
+int mgbx_comm_init(mgbx_handle *h, int rank, int nranks, const char id[128]) {
+  if (!h || !id || nranks < 1 || rank < 0 || rank >= nranks) return MGBX_ERR_ARG;
+  return guarded(h, [&]() -> int {
+    if (h->comm) throw ArgError("mgbx_comm_init: communicator already initialised");
+    if (nranks == 1) return MGBX_OK;
+    for (int w = 0; w < 2; ++w)
+      if (h->amg[w].sys_cond || h->amg[w].sys_coarse || h->amg[w].sys_hook) throw ArgError("mgbx_comm_init must precede the first solve");
+    NcclUniqueId u;
+    memcpy(u.internal, id, 128);
+    void *comm = nullptr;
+    NCK(nccl_api().CommInitRank(&comm, nranks, u, rank));
+    h->comm = comm;
+    h->rank = rank;
+    h->nranks = nranks;
+    return MGBX_OK;
+  });
 }
 
 int mgbx_step(mgbx_handle *h, int which, double t, const mgbx_step_opts *o, mgbx_step_result *r) {
@@ -1980,6 +2057,7 @@ int mgbx_scalars(mgbx_handle *h, int which, mgbx_scalars_out *out) {
     out->all_finite = 1;
     for (int v = 0; v < A.nu; ++v) {
       E_LAUNCH(KC_VEC, k_maxabs<<<E.red_grid(A.n), kRedThreads, 0, h->stream>>>(A.n, A.z + (int64_t)v * A.n, h->partials, h->ticket, h->dscal));
+      if (E.dist()) E.allreduce(h->dscal, 3, kNcclMax);
       E.fetch(3);
       out->var_max[v] = h->hscal[0];
       out->var_absmax[v] = h->hscal[1];
@@ -2001,6 +2079,7 @@ int mgbx_phase1_init(mgbx_handle *h, int32_t *needs_phase1, double *b, double *z
     double zmax = 0.0;
     for (int v = 0; v < A.nu; ++v) {
       E_LAUNCH(KC_VEC, k_maxabs<<<E.red_grid(A.n), kRedThreads, 0, h->stream>>>(A.n, A.z + (int64_t)v * A.n, h->partials, h->ticket, h->dscal));
+      if (E.dist()) E.allreduce(h->dscal, 3, kNcclMax);
       E.fetch(3);
       zmax = std::max(zmax, h->hscal[1]);
     }
@@ -2016,6 +2095,7 @@ int mgbx_phase1_init(mgbx_handle *h, int32_t *needs_phase1, double *b, double *z
       E.copy(F.zinit, A.z, (int64_t)A.nu * A.n);
       E.copy(F.z, F.zinit, (int64_t)F.nu * F.n);
       E_LAUNCH(KC_VEC, k_maxabs<<<E.red_grid(A.n), kRedThreads, 0, h->stream>>>(A.n, F.zinit + (int64_t)A.nu * A.n, h->partials, h->ticket, h->dscal));
+      if (E.dist()) E.allreduce(h->dscal, 3, kNcclMax);
       E.fetch(3);
       *b = 2.0 * std::max(1.0, h->hscal[0]);
     }
@@ -2220,6 +2300,7 @@ int mgbx_hessian_values(mgbx_handle *h, int which, int level, double t, const do
       ElemParams EP = E.elem_params(A);
       E_LAUNCH(KC_BLOCKHESS, k_blockhess<<<nblk(S.hblk_size), 256, 0, h->stream>>>(EP, S.pl, A.Hn, S.Hblk));
       E_LAUNCH(KC_GATHER, k_sell_gather<<<nblk(S.lev[0].A.nnz), 256, 0, h->stream>>>(S.top, S.Hblk, S.lev[0].A.val));
+      if (E.dist()) E.allreduce(S.lev[0].A.val, S.lev[0].A.nnz);
       const int ktop = A.L - 1 - level;
       for (int k = 0; k < ktop; ++k) {
         SysLevel &Lv = S.lev[k];

@@ -147,7 +147,8 @@ def mgb_driver(h: native.Handle, M, t=0.1, t_feasibility=None, feasibility_Rmax=
     if log is None:
         log = lambda *a: None
     M1, M2 = M
-    n = len(M1.w)
+    n = int(getattr(M1, "n_global", 0) or len(M1.w))     # the WHOLE mesh's node count (a multi-GPU rank holds a slice)
+    n_loc = len(M1.w)
     ncomp = M1.nu
     L1 = len(M1.R_fine)
     rest.setdefault("stop_lambda_tol", 0.25 / math.sqrt(n))
@@ -215,23 +216,36 @@ def mgb_driver(h: native.Handle, M, t=0.1, t_feasibility=None, feasibility_Rmax=
                 log("_matched_t: warm start matches t=%r, starting main ramp at t=%r" % (tstar, tm))
         t = min(t, tm)
     SOL_main = mgb_core(h, native.MAIN, L1, t=t, finalize=finalize, log=log, stats=stats, **rest)
-    z = h.get_z(native.MAIN).reshape(ncomp, n).T.copy()
+    z = h.get_z(native.MAIN).reshape(ncomp, n_loc).T.copy()
     return dict(z=z, SOL_feasibility=SOL_feas, SOL_main=SOL_main)
 
 
-def mgb_solve(prob, barrier_nodes=None, config=None, log=None, handle=None, **kw):
-    """src/mgb.jl:798-842.  Returns dict(z, SOL_main, SOL_feasibility, log, geometry, stats)."""
+def mgb_solve(prob, barrier_nodes=None, config=None, log=None, handle=None, comm=None, **kw):
+    """src/mgb.jl:798-842.  Returns dict(z, SOL_main, SOL_feasibility, log, geometry, stats).
+
+    comm = (rank, world, nccl_id): multi-GPU run, one process per GPU.  `prob` is the WHOLE problem on every rank; this
+    rank keeps the element block partition.element_range(N, rank, world) and returns its rows of z in sol["z"]
+    (sol["node_range"] = (i0, i1)); the scalar histories (its, ts, c_dot_Dz) are identical on all ranks."""
     lines = []
+    node_range = None
+    if comm is not None and comm[1] > 1:
+        from . import partition
+        bw_full = barrier_weights(prob.M[0].w, barrier_nodes)
+        prob = partition.shard_problem(prob, comm[0], comm[1])
+        node_range = prob.node_range
+        bw_shard = partition.shard_barrier_weights(bw_full, *node_range)
+    else:
+        comm = None
 
     def _log(*a):
         s = "".join(str(x) for x in a)
         lines.append(s)
         if log is not None:
             log(s)
-    bw = barrier_weights(prob.M[0].w, barrier_nodes)
+    bw = bw_shard if comm is not None else barrier_weights(prob.M[0].w, barrier_nodes)
     own = handle is None
     t0 = time.time()
-    h = handle if handle is not None else native.Handle(prob, barrier_weights=bw, **(config or {}))
+    h = handle if handle is not None else native.Handle(prob, barrier_weights=bw, comm=comm, **(config or {}))
     t_create = time.time() - t0
     stats = dict(f01_evals=0, f2_evals=0, linear_solves=0, pcg_iters=0, ms_f01=0.0, ms_f2=0.0, ms_solve=0.0)
     try:
@@ -244,6 +258,7 @@ def mgb_solve(prob, barrier_nodes=None, config=None, log=None, handle=None, **kw
     stats["create_s"] = t_create
     sol["log"] = "\n".join(lines)
     sol["geometry"] = prob.geometry
+    sol["node_range"] = node_range
     sol["stats"] = stats
     return sol
 
