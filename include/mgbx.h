@@ -188,7 +188,9 @@ const char *mgbx_last_error(const mgbx_handle *h);   /* h may be NULL: last crea
  * and every rank then runs the identical (deterministic) multigrid-PCG solve on the shared unknowns.  NCCL is loaded with
  * dlopen("libnccl.so.2") only when mgbx_comm_init is called.  Rank 0 obtains an id and the host broadcasts it. */
 int mgbx_nccl_unique_id(char id[128]);
-int mgbx_comm_init(mgbx_handle *h, int rank, int nranks, const char id[128]);
+int mgbx_comm_init(mgbx_handle *h, int rank, int nranks, const char id[128]);   /* id == NULL: reuse the process-wide communicator
+                                                                                  created by an earlier call with the same (rank, nranks) */
+int mgbx_comm_finalize(void);
 
 /* the hot path */
 int mgbx_step(mgbx_handle *h, int which, double t, const mgbx_step_opts *o, mgbx_step_result *r);

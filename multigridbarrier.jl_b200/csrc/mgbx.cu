@@ -1987,7 +1987,6 @@ void mgbx_destroy(mgbx_handle *h) {
       if (S)
         for (auto &kv : S->graphs) cudaGraphExecDestroy(kv.second);
   h->pool.release();
-  if (h->comm) nccl_api().CommDestroy(h->comm);
   if (h->hscal) cudaFreeHost(h->hscal);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -2010,22 +2009,43 @@ int mgbx_nccl_unique_id(char id[128]) {
   });
 }
 
+// The communicator is process-wide: creating one costs about a second, so handles share it.  id != NULL creates
+// (or replaces) it; id == NULL reuses the existing one for the same (rank, nranks).
+static void *g_comm = nullptr;
+static int g_comm_rank = -1, g_comm_nranks = 0;
+
 int mgbx_comm_init(mgbx_handle *h, int rank, int nranks, const char id[128]) {
-  if (!h || !id || nranks < 1 || rank < 0 || rank >= nranks) return MGBX_ERR_ARG;
+  if (!h || nranks < 1 || rank < 0 || rank >= nranks) return MGBX_ERR_ARG;
   return guarded(h, [&]() -> int {
     if (h->comm) throw ArgError("mgbx_comm_init: communicator already initialised");
     if (nranks == 1) return MGBX_OK;
     for (int w = 0; w < 2; ++w)
       if (h->amg[w].sys_cond || h->amg[w].sys_coarse || h->amg[w].sys_hook) throw ArgError("mgbx_comm_init must precede the first solve");
-    NcclUniqueId u;
-    memcpy(u.internal, id, 128);
-    void *comm = nullptr;
-    NCK(nccl_api().CommInitRank(&comm, nranks, u, rank));
-    h->comm = comm;
+    if (id) {
+      NcclUniqueId u;
+      memcpy(u.internal, id, 128);
+      void *comm = nullptr;
+      NCK(nccl_api().CommInitRank(&comm, nranks, u, rank));
+      if (g_comm) nccl_api().CommDestroy(g_comm);
+      g_comm = comm;
+      g_comm_rank = rank;
+      g_comm_nranks = nranks;
+    } else if (!g_comm || g_comm_rank != rank || g_comm_nranks != nranks) {
+      throw ArgError("mgbx_comm_init: no process-wide communicator for this (rank, nranks); pass an NCCL id first");
+    }
+    h->comm = g_comm;
     h->rank = rank;
     h->nranks = nranks;
     return MGBX_OK;
   });
+}
+
+int mgbx_comm_finalize(void) {
+  if (g_comm) nccl_api().CommDestroy(g_comm);
+  g_comm = nullptr;
+  g_comm_rank = -1;
+  g_comm_nranks = 0;
+  return MGBX_OK;
 }
 
 int mgbx_step(mgbx_handle *h, int which, double t, const mgbx_step_opts *o, mgbx_step_result *r) {

@@ -90,7 +90,7 @@ class SolverInfo(C.Structure):
 EXPORTS = [
     "mgbx_default_config", "mgbx_default_step_opts", "mgbx_abi_version", "mgbx_device_count",
     "mgbx_create", "mgbx_destroy", "mgbx_last_error", "mgbx_step", "mgbx_scalars",
-    "mgbx_nccl_unique_id", "mgbx_comm_init",
+    "mgbx_nccl_unique_id", "mgbx_comm_init", "mgbx_comm_finalize",
     "mgbx_phase1_init", "mgbx_attach_feasibility", "mgbx_set_feasibility_box", "mgbx_reset_feasibility_state", "mgbx_handoff",
     "mgbx_matched_t", "mgbx_get_z", "mgbx_set_z", "mgbx_set_grids", "mgbx_level_size",
     "mgbx_barrier_eval", "mgbx_hessian_pattern", "mgbx_hessian_values", "mgbx_solve_newton_system",
