@@ -1153,7 +1153,7 @@ void Engine::setup_hierarchy(Amg &A, System &S, int ktop) {
     }
   }
   if (direct) {
-    dense_factor(S, Ltop, false);
+    if (Ltop.m > kCoarseMaxDense) dense_factor(S, Ltop, false);   // tiny systems are factorised inside k_dense_solve_small
     return;
   }
   for (int k = ktop; k <= kend; ++k) {
@@ -1431,10 +1431,15 @@ int Engine::pcg(System &S, int ktop, const double *b, double *x) {
 int Engine::solve_compact(System &S, int ktop, const double *b, double *x) {
   SysLevel &Lv = S.lev[ktop];
   if (use_direct(S, Lv)) {
-    dense_apply(Lv, b, x);
+    const bool small = Lv.m <= kCoarseMaxDense;
+    auto apply = [&](const double *rhs, double *out) {
+      if (small) LAUNCH(KC_DENSE, k_dense_solve_small<<<1, 1024, dense_solve_small_smem((int)Lv.m), s>>>(Lv.A, rhs, out, nullptr));
+      else dense_apply(Lv, rhs, out);
+    };
+    apply(b, x);
     // one step of iterative refinement against the CSR operator
     spmv(Lv.A, x, b, -1.0, Lv.r, Lv.spmv_group);
-    dense_apply(Lv, Lv.r, Lv.x2);
+    apply(Lv.r, Lv.x2);
     LAUNCH(KC_VEC, k_axpby<<<nblk(Lv.m), 256, 0, s>>>(Lv.m, 1.0, x, 1.0, Lv.x2, x));
     return 0;
   }
@@ -1511,6 +1516,8 @@ Engine::NewtonOut Engine::newton(Amg &A, int J, double t, int maxit, int stop_ki
   zero(A.x, m);
   EvalOut e0 = eval_f01(A, J, t, A.z, A.x, A.g);
   if (!e0.finite) {
+    if (h->cfg.verbose > 0)
+      fprintf(stderr, "[mgbx] newton J=%d: starting point outside the domain (y=%g, non-finite nodes=%g, |g|=%g)\n", J, e0.y, e0.nonfinite_nodes, e0.gnorm);
     out.status = MGBX_NON_FINITE;
     out.y = e0.y;
     return out;
@@ -1530,6 +1537,9 @@ Engine::NewtonOut Engine::newton(Amg &A, int J, double t, int maxit, int stop_ki
     if (h->cfg.verbose > 1)
       fprintf(stderr, "[mgbx] newton J=%d m=%lld k=%d y=%.17g |g|=%.6g lam2=%.6g pcg=%d t=%g\n", J, (long long)m, k, y, gnorm, inc, pit, t);
     if (!dir_finite) {
+      if (h->cfg.verbose > 0)
+        fprintf(stderr, "[mgbx] newton J=%d m=%lld k=%d: non-finite direction (g.d=%g |d|^2=%g non-finite entries=%g, pcg=%d, |r|^2=%g |b|^2=%g)\n", J,
+                (long long)m, k, inc, h->hscal[5], h->hscal[6], pit, h->hscal[9], h->hscal[11]);
       out.status = MGBX_NON_FINITE;
       break;
     }
@@ -1948,6 +1958,7 @@ int mgbx_create(const mgbx_problem *prob, const mgbx_config *cfg, mgbx_handle **
       if (!coop || per_sm < 1) throw std::runtime_error("CUDA device cannot run the cooperative persistent solve kernel");
       h->pcg_grid = std::min(nsm, kPcgMaxGrid);   // one CTA per SM
       CK(cudaFuncSetAttribute(k_coarse_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coarse_inverse_smem(kCoarseMaxDense)));
+      CK(cudaFuncSetAttribute(k_dense_solve_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dense_solve_small_smem(kCoarseMaxDense)));
     }
     CK(cudaEventCreate(&h->ev0));
     CK(cudaEventCreate(&h->ev1));

@@ -126,7 +126,10 @@ __global__ void __launch_bounds__(1024) k_coarse_inverse(DevCsr A, double *Minv)
   __syncthreads();
   // right-looking Cholesky on the lower triangle
   for (int j = 0; j < m; ++j) {
-    if (tid == 0) S[j * ld + j] = sqrt(S[j * ld + j]);
+    if (tid == 0) {   // the scaled matrix has unit diagonal: a pivot below 1e-13 means numerical singularity; keep the
+      const double v = S[j * ld + j];   // preconditioner finite (any SPD approximation is a valid preconditioner)
+      S[j * ld + j] = sqrt((v > 1e-13 && isfinite(v)) ? v : 1e-13);
+    }
     __syncthreads();
     const double piv = S[j * ld + j];
     for (int i = j + 1 + tid; i < m; i += nt) S[i * ld + j] /= piv;
@@ -160,6 +163,142 @@ __global__ void __launch_bounds__(1024) k_coarse_inverse(DevCsr A, double *Minv)
     Minv[t] = s * d[i] * d[j];
   }
 }
+
+
+// ------------------------------------------------------------------------------------------------
+// Robust direct solve of a small system (m <= kCoarseMaxDense) in one CTA:  x = A^{-1} b.
+// Mirrors the reference's `Symmetric(H) \ g` (src/utils.jl:142-145: Cholesky, falling back to a pivoted
+// factorisation when H is numerically indefinite): diagonally scaled Cholesky first; if a pivot is not
+// positive, Gaussian elimination with partial pivoting on the same matrix.  info[0] = 0 / 1 says which ran.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_dense_solve_small(DevCsr A, const double *__restrict__ b, double *x, int *info) {
+  extern __shared__ double sm[];
+  const int m = (int)A.rows;
+  const int ld = m + 1;
+  double *S = sm;                       // m x (m+1)
+  double *rhs = S + (size_t)m * ld;     // m
+  double *d = rhs + m;                  // m
+  __shared__ int fail, piv;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  auto load = [&](bool scaled) {
+    for (int t = tid; t < m * ld; t += nt) S[t] = 0.0;
+    __syncthreads();
+    for (int row = tid; row < m; row += nt)
+      for (int64_t k = A.ptr[row]; k < A.ptr[row + 1]; ++k)
+        S[row * ld + A.idx[k]] = scaled ? A.val[k] * d[row] * d[A.idx[k]] : A.val[k];
+    __syncthreads();
+  };
+  for (int row = tid; row < m; row += nt) {
+    double dg = 0.0;
+    for (int64_t k = A.ptr[row]; k < A.ptr[row + 1]; ++k)
+      if (A.idx[k] == row) dg = A.val[k];
+    d[row] = (dg > 0.0 && isfinite(dg)) ? 1.0 / sqrt(dg) : 1.0;
+  }
+  if (tid == 0) fail = 0;
+  __syncthreads();
+  load(true);
+  for (int j = 0; j < m && !fail; ++j) {
+    if (tid == 0) {
+      const double v = S[j * ld + j];
+      if (!(v > 0.0) || !isfinite(v)) fail = 1;
+      else S[j * ld + j] = sqrt(v);
+    }
+    __syncthreads();
+    if (fail) break;
+    const double pv = S[j * ld + j];
+    for (int i = j + 1 + tid; i < m; i += nt) S[i * ld + j] /= pv;
+    __syncthreads();
+    const int rem = m - j - 1;
+    for (int t = tid; t < rem * rem; t += nt) {
+      const int i = j + 1 + t / rem, k = j + 1 + t % rem;
+      if (k <= i) S[i * ld + k] -= S[i * ld + j] * S[k * ld + j];
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (!fail) {
+    // L L' y = D b, x = D y  (one warp: the triangular solves are sequential in the row index)
+    for (int i = tid; i < m; i += nt) rhs[i] = b[i] * d[i];
+    __syncthreads();
+    if (tid < 32) {
+      for (int k = 0; k < m; ++k) {
+        double sacc = 0.0;
+        for (int j = tid; j < k; j += 32) sacc += S[k * ld + j] * rhs[j];
+        sacc = warp_sum(sacc);
+        if (tid == 0) rhs[k] = (rhs[k] - sacc) / S[k * ld + k];
+        __syncwarp();
+      }
+      for (int k = m - 1; k >= 0; --k) {
+        if (tid == 0) rhs[k] = rhs[k] / S[k * ld + k];
+        __syncwarp();
+        const double xk = rhs[k];
+        for (int j = tid; j < k; j += 32) rhs[j] -= S[k * ld + j] * xk;
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < m; i += nt) x[i] = rhs[i] * d[i];
+    if (tid == 0 && info) info[0] = 0;
+    return;
+  }
+  // pivoted elimination on the unscaled matrix
+  load(false);
+  for (int i = tid; i < m; i += nt) rhs[i] = b[i];
+  __syncthreads();
+  for (int k = 0; k < m; ++k) {
+    if (tid == 0) {
+      int best = k;
+      double bv = fabs(S[k * ld + k]);
+      for (int i = k + 1; i < m; ++i) {
+        const double v = fabs(S[i * ld + k]);
+        if (v > bv) {
+          bv = v;
+          best = i;
+        }
+      }
+      piv = best;
+    }
+    __syncthreads();
+    const int pr = piv;
+    if (pr != k) {
+      for (int j = tid; j < m; j += nt) {
+        const double t = S[k * ld + j];
+        S[k * ld + j] = S[pr * ld + j];
+        S[pr * ld + j] = t;
+      }
+      if (tid == 0) {
+        const double t = rhs[k];
+        rhs[k] = rhs[pr];
+        rhs[pr] = t;
+      }
+    }
+    __syncthreads();
+    const double pv = S[k * ld + k];
+    // multipliers in column k (kept in place), then the trailing update
+    for (int i = k + 1 + tid; i < m; i += nt) S[i * ld + k] /= pv;
+    __syncthreads();
+    const int rem = m - k - 1;
+    for (int t = tid; t < rem * rem; t += nt) {
+      const int i = k + 1 + t / rem, j = k + 1 + t % rem;
+      S[i * ld + j] -= S[i * ld + k] * S[k * ld + j];
+    }
+    for (int i = k + 1 + tid; i < m; i += nt) rhs[i] -= S[i * ld + k] * rhs[k];
+    __syncthreads();
+  }
+  if (tid < 32) {
+    for (int k = m - 1; k >= 0; --k) {
+      double sacc = 0.0;
+      for (int j = k + 1 + tid; j < m; j += 32) sacc += S[k * ld + j] * rhs[j];
+      sacc = warp_sum(sacc);
+      if (tid == 0) rhs[k] = (rhs[k] - sacc) / S[k * ld + k];
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < m; i += nt) x[i] = rhs[i];
+  if (tid == 0 && info) info[0] = 1;
+}
+inline size_t dense_solve_small_smem(int m) { return sizeof(double) * ((size_t)m * (m + 1) + 2 * (size_t)m); }
 
 // ------------------------------------------------------------------------------------------------
 // persistent PCG
