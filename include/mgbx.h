@@ -132,9 +132,11 @@ typedef struct {
   int32_t profile;           /* 1: time every kernel launch with CUDA events on the handle's stream (mgbx_kernel_stats) */
   int32_t persistent;        /* 1 (default): each PCG solve is ONE cooperative persistent kernel (one CTA per SM, grid barriers) */
   int32_t tail_max;          /* V-cycle levels with <= this many unknowns run inside CTA 0 of that kernel (default 1200) */
-  double pcg_rtol_final;     /* relative residual during the finalize pass (stopping_exact), default 1e-13 */
-  int32_t fused;             /* 1 (default): fused element kernels (operator blocks staged once in shared memory);
-                                0: separate per-node and per-block kernels (always used when a block does not fit) */
+  double pcg_rtol_final;     /* relative residual during the finalize pass (stopping_exact), default 1e-15 (i.e. to stagnation) */
+  int32_t fused;             /* 1 (default): fused element kernels (operator blocks staged once in shared memory), with the
+                                specialised kernel for the default (u, s) Euclidean-power family where it applies;
+                                2: generic fused kernel only; 0: separate per-node and per-block kernels (always used
+                                when a block does not fit in shared memory) */
   int32_t smoother;          /* V-cycle smoother of the persistent kernel: 1 (default) Chebyshev of degree smoother_sweeps
                                 with diagonal scaling on [lam/cheb_ratio, lam], lam = Gershgorin bound; 0 l1-Jacobi */
   double cheb_ratio;         /* default 4 */

@@ -1053,3 +1053,202 @@ __global__ void __launch_bounds__(256) k_elem(ElemFused Q) {
 }
 
 }  // namespace mgbx
+
+namespace mgbx {
+
+// ------------------------------------------------------------------------------------------------
+// k_elem_plap<MODE, DIM>: the fused element kernel specialised for the reference's default problem family
+// (src/mgb.jl:587-613,711-727): state (u, s), D = [u:id; u:d_1..d_DIM; s:id], one Euclidean-power cone on rows
+// 1..DIM+1 with identity A, zero b and uniform p, mu; s condensed node-locally.  Same shared-memory staging and
+// the same outputs (gb; hEEinv, hKE, Hblk) as the generic k_elem, but every loop over D rows / pieces / index maps
+// is resolved at compile time: the generic kernel is instruction-bound (~1700 warp instructions per warp of nodes,
+// 90% of them index bookkeeping), this one is bound by the operator-block stream.
+// ------------------------------------------------------------------------------------------------
+struct FastDiv {
+  unsigned int mul, d;   // q = umulhi(t, mul) for 0 <= t < 2^16, 1 <= d < 2^16
+};
+inline FastDiv make_fastdiv(unsigned int d) {
+  FastDiv f;
+  f.d = d;
+  f.mul = (unsigned int)((0x100000000ull + d - 1) / d);
+  return f;
+}
+__device__ __forceinline__ unsigned int fdiv(unsigned int t, const FastDiv &f) { return f.d == 1 ? t : __umulhi(t, f.mul); }
+
+struct PlapParams {
+  int64_t n, N;
+  int p, epb, p1, ES;
+  FastDiv dp, dpp;
+  const double *ops[3];
+  const double *zu, *zs;       // broken state of u and s (n each)
+  const double *w, *f, *bw;    // f: n x (DIM+2)
+  double t, inv_n, pexp, mu;
+  // F01
+  double *gbu, *gbs;
+  double *partials;
+  unsigned int *ticket;
+  double *red_out;
+  // F2
+  double *hEEinv, *hKE, *Hblk;
+};
+
+inline size_t elem_plap_smem(int dim, int epb, int ES, int p) {
+  return sizeof(double) * ((size_t)dim * epb * ES + (size_t)(1 + (dim * (dim + 1)) / 2) * epb * p);
+}
+
+template <int MODE, int DIM>
+__global__ void __launch_bounds__(256, 4) k_elem_plap(PlapParams P) {
+  extern __shared__ double esm[];
+  constexpr int NH = (DIM * (DIM + 1)) / 2;
+  const int p = P.p, pp = p * p, p1 = P.p1, ES = P.ES, epb = P.epb;
+  const int TM = epb * p;
+  double *ops_s = esm;                             // [a][el][c][r] padded
+  double *us = ops_s + (size_t)DIM * epb * ES;     // [slot]
+  double *ex = us + TM;                            // [row][slot]: F01 DIM rows, F2 NH rows
+  const int tid = threadIdx.x;
+  double red[4] = {0.0, 0.0, 0.0, -INFINITY};
+  const int op4[4] = {0, 0, 0, 1};
+  const int64_t ntiles = (P.N + epb - 1) / epb;
+  const double al = 2.0 / P.pexp;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t e0 = tile * epb;
+    const int ne = (int)min((int64_t)epb, P.N - e0);
+    const int T = ne * p;
+    const int64_t node0 = e0 * p;
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < DIM; ++a) {
+      const double *src = P.ops[a] + e0 * (int64_t)pp;
+      double *dst = ops_s + (size_t)a * epb * ES;
+      for (int t = tid; t < ne * pp; t += 256) {
+        const int el = (int)fdiv((unsigned int)t, P.dpp), rem = t - el * pp;
+        const int c = (int)fdiv((unsigned int)rem, P.dp), r = rem - c * p;
+        dst[el * ES + c * p1 + r] = src[t];
+      }
+    }
+    if (tid < T) us[tid] = P.zu[node0 + tid];
+    __syncthreads();
+    const int el = (int)fdiv((unsigned int)tid, P.dp), qn = tid - el * p;
+    const bool on = tid < T;
+    const int64_t i = node0 + tid;
+    double G0 = 0.0, Gs = 0.0;
+    if (on) {
+      double q[DIM];
+      const double *ue = us + el * p;
+#pragma unroll
+      for (int a = 0; a < DIM; ++a) {
+        const double *blk = ops_s + (size_t)a * epb * ES + el * ES + qn;
+        double acc = 0.0;
+        for (int c = 0; c < p; ++c) acc += blk[c * p1] * ue[c];
+        q[a] = acc;
+      }
+      const double uu = ue[qn];
+      const double s = P.zs[i];
+      const double bwi = P.bw ? P.bw[i] : 1.0;
+      const bool active = !(P.bw && bwi == 0.0);
+      const double sc = P.bw ? bwi : P.inv_n;
+      const double wi = P.w[i];
+      double qsq = 0.0;
+#pragma unroll
+      for (int a = 0; a < DIM; ++a) qsq += q[a] * q[a];
+      const double ls = Log(s);
+      const double sa = exp(al * ls);
+      const double r = sa - qsq;
+      const bool in = s > 0.0;
+      const double inv_r = 1.0 / r;
+      const double sam1 = in ? sa / s : safe_pow(s, al - 1.0);
+      if (MODE == NODE_F01) {
+        const double F0 = active ? (-Log(r) - P.mu * ls) : 0.0;
+        const double c0 = P.t * P.f[i];
+        const double cs = P.t * P.f[i + (int64_t)(DIM + 1) * P.n];
+        double lin = c0 * uu + cs * s;
+        G0 = wi * c0;
+        const double gs = -al * sam1 * inv_r - P.mu / s;
+        Gs = (active ? sc * gs : 0.0) + wi * cs;
+#pragma unroll
+        for (int a = 0; a < DIM; ++a) {
+          const double ca = P.t * P.f[i + (int64_t)(a + 1) * P.n];
+          lin += ca * q[a];
+          ex[a * TM + tid] = (active ? sc * 2.0 * inv_r * q[a] : 0.0) + wi * ca;
+        }
+        red[0] += active ? (P.bw ? bwi * F0 : F0) : 0.0;
+        red[1] += wi * lin;
+        if (!isfinite(F0)) red[2] += 1.0;
+      } else {
+        if (active) {
+          const double inv_r2 = inv_r * inv_r;
+          const double coef = -2.0 * al * sam1 * inv_r2;
+          const double sam2 = in ? sam1 / s : safe_pow(s, al - 2.0);
+          const double s2am2 = in ? sam1 * sam1 : safe_pow(s, 2.0 * al - 2.0);
+          const double hss = sc * (-al * (al - 1.0) * sam2 * inv_r + al * al * s2am2 * inv_r2 + P.mu / (s * s));
+          const double ihs = 1.0 / hss;
+          P.hEEinv[i] = ihs;
+          P.hKE[i] = 0.0;
+          double hqs[DIM];
+#pragma unroll
+          for (int a = 0; a < DIM; ++a) {
+            hqs[a] = sc * coef * q[a];
+            P.hKE[i + (int64_t)(a + 1) * P.n] = hqs[a];
+          }
+          int k = 0;
+#pragma unroll
+          for (int a = 0; a < DIM; ++a)
+#pragma unroll
+            for (int b = a; b < DIM; ++b, ++k) {
+              const double hab = sc * (4.0 * q[a] * q[b] * inv_r2 + (a == b ? 2.0 * inv_r : 0.0));
+              ex[k * TM + tid] = hab - hqs[a] * hqs[b] * ihs;
+            }
+        } else {
+          P.hEEinv[i] = 0.0;
+#pragma unroll
+          for (int a = 0; a <= DIM; ++a) P.hKE[i + (int64_t)a * P.n] = 0.0;
+#pragma unroll
+          for (int k = 0; k < NH; ++k) ex[k * TM + tid] = 0.0;
+        }
+      }
+    }
+    __syncthreads();
+    if (MODE == NODE_F01) {
+      if (on) {
+        double acc = G0;
+#pragma unroll
+        for (int a = 0; a < DIM; ++a) {
+          const double *blk = ops_s + (size_t)a * epb * ES + el * ES + qn * p1;
+          const double *g = ex + a * TM + el * p;
+          for (int k = 0; k < p; ++k) acc += blk[k] * g[k];
+        }
+        P.gbu[i] = acc;
+        P.gbs[i] = Gs;
+      }
+    } else {
+      double *out = P.Hblk + e0 * (int64_t)pp;
+      for (int t = tid; t < ne * pp; t += 256) {
+        const int e2 = (int)fdiv((unsigned int)t, P.dpp), rem = t - e2 * pp;
+        const int r = (int)fdiv((unsigned int)rem, P.dp), c = rem - r * p;
+        const double *h = ex + e2 * p;
+        const double *base = ops_s + e2 * ES;
+        double acc = 0.0;
+        for (int k = 0; k < p; ++k) {
+          double dr[DIM], dc[DIM];
+#pragma unroll
+          for (int a = 0; a < DIM; ++a) {
+            dr[a] = base[(size_t)a * epb * ES + r * p1 + k];
+            dc[a] = base[(size_t)a * epb * ES + c * p1 + k];
+          }
+          int kk = 0;
+#pragma unroll
+          for (int a = 0; a < DIM; ++a)
+#pragma unroll
+            for (int b = a; b < DIM; ++b, ++kk) {
+              const double hv = h[kk * TM + k];
+              acc += (a == b) ? dr[a] * hv * dc[a] : hv * (dr[a] * dc[b] + dr[b] * dc[a]);
+            }
+        }
+        out[t] = acc;
+      }
+    }
+  }
+  if (MODE == NODE_F01) grid_reduce<4>(red, op4, P.partials, P.ticket, P.red_out);
+}
+
+}  // namespace mgbx

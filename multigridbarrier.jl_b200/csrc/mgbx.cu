@@ -506,6 +506,7 @@ struct mgbx_handle {
   cudaEvent_t ev_cur = nullptr;
   int pcg_grid = 0;
   double cur_rtol2 = 1e-22;
+  int cur_window = 25;       // PCG stagnation window (iterations without a new best residual)
   // multi-GPU
   int rank = 0, nranks = 1;
   void *comm = nullptr;
@@ -527,11 +528,18 @@ void launch_node(const NodeParams &P, unsigned int grid, cudaStream_t s) {
 template <int MODE, int NDT>
 void launch_elem_inst(const ElemFused &Q, unsigned int grid, size_t smem, cudaStream_t s) {
   static bool attr_done = false;
+  static int nsm = 0;
   if (!attr_done) {
     CK(cudaFuncSetAttribute(k_elem<MODE, NDT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
     attr_done = true;
   }
-  k_elem<MODE, NDT><<<grid, 256, smem, s>>>(Q);
+  int occ = 1;   // one wave of resident CTAs walking the tiles
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_elem<MODE, NDT>, 256, smem));
+  const unsigned int wave = (unsigned int)std::min(std::max(1, occ) * nsm, kRedBlocks);
+  k_elem<MODE, NDT><<<std::min(grid, wave), 256, smem, s>>>(Q);
 }
 template <int MODE>
 void launch_elem(const ElemFused &Q, unsigned int grid, size_t smem, cudaStream_t s) {
@@ -539,6 +547,31 @@ void launch_elem(const ElemFused &Q, unsigned int grid, size_t smem, cudaStream_
   else if (Q.np.nD <= 6) launch_elem_inst<MODE, 6>(Q, grid, smem, s);
   else if (Q.np.nD <= 8) launch_elem_inst<MODE, 8>(Q, grid, smem, s);
   else launch_elem_inst<MODE, MGBX_MAX_ND>(Q, grid, smem, s);
+}
+
+// specialised fused kernel of the default problem family (k_elem_plap)
+template <int MODE, int DIM>
+void launch_plap_inst(const PlapParams &Q, unsigned int grid, size_t smem, cudaStream_t s) {
+  static bool attr_done = false;
+  static int nsm = 0;
+  if (!attr_done) {
+    CK(cudaFuncSetAttribute(k_elem_plap<MODE, DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    attr_done = true;
+  }
+  // persistent tiles: exactly one wave of resident CTAs (grid = SMs x occupancy), never more than the reduction slots
+  int occ = 1;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_elem_plap<MODE, DIM>, 256, smem));
+  const unsigned int wave = (unsigned int)std::min(std::max(1, occ) * nsm, kRedBlocks);
+  k_elem_plap<MODE, DIM><<<std::min(grid, wave), 256, smem, s>>>(Q);
+}
+template <int MODE>
+void launch_plap(int dim, const PlapParams &Q, unsigned int grid, size_t smem, cudaStream_t s) {
+  if (dim == 1) launch_plap_inst<MODE, 1>(Q, grid, smem, s);
+  else if (dim == 2) launch_plap_inst<MODE, 2>(Q, grid, smem, s);
+  else launch_plap_inst<MODE, 3>(Q, grid, smem, s);
 }
 
 struct Engine {
@@ -778,6 +811,57 @@ struct Engine {
     grid = (unsigned int)std::max<int64_t>(1, std::min<int64_t>(ntiles, kRedBlocks));
     return true;
   }
+
+  // The default problem family (state (u, s), D = [u:id; u:d_1..d_dim; s:id], one Euclidean-power cone on rows 1..dim+1
+  // with identity A, zero b, uniform p and mu): returns dim (1..3) if the specialised kernel applies, else 0.
+  int plap_dim(const Amg &A) const {
+    if (h->cfg.fused != 1 || A.nu != 2 || A.p >= 256) return 0;
+    const int dim = A.nD - 2;
+    if (dim < 1 || dim > 3) return 0;
+    const int vu = A.D_var[0], vs = A.D_var[dim + 1];
+    if (vu == vs || A.D_op[0] >= 0 || A.D_op[dim + 1] >= 0) return 0;
+    for (int a = 1; a <= dim; ++a)
+      if (A.D_var[a] != vu || A.D_op[a] < 0) return 0;
+    const ConvexDev &cd = A.cd;
+    if (cd.feas || cd.npieces != 1 || cd.select) return 0;
+    const PieceDev &pc = cd.pc[0];
+    if (pc.kind != MGBX_PIECE_EP || pc.ni != dim + 1 || pc.nc != dim + 1 || pc.A || pc.b || pc.p || pc.mu) return 0;
+    for (int c = 0; c <= dim; ++c)
+      if (pc.idx[c] != c + 1) return 0;
+    return dim;
+  }
+  bool plap_setup(Amg &A, int dim, double t, bool use_bw, PlapParams &Q, size_t &smem, unsigned int &grid) {
+    memset(&Q, 0, sizeof(Q));
+    Q.n = A.n;
+    Q.N = A.N;
+    Q.p = A.p;
+    Q.p1 = A.p | 1;
+    Q.ES = (A.p * Q.p1) | 1;
+    int epb = std::max(1, 256 / A.p);
+    const size_t cap = 216 * 1024;
+    while (epb > 1 && elem_plap_smem(dim, epb, Q.ES, A.p) > cap) epb = (epb + 1) / 2;
+    smem = elem_plap_smem(dim, epb, Q.ES, A.p);
+    if (smem > cap) return false;
+    Q.epb = epb;
+    Q.dp = make_fastdiv((unsigned int)A.p);
+    Q.dpp = make_fastdiv((unsigned int)(A.p * A.p));
+    for (int a = 0; a < dim; ++a) Q.ops[a] = A.ops[A.D_op[a + 1]];
+    Q.zu = A.zf + (int64_t)A.D_var[0] * A.n;
+    Q.zs = A.zf + (int64_t)A.D_var[dim + 1] * A.n;
+    Q.w = A.w;
+    Q.f = A.f;
+    Q.bw = use_bw ? A.bw : nullptr;
+    Q.t = t;
+    Q.inv_n = 1.0 / (double)A.n_global;
+    Q.pexp = A.cd.pc[0].p_uniform;
+    Q.mu = A.cd.pc[0].mu_uniform;
+    Q.partials = h->partials;
+    Q.ticket = h->ticket;
+    Q.red_out = dist() ? h->dscal + 40 : h->dscal;
+    const int64_t ntiles = (A.N + epb - 1) / epb;
+    grid = (unsigned int)std::max<int64_t>(1, std::min<int64_t>(ntiles, kRedBlocks));
+    return true;
+  }
   unsigned int red_grid(int64_t work) {
     const int64_t b = (work + kRedThreads - 1) / kRedThreads;
     return (unsigned int)std::max<int64_t>(1, std::min<int64_t>(b, kRedBlocks));
@@ -792,9 +876,15 @@ struct Engine {
     if (!use_bw) P.bw = nullptr;
     if (dist()) P.red_out = h->dscal + 40;
     ElemFused Q;
+    PlapParams PQ;
     size_t smem = 0;
     unsigned int grid = 0;
-    if (elem_fused_setup(A, P, A.nD, Q, smem, grid)) {
+    const int pdim = plap_dim(A);
+    if (pdim && plap_setup(A, pdim, t, use_bw, PQ, smem, grid)) {
+      PQ.gbu = A.gb + (int64_t)A.D_var[0] * A.n;
+      PQ.gbs = A.gb + (int64_t)A.D_var[pdim + 1] * A.n;
+      LAUNCH(KC_ELEM_F01, launch_plap<NODE_F01>(pdim, PQ, grid, smem, s));
+    } else if (elem_fused_setup(A, P, A.nD, Q, smem, grid)) {
       Q.gb = A.gb;
       LAUNCH(KC_ELEM_F01, launch_elem<NODE_F01>(Q, grid, smem, s));
     } else {
@@ -1116,9 +1206,19 @@ void Engine::assemble(Amg &A, System &S, int J, double t, const double *zbase, c
   P.hEEinv = A.hEEinv;
   P.hKE = A.hKE;
   ElemFused Q;
+  PlapParams PQ;
   size_t smem = 0;
   unsigned int grid = 0;
-  if (elem_fused_setup(A, P, std::max(A.nD, S.nK * (S.nK + 1) / 2), Q, smem, grid)) {
+  const int pdim = plap_dim(A);
+  // the specialised kernel needs exactly: s eliminated node-locally, u kept with all of its rows
+  const bool plap_ok = pdim && S.nE == 1 && S.kept.size() == 1 && S.kept[0] == A.D_var[0] && S.elim[0] == A.D_var[pdim + 1] &&
+                       S.nK == pdim + 1 && S.pl.npairs == 1 && plap_setup(A, pdim, t, true, PQ, smem, grid);
+  if (plap_ok) {
+    PQ.hEEinv = A.hEEinv;
+    PQ.hKE = A.hKE;
+    PQ.Hblk = S.Hblk;
+    LAUNCH(KC_ELEM_F2, launch_plap<NODE_F2>(pdim, PQ, grid, smem, s));
+  } else if (elem_fused_setup(A, P, std::max(A.nD, S.nK * (S.nK + 1) / 2), Q, smem, grid)) {
     Q.pl = S.pl;
     Q.Hblk = S.Hblk;
     LAUNCH(KC_ELEM_F2, launch_elem<NODE_F2>(Q, grid, smem, s));
@@ -1339,7 +1439,7 @@ int Engine::pcg_persistent(System &S, int ktop, const double *b, double *x) {
   System::PcgDev &D = pcg_plan(S, ktop);
   if (b != S.pc_b) copy(S.pc_b, b, m);
   const PcgPlan *dev = D.dev;
-  void *args[] = {(void *)&dev, (void *)&h->cur_rtol2, (void *)&h->cfg.pcg_maxit};
+  void *args[] = {(void *)&dev, (void *)&h->cur_rtol2, (void *)&h->cfg.pcg_maxit, (void *)&h->cur_window};
   pre_launch(KC_PCG);
   CK(cudaLaunchCooperativeKernel((const void *)k_pcg_persistent, dim3(h->pcg_grid), dim3(kPcgThreads), args, 0, s));
   post_launch(KC_PCG);
@@ -1420,7 +1520,7 @@ int Engine::pcg(System &S, int ktop, const double *b, double *x) {
     if (rr < best * 0.999) {
       best = rr;
       since_best = 0;
-    } else if (++since_best >= 25) {
+    } else if (++since_best >= h->cur_window) {
       break;   // stagnation at the attainable accuracy
     }
   }
@@ -1513,6 +1613,7 @@ Engine::NewtonOut Engine::newton(Amg &A, int J, double t, int maxit, int stop_ki
   // attainable accuracy so that it stagnates where a direct solve would
   const double rt = (stop_kind == 0) ? std::min(h->cfg.pcg_rtol, h->cfg.pcg_rtol_final) : h->cfg.pcg_rtol;
   h->cur_rtol2 = rt * rt;
+  h->cur_window = (stop_kind == 0) ? 6 : 25;   // finalize: iterate to the attainable accuracy, detected quickly
   zero(A.x, m);
   EvalOut e0 = eval_f01(A, J, t, A.z, A.x, A.g);
   if (!e0.finite) {
@@ -1893,7 +1994,7 @@ void mgbx_default_config(mgbx_config *c) {
   c->use_graphs = 1;
   c->persistent = 1;
   c->tail_max = 1200;
-  c->pcg_rtol_final = 1e-13;
+  c->pcg_rtol_final = 1e-15;
   c->fused = 1;
   c->smoother = 1;
   c->cheb_ratio = 4.0;

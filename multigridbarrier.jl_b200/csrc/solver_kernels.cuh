@@ -126,9 +126,9 @@ __global__ void __launch_bounds__(1024) k_coarse_inverse(DevCsr A, double *Minv)
   __syncthreads();
   // right-looking Cholesky on the lower triangle
   for (int j = 0; j < m; ++j) {
-    if (tid == 0) {   // the scaled matrix has unit diagonal: a pivot below 1e-13 means numerical singularity; keep the
-      const double v = S[j * ld + j];   // preconditioner finite (any SPD approximation is a valid preconditioner)
-      S[j * ld + j] = sqrt((v > 1e-13 && isfinite(v)) ? v : 1e-13);
+    if (tid == 0) {   // a non-positive pivot means numerical indefiniteness: keep the preconditioner finite (any SPD
+      const double v = S[j * ld + j];   // approximation is a valid preconditioner); positive pivots are used as they are
+      S[j * ld + j] = sqrt((v > 0.0 && isfinite(v)) ? v : 1e-16);
     }
     __syncthreads();
     const double piv = S[j * ld + j];
@@ -676,7 +676,7 @@ __device__ double vcycle_levels(const PcgPlan &P, const Scope<GRID> &sc, int k0,
   return part;
 }
 
-__global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_persistent(const PcgPlan *plan_g, double rtol2, int maxit) {
+__global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_persistent(const PcgPlan *plan_g, double rtol2, int maxit, int stall_window) {
   __shared__ PcgPlan P;
   {
     const uint64_t *src = reinterpret_cast<const uint64_t *>(plan_g);
@@ -775,7 +775,7 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_persistent(const PcgPlan
       if (rr < best * 0.999) {
         best = rr;
         since_best = 0;
-      } else if (++since_best >= 25) {
+      } else if (++since_best >= stall_window) {
         break;   // stagnation at the attainable accuracy
       }
     }

@@ -169,11 +169,15 @@ def _check_newton_counts(idv, iov):
     """Newton counts +-1 per barrier step (north-star gate).  The LAST column also holds the finalize pass
     (mgb.jl:76-80), a second Newton run whose only stop rule is floating-point stagnation
     (`stopping_exact`, newton.jl:187: ynext >= ymin && |gnext| >= 0.9 gmin at roundoff level): its length is a
-    roundoff random walk that differs between any two linear solvers (CHOLMOD vs SuperLU vs PCG), so that column
-    is held to +-1 for the t-step plus +-2 for the stagnation tail; the no-finalize runs pin +-1 everywhere."""
+    roundoff random walk: at t ~ 1e8 the objective is ~1e9 and the Armijo test compares differences of ~1e-8, i.e.
+    it is decided by the summation order of f0; when the full step is rejected by noise the search accepts s = 1/2
+    and |g| merely halves per iteration until it reaches its floor (observed: 1 iteration in the oracle, 3 with one
+    GPU kernel variant, 7 with another, all ending at the same z to 1e-12).  That column is therefore only held to
+    +-1 for the t-step plus the halving tail (<= log2 of the gradient's dynamic range, ~10); the no-finalize runs
+    pin +-1 on every barrier step, and z / objective parity is asserted separately."""
     d = np.abs(idv.sum(axis=0) - iov.sum(axis=0))
     assert np.max(d[:-1], initial=0) <= 1
-    assert d[-1] <= 3
+    assert d[-1] <= 11
 
 
 @pytest.mark.parametrize("L,p,cfg", [(5, 1.5, {}), (6, 1.0, {}), (6, 1.5, dict(dense_direct_max=64, coarse_max=32))])
@@ -201,6 +205,10 @@ def test_fem3d_midsize_matches_oracle():
     so = O.mgb_solve(prob)
     assert rel(sd["z"], so["z"]) < 1e-6
     _check_newton_counts(sd["SOL_main"]["its"], so["SOL_main"]["its"])
+    sd2 = solver.mgb_solve(prob, config=dict(dense_direct_max=64, coarse_max=32), finalize=False)
+    so2 = O.mgb_solve(prob, finalize=False)
+    assert np.max(np.abs(sd2["SOL_main"]["its"].sum(axis=0) - so2["SOL_main"]["its"].sum(axis=0))) <= 1
+    assert rel(sd2["z"], so2["z"]) < 1e-6
 
 
 # ------------------------------------------------------------------------------------------ persistent solve kernel
@@ -249,6 +257,38 @@ def test_persistent_pcg_uncondensed_and_coarse_levels():
             assert np.linalg.norm(Hm @ x - g) <= 1e-8 * np.linalg.norm(g)
     finally:
         h.close()
+
+
+# ------------------------------------------------------------------------------------------ element kernel variants
+@pytest.mark.parametrize("name", ["p1L4_p1.5", "q1L2_p1", "fem1d_p1", "p2L2_p1.5"])
+def test_element_kernel_variants_agree(name):
+    """fused=1 (specialised kernel of the default (u, s) Euclidean-power family), fused=2 (generic fused kernel) and
+    fused=0 (separate node / block kernels) evaluate the same f0, f1 and Newton direction."""
+    prob = {"p1L4_p1.5": lambda: P.assemble(H.amg(G.subdivide(G.fem2d_P1(), 4)), p=1.5),
+            "q1L2_p1": lambda: default_problem("fem3d_k1_L2", 1.0),
+            "fem1d_p1": lambda: default_problem("fem1d_5nodes", 1.0),
+            "p2L2_p1.5": lambda: default_problem("fem2d_P2_L2", 1.5)}[name]()
+    M = prob.M[0]
+    J = len(M.R_fine) - 1
+    m = M.R_fine[J].shape[1]
+    rng = np.random.default_rng(9)
+    s = 1e-3 * rng.normal(size=m)
+    rhs = rng.normal(size=m)
+    bw = O.barrier_weights(M.w)
+    res = []
+    for fused in (1, 2, 0):
+        h = native.Handle(prob, barrier_weights=bw, fused=fused)
+        try:
+            f0 = h.barrier_eval(0, J, 0.9, s, 0)
+            g = h.barrier_eval(0, J, 0.9, s, 1)
+            x, _ = h.solve_newton_system(0, J, 0.9, s, rhs)
+            res.append((f0, g, x))
+        finally:
+            h.close()
+    for f0, g, x in res[1:]:
+        assert abs(f0 - res[0][0]) <= 1e-13 * max(1.0, abs(res[0][0]))
+        assert rel(g, res[0][1]) < 1e-12
+        assert rel(x, res[0][2]) < 1e-8
 
 
 # ------------------------------------------------------------------------------------------ bench-size properties
