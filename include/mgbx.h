@@ -123,7 +123,7 @@ typedef struct {
   int32_t dense_direct_max;  /* Newton systems with <= this many unknowns: dense Cholesky (default 2048) */
   int32_t coarse_max;        /* V-cycle is cut at the first level with <= this many unknowns (default 128 = the maximum) */
   int32_t pcg_maxit;         /* default 400 */
-  double pcg_rtol;           /* relative residual, default 1e-11 */
+  double pcg_rtol;           /* relative residual, default 1e-9 (Newton counts and the t-schedule match the direct-solve oracle, tests) */
   int32_t smoother_sweeps;   /* pre = post smoothing sweeps (Chebyshev degree), default 2 */
   int32_t condense;          /* 1 (default): eliminate node-local :full variables exactly before PCG */
   int32_t device;            /* CUDA device ordinal, -1 = current */

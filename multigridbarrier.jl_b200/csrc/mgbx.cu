@@ -1985,7 +1985,7 @@ void mgbx_default_config(mgbx_config *c) {
   c->dense_direct_max = 2048;
   c->coarse_max = 128;
   c->pcg_maxit = 400;
-  c->pcg_rtol = 1e-11;
+  c->pcg_rtol = 1e-9;
   c->smoother_sweeps = 2;
   c->condense = 1;
   c->device = -1;

@@ -226,7 +226,7 @@ def test_persistent_pcg_matches_multilaunch_pcg(tail_max):
     g = rng.normal(size=m)
     out = []
     for persistent in (0, 1):
-        h = native.Handle(prob, dense_direct_max=0, coarse_max=40, persistent=persistent, tail_max=tail_max, smoother=0)
+        h = native.Handle(prob, dense_direct_max=0, coarse_max=40, persistent=persistent, tail_max=tail_max, smoother=0, pcg_rtol=1e-11)
         try:
             x, its = h.solve_newton_system(0, J, 2.0, s, g)
             Hm = h.hessian(0, J, 2.0, s)
@@ -246,7 +246,7 @@ def test_persistent_pcg_uncondensed_and_coarse_levels():
     M = prob.M[0]
     L = len(M.R_fine)
     rng = np.random.default_rng(4)
-    h = native.Handle(prob, dense_direct_max=0, coarse_max=20, condense=0)
+    h = native.Handle(prob, dense_direct_max=0, coarse_max=20, condense=0, pcg_rtol=1e-11)
     try:
         for J in (L - 1, L - 2, L - 3):
             m = M.R_fine[J].shape[1]
