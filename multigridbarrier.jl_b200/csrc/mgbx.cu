@@ -1648,11 +1648,70 @@ Engine::NewtonOut Engine::newton(Amg &A, int J, double t, int maxit, int stop_ki
       converged = std::fabs(inc) <= eps * std::max(std::fabs(y), 1.0);
       break;
     }
-    // backtracking line search (newton.jl:139-154 with the trial loop of :35-50)
     double sstep = 1.0;
     double yn = y, gnn = gnorm;
     bool have_trial = false;   // xbest/gbest hold the last finite trial
-    while (sstep > 0.0) {
+    // exact line search by Illinois root finding on phi(sigma) = F1(x - sigma n).n  (newton.jl:4-27,84-103)
+    while (o.line_search == 1 && sstep > 0.0) {
+      bool ok = true;
+      auto launch_trial = [&](double sigma) {
+        if (!dist()) LAUNCH(KC_VEC, k_trial<<<red_grid(m), kRedThreads, 0, s>>>(m, A.x, A.dir, sigma, A.xn, h->partials, h->ticket, h->dscal + 7));
+        else LAUNCH(KC_VEC, k_trial_seg<<<red_grid(m), kRedThreads, 0, s>>>(seglist(A, J), m, A.x, A.dir, sigma, A.xn, h->partials, h->ticket, h->dscal + 38));
+      };
+      auto phi = [&](double sigma) -> double {
+        launch_trial(sigma);
+        EvalOut e = eval_f01(A, J, t, A.z, A.xn, A.gn);
+        if (!std::isfinite(e.y)) {   // "line search: non-finite barrier value"
+          ok = false;
+          return NAN;
+        }
+        dot2_fetch(A, J, A.gn, A.dir);
+        if (!std::isfinite(h->hscal[4])) ok = false;   // @assert isfinite(fc)
+        return h->hscal[4];
+      };
+      double a = 0.0, b = sstep, fa = inc, fb = phi(b), sstar = b;
+      if (ok) {
+        if (fa == 0.0) sstar = a;
+        else if (fa * fb >= 0.0) sstar = b;
+        else {
+          bool found = false;
+          for (int kk = 0; kk < 10000 && ok; ++kk) {
+            const double c = (a * fb - b * fa) / (fb - fa);
+            const double fc = phi(c);
+            if (!ok) break;
+            if (c <= std::min(a, b) || c >= std::max(a, b) || fc * fa == 0.0 || fc * fb == 0.0) {
+              sstar = c;
+              found = true;
+              break;
+            }
+            if (fb * fc < 0.0) {
+              a = b;
+              fa = fb;
+            } else {
+              fa /= 2.0;
+            }
+            b = c;
+            fb = fc;
+          }
+          if (!found) ok = false;   // trial rejected (or "Illinois solver failed to converge")
+        }
+      }
+      if (ok) {
+        launch_trial(sstar);
+        EvalOut et = eval_f01(A, J, t, A.z, A.xn, A.gn);
+        if (et.finite) {
+          std::swap(A.xn, A.xbest);
+          std::swap(A.gn, A.gbest);
+          have_trial = true;
+          yn = et.y;
+          gnn = et.gnorm;
+          break;
+        }
+      }
+      sstep *= o.ls_beta;
+    }
+    // backtracking line search (newton.jl:139-154 with the trial loop of :35-50)
+    while (o.line_search == 0 && sstep > 0.0) {
       if (!dist()) LAUNCH(KC_VEC, k_trial<<<red_grid(m), kRedThreads, 0, s>>>(m, A.x, A.dir, sstep, A.xn, h->partials, h->ticket, h->dscal + 7));
       else LAUNCH(KC_VEC, k_trial_seg<<<red_grid(m), kRedThreads, 0, s>>>(seglist(A, J), m, A.x, A.dir, sstep, A.xn, h->partials, h->ticket, h->dscal + 38));
       EvalOut et = eval_f01(A, J, t, A.z, A.xn, A.gn);
@@ -2164,10 +2223,7 @@ int mgbx_step(mgbx_handle *h, int which, double t, const mgbx_step_opts *o, mgbx
   if (!h || !o || !r) return MGBX_ERR_ARG;
   const int rc = guarded(h, [&]() -> int {
     if (which < 0 || which > 1 || (which == 1 && !h->has_feas)) throw ArgError("mgbx_step: no such AMG");
-    if (o->line_search != 0) {
-      h->err = "line_search = illinois is not implemented yet";
-      return MGBX_ERR_UNSUPPORTED;
-    }
+    if (o->line_search != 0 && o->line_search != 1) throw ArgError("mgbx_step: line_search must be 0 (backtracking) or 1 (illinois)");
     Engine E(h);
     return E.step(which, t, *o, r);
   });

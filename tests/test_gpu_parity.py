@@ -211,6 +211,27 @@ def test_fem3d_midsize_matches_oracle():
     assert rel(sd2["z"], so2["z"]) < 1e-6
 
 
+def test_illinois_line_search_matches_oracle():
+    """linesearch_illinois (newton.jl:84-103): exact line search by Illinois root finding, device evaluations."""
+    prob = P.assemble(H.amg(G.subdivide(G.fem2d_P1(), 4)), p=1.5)
+    sd = solver.mgb_solve(prob, line_search=1)
+    so = O.mgb_solve(prob, line_search=O.linesearch_illinois())
+    assert rel(sd["z"], so["z"]) < 1e-6
+    assert sd["SOL_main"]["its"].shape == so["SOL_main"]["its"].shape
+    d = np.abs(sd["SOL_main"]["its"].sum(axis=0) - so["SOL_main"]["its"].sum(axis=0))
+    assert np.max(d[:-1], initial=0) <= 1
+
+
+def test_parabolic_midsize_matches_oracle():
+    """parabolic_solve (Parabolic.jl:126-173) on fem2d_P2 at level 4 (n = 896): 3 state variables, a piecewise intersection of
+    two Euclidean-power cones, phase I at every time step (feasibility AMG attached lazily), one handle reused across steps."""
+    mg = H.amg(G.subdivide(G.fem2d_P2(), 4))
+    sd = solver.parabolic_solve(mg, h=0.5, p=1.0)
+    so = O.parabolic_solve(mg, P.assemble, P.intersect, P.convex_Euclidian_power, H.prepare_amg, P.default_slack_space, h=0.5, p=1.0)
+    ud, uo = np.stack(sd["u"], axis=2), np.stack(so["u"], axis=2)
+    assert rel(ud, uo) < 1e-6
+
+
 # ------------------------------------------------------------------------------------------ persistent solve kernel
 @pytest.mark.parametrize("tail_max", [0, 300, 10 ** 9])
 def test_persistent_pcg_matches_multilaunch_pcg(tail_max):
