@@ -1,0 +1,105 @@
+// dense_kernels.cuh -- the spectral (dense) assembly path on the FP64 tensor cores.
+//
+// For spectral1d / spectral2d the "element" is the whole domain: the derivative operators are dense n x n Chebyshev
+// differentiation matrices (src/spectral1d.jl:63-109, src/spectral2d.jl:15-42) and R is a dense basis-evaluation
+// matrix, so  H = sum_jk D_j' diag(h_jk) D_k  and  R'HR  (src/convex.jl:181-202, src/BlockMatrices.jl:506-555 with one
+// p x p block) are true dense contractions.  They run here as FP64 DMMA GEMMs (mma.sync m8n8k4 f64, the only FP64
+// tensor-core path on sm_100a; tcgen05 has no FP64 kind).  One kernel form covers all three products:
+//     C[i*ldc + j] (+)= sum_k A[i*lda + k] * s[k] * B[j*ldb + k]          ("NT": both operands contiguous along k)
+//   (1) Hd[r][c]  += sum_q  D_j[q][r] h[q] D_k[q][c]     A = ops_j, B = ops_k (column-major n x n), s = h
+//   (2) Wt[j][r]   = sum_c  Rt_b[j][c] Hd[r][c]          A = Rt_b (m_b x n),  B = Hd
+//   (3) A_top[i][j] = sum_r Rt_a[i][r] Wt[j][r]          A = Rt_a (m_a x n),  B = Wt, C = a block of the m x m system
+#pragma once
+#include "kernels.cuh"
+
+namespace mgbx {
+
+constexpr int kGemmBM = 64, kGemmBN = 64, kGemmBK = 16, kGemmLd = kGemmBK + 4;
+
+__device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// 128 threads = 4 warps in a 2 x 2 arrangement; each warp owns a 32 x 32 sub-tile = 4 x 4 DMMA tiles.
+__global__ void __launch_bounds__(128) k_dgemm_nt(int M, int N, int K, const double *__restrict__ A, int64_t lda, const double *__restrict__ B,
+                                                   int64_t ldb, const double *__restrict__ s, double *C, int64_t ldc, int accumulate) {
+  __shared__ double As[kGemmBM][kGemmLd], Bs[kGemmBN][kGemmLd];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 1, wn = warp & 1;
+  const int i0 = blockIdx.y * kGemmBM, j0 = blockIdx.x * kGemmBN;
+  double acc[4][4][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+  const int lr = lane >> 2, lk = lane & 3;
+  for (int k0 = 0; k0 < K; k0 += kGemmBK) {
+    // stage 64 x 16 of A (scaled by s) and of B: thread t loads rows t/2 (+ 0), k-half t%2 (8 consecutive doubles)
+    {
+      const int row = tid >> 1, kh = (tid & 1) * 8;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int k = k0 + kh + q;
+        const bool kin = k < K;
+        const double sv = (kin && s) ? s[k] : 1.0;
+        As[row][kh + q] = (kin && i0 + row < M) ? A[(int64_t)(i0 + row) * lda + k] * sv : 0.0;
+        Bs[row][kh + q] = (kin && j0 + row < N) ? B[(int64_t)(j0 + row) * ldb + k] : 0.0;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k4 = 0; k4 < kGemmBK; k4 += 4) {
+      double af[4], bf[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) af[a] = As[wm * 32 + a * 8 + lr][k4 + lk];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) bf[b] = Bs[wn * 32 + b * 8 + lr][k4 + lk];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+    }
+    __syncthreads();
+  }
+  // C fragment: row = lane / 4, cols = 2 * (lane % 4) + {0, 1}
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int i = i0 + wm * 32 + a * 8 + lr;
+      const int j = j0 + wn * 32 + b * 8 + 2 * lk;
+      if (i < M) {
+        double *c = C + (int64_t)i * ldc + j;
+        if (j < N) c[0] = (accumulate ? c[0] : 0.0) + acc[a][b][0];
+        if (j + 1 < N) c[1] = (accumulate ? c[1] : 0.0) + acc[a][b][1];
+      }
+    }
+}
+
+// Hd[r][c] += (ident_j ? delta : D_j[.][r]) ... the three cheap cases of D_j' diag(h) D_k with an identity operand:
+//   mode 0: both identities          Hd[r][r] += h[r]
+//   mode 1: D_j = I, D_k = Dk        Hd[r][c] += h[r] * Dk[r][c]        (Dk column-major: Dk[c*n + r])
+//   mode 2: D_j = Dj, D_k = I        Hd[r][c] += Dj[c][r] * h[c]        (Dj[r*n + c])
+__global__ void __launch_bounds__(256) k_dense_hess_ident(int n, int mode, const double *__restrict__ h, const double *__restrict__ D, double *Hd) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (mode == 0) {
+    if (t < n) Hd[t * n + t] += h[t];
+    return;
+  }
+  if (t >= (int64_t)n * n) return;
+  const int r = (int)(t / n), c = (int)(t % n);
+  if (mode == 1) Hd[t] += h[r] * D[(int64_t)c * n + r];
+  else Hd[t] += D[(int64_t)r * n + c] * h[c];
+}
+
+// Rt[j][i] = R[i][cols j] for the row block [r0, r0+n) and column block [c0, c0+mv) of a CSR matrix (dense transposed copy)
+__global__ void k_csr_block_to_dense_t(DevCsr R, int64_t r0, int n, int64_t c0, int mv, double *Rt) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int64_t k = R.ptr[r0 + i]; k < R.ptr[r0 + i + 1]; ++k) {
+    const int64_t c = R.idx[k] - c0;
+    if (c >= 0 && c < mv) Rt[c * (int64_t)n + i] = R.val[k];
+  }
+}
+
+}  // namespace mgbx

@@ -28,6 +28,7 @@
 #include "kernels.cuh"
 #include "solver_kernels.cuh"
 #include "setup_kernels.cuh"
+#include "dense_kernels.cuh"
 
 using namespace mgbx;
 
@@ -43,9 +44,9 @@ static thread_local std::string g_last_error;
 
 // kernel classes for the optional per-class device timing (cfg.profile) and launch statistics
 enum KClass { KC_NODE_F01 = 0, KC_NODE_F2, KC_BLOCKGRAD, KC_BLOCKHESS, KC_GATHER, KC_SPMV, KC_JACOBI, KC_SPGEMM, KC_VEC, KC_COND,
-              KC_DENSE, KC_PCG, KC_ELEM_F01, KC_ELEM_F2, KC_COUNT };
+              KC_DENSE, KC_PCG, KC_ELEM_F01, KC_ELEM_F2, KC_DGEMM, KC_COUNT };
 static const char *kKClassNames[KC_COUNT] = {"node_f01", "node_f2", "blockgrad", "blockhess", "csr_gather", "spmv", "jacobi",
-                                             "spgemm", "vector", "condense", "dense", "pcg_persistent", "elem_f01", "elem_f2"};
+                                             "spgemm", "vector", "condense", "dense", "pcg_persistent", "elem_f01", "elem_f2", "dgemm_dmma"};
 enum { STAGE_F01 = -1, STAGE_F2 = -2, STAGE_SOLVE = -3 };
 #define LAUNCH(kc, ...)   \
   do {                    \
@@ -429,6 +430,10 @@ struct System {
   int64_t hblk_size = 0;
   int cut = -1;                      // V-cycle bottom (dense inverse) level index, -1: none
   bool dense_elements = false;       // spectral-type geometry (one dense "element"): small systems are solved directly
+  // dense assembly path (spectral): R'HR by FP64 DMMA GEMMs into the (full) top matrix; no gather plan, no hierarchy
+  bool dense = false;
+  std::vector<double *> Rt;          // per kept variable: transposed dense prolongation block (m_q x n)
+  double *Hd = nullptr, *Wt = nullptr;
   // PCG work at the largest size
   double *pc_r = nullptr, *pc_z = nullptr, *pc_p = nullptr, *pc_Ap = nullptr, *pc_x = nullptr, *pc_b = nullptr;
   std::map<int, cudaGraphExec_t> graphs;        // captured PCG iteration per top level (non-persistent path)
@@ -463,6 +468,7 @@ struct Amg {
   double *x = nullptr, *xn = nullptr, *g = nullptr, *gn = nullptr, *dir = nullptr, *rhs = nullptr, *tmp = nullptr, *xbest = nullptr,
          *gbest = nullptr;
   std::unique_ptr<System> sys_cond, sys_coarse, sys_hook;   // fine-level (condensed), levels < L-1, parity hooks
+  std::map<int, std::unique_ptr<System>> sys_dense;         // dense (spectral) discretisations: one directly assembled system per level
   double fb = 0.0, fR = 0.0;
   int64_t n_global = 0;              // nodes of the whole mesh (== n on a single rank)
   std::vector<char> var_local;       // per variable: node-local unknowns at the fine level (multi-GPU)
@@ -505,6 +511,7 @@ struct mgbx_handle {
   std::vector<Pending> ev_pending;
   cudaEvent_t ev_cur = nullptr;
   int pcg_grid = 0;
+  double dgemm_flops = 0.0;   // FP64 tensor-core flops issued so far (spectral path)
   double cur_rtol2 = 1e-22;
   int cur_window = 25;       // PCG stagnation window (iterations without a new best residual)
   // multi-GPU
@@ -931,6 +938,8 @@ struct Engine {
     return Lv.m <= kCoarseMaxDense || S.dense_elements || S.lev.size() == 1;
   }
   void assemble(Amg &A, System &S, int J, double t, const double *zbase, const double *x);
+  void assemble_dense(Amg &A, System &S, const NodeParams &P);
+  void dgemm_nt(int M, int N, int K, const double *Am, int64_t lda, const double *Bm, int64_t ldb, const double *sc, double *C, int64_t ldc, bool acc);
   void setup_hierarchy(Amg &A, System &S, int ktop);
   void dense_factor(System &S, SysLevel &Lv, bool want_inverse);
   void dense_apply(SysLevel &Lv, const double *b, double *x);      // x = A^{-1} b via factor (direct)
@@ -965,6 +974,9 @@ struct Engine {
 // Build the index plans of one linear-system family.  ltop: the AMG level the top matrix lives on.  The top
 // matrix is assembled directly from the element blocks with R_top = R_fine[ltop] (= R_fine[L-1] * T[L-2] ... T[ltop]),
 // every coarser level by Galerkin gather plans.
+// spectral discretisations: one dense "element" (N == 1) with more nodes than a finite element ever has
+inline bool dense_mode(const Amg &A) { return A.N == 1 && A.p > 64; }
+
 std::unique_ptr<System> build_system(mgbx_handle *h, Amg &A, bool condensed, int ltop) {
   auto S = std::make_unique<System>();
   Pool &pool = h->pool;
@@ -1044,6 +1056,59 @@ std::unique_ptr<System> build_system(mgbx_handle *h, Amg &A, bool condensed, int
     Lv.off.assign(1, 0);
     for (int v : S->kept) Lv.off.push_back(Lv.off.back() + (A.voff[l][v + 1] - A.voff[l][v]));
     Lv.m = Lv.off.back();
+  }
+  if (dense_mode(A)) {
+    // ---- dense (spectral) system: full m x m matrix assembled by GEMMs, solved directly; no plans, no hierarchy
+    S->dense = true;
+    S->lev.resize(1);
+    SysLevel &Lv = S->lev[0];
+    const int64_t m = Lv.m;
+    if (m > 4096) throw std::runtime_error("dense (spectral) Newton systems are limited to 4096 unknowns in this build");
+    HostCsr full;
+    full.rows = full.cols = m;
+    full.ptr.resize(m + 1);
+    full.idx.resize((size_t)m * m);
+    for (int64_t i = 0; i <= m; ++i) full.ptr[i] = i * m;
+    for (int64_t i = 0; i < m; ++i)
+      for (int64_t j = 0; j < m; ++j) full.idx[i * m + j] = (int32_t)j;
+    Lv.A = upload_csr(pool, full, s, false);
+    Lv.spmv_group = 32;
+    Lv.dinv = pool.alloc<double>(m);
+    Lv.diag = pool.alloc<double>(m);
+    Lv.lam = pool.zeros<double>(1, s);
+    Lv.b = pool.alloc<double>(m);
+    Lv.x = pool.alloc<double>(m);
+    Lv.x2 = pool.alloc<double>(m);
+    Lv.r = pool.alloc<double>(m);
+    TempCsr rt = upload_csr_temp(Rtop, s, true);
+    int64_t mvmax = 1;
+    for (size_t q = 0; q < S->kept.size(); ++q) {
+      const int v = S->kept[q];
+      const int64_t mv = Lv.off[q + 1] - Lv.off[q];
+      mvmax = std::max(mvmax, mv);
+      double *d = pool.zeros<double>((size_t)mv * A.n, s);
+      k_csr_block_to_dense_t<<<nblk(A.n), 256, 0, s>>>(rt.d, (int64_t)v * A.n, (int)A.n, A.voff[L - 1][v], (int)mv, d);
+      CK(cudaGetLastError());
+      S->Rt.push_back(d);
+    }
+    CK(cudaStreamSynchronize(s));
+    rt.free_all();
+    S->Hd = pool.alloc<double>((size_t)A.n * A.n);
+    S->Wt = pool.alloc<double>((size_t)mvmax * A.n);
+    S->cut = -1;
+    S->pc_r = pool.alloc<double>(m);
+    S->pc_z = pool.alloc<double>(m);
+    S->pc_p = pool.alloc<double>(m);
+    S->pc_p2 = pool.alloc<double>(m);
+    S->pc_Ap = pool.alloc<double>(m);
+    S->pc_x = pool.alloc<double>(m);
+    S->pc_b = pool.alloc<double>(m);
+    S->pcg_partials = pool.zeros<double>(3 * (size_t)kPcgMaxGrid, s);
+    S->pcg_out = pool.zeros<double>(8, s);
+    S->pcg_bar = pool.zeros<unsigned int>(4, s);
+    CK(cudaStreamSynchronize(s));
+    if (h->cfg.verbose > 0) fprintf(stderr, "[mgbx] build_system(dense, level %d): m=%lld, n=%lld\n", ltop, (long long)m, (long long)A.n);
+    return S;
   }
   // top pattern = reference plan pattern restricted to the kept variables
   const int64_t mtop = S->lev[0].m;
@@ -1176,6 +1241,11 @@ std::unique_ptr<System> build_system(mgbx_handle *h, Amg &A, bool condensed, int
 }
 
 System &Engine::system_for(Amg &A, int J) {
+  if (dense_mode(A)) {
+    auto &p = A.sys_dense[J];
+    if (!p) p = build_system(h, A, false, J);
+    return *p;
+  }
   const bool fine = (J == A.L - 1);
   if (fine) {
     if (h->cfg.condense) {
@@ -1205,6 +1275,12 @@ void Engine::assemble(Amg &A, System &S, int J, double t, const double *zbase, c
   P.Hn = A.Hn;
   P.hEEinv = A.hEEinv;
   P.hKE = A.hKE;
+  if (S.dense) {
+    assemble_dense(A, S, P);
+    stage_end(STAGE_F2, st);
+    if (h->res) h->res->f2_evals++;
+    return;
+  }
   ElemFused Q;
   PlapParams PQ;
   size_t smem = 0;
@@ -1236,6 +1312,52 @@ void Engine::assemble(Amg &A, System &S, int J, double t, const double *zbase, c
   setup_hierarchy(A, S, ktop);
   stage_end(STAGE_F2, st);
   if (h->res) h->res->f2_evals++;
+}
+
+
+void Engine::dgemm_nt(int M, int N, int K, const double *Am, int64_t lda, const double *Bm, int64_t ldb, const double *sc, double *C, int64_t ldc,
+                      bool acc) {
+  if (M <= 0 || N <= 0) return;
+  dim3 grid((N + kGemmBN - 1) / kGemmBN, (M + kGemmBM - 1) / kGemmBM);
+  LAUNCH(KC_DGEMM, k_dgemm_nt<<<grid, 128, 0, s>>>(M, N, K, Am, lda, Bm, ldb, sc, C, ldc, acc ? 1 : 0));
+  h->dgemm_flops += 2.0 * M * (double)N * K;
+}
+
+// Dense (spectral) assembly: per pair of state variables  Hd = sum_jk D_j' diag(h_jk) D_k  (n x n),  then
+// A_top[a-block, b-block] = R_a' Hd R_b  by two GEMMs, written straight into the full row-major top matrix.
+void Engine::assemble_dense(Amg &A, System &S, const NodeParams &P) {
+  LAUNCH(KC_NODE_F2, launch_node<NODE_F2>(P, red_grid(A.n), s));
+  SysLevel &top = S.lev[0];
+  const int64_t m = top.m;
+  const int n = (int)A.n, nK = S.nK;
+  zero(top.A.val, m * m);
+  for (size_t qa = 0; qa < S.kept.size(); ++qa)
+    for (size_t qb = 0; qb < S.kept.size(); ++qb) {
+      const int va = S.kept[qa], vb = S.kept[qb];
+      bool any = false;
+      zero(S.Hd, (int64_t)n * n);
+      for (int ja = 0; ja < nK; ++ja) {
+        const int j = S.Krow[ja];
+        if (A.D_var[j] != va) continue;
+        for (int kb = 0; kb < nK; ++kb) {
+          const int k = S.Krow[kb];
+          if (A.D_var[k] != vb) continue;
+          any = true;
+          const int a = std::min(ja, kb), b = std::max(ja, kb);
+          const double *hv = A.Hn + (int64_t)(a * nK - (a * (a - 1)) / 2 + (b - a)) * A.n;
+          const int oj = A.D_op[j], ok = A.D_op[k];
+          if (oj < 0 && ok < 0) LAUNCH(KC_DENSE, k_dense_hess_ident<<<nblk(n), 256, 0, s>>>(n, 0, hv, nullptr, S.Hd));
+          else if (oj < 0) LAUNCH(KC_DENSE, k_dense_hess_ident<<<nblk((int64_t)n * n), 256, 0, s>>>(n, 1, hv, A.ops[ok], S.Hd));
+          else if (ok < 0) LAUNCH(KC_DENSE, k_dense_hess_ident<<<nblk((int64_t)n * n), 256, 0, s>>>(n, 2, hv, A.ops[oj], S.Hd));
+          else dgemm_nt(n, n, n, A.ops[oj], n, A.ops[ok], n, hv, S.Hd, n, true);
+        }
+      }
+      if (!any) continue;
+      const int ma = (int)(top.off[qa + 1] - top.off[qa]), mb = (int)(top.off[qb + 1] - top.off[qb]);
+      dgemm_nt(mb, n, n, S.Rt[qb], n, S.Hd, n, nullptr, S.Wt, n, false);                                   // Wt = (Hd R_b)'
+      dgemm_nt(ma, mb, n, S.Rt[qa], n, S.Wt, n, nullptr, top.A.val + top.off[qa] * m + top.off[qb], m, false);   // R_a' Hd R_b
+    }
+  setup_hierarchy(A, S, 0);
 }
 
 void Engine::setup_hierarchy(Amg &A, System &S, int ktop) {
@@ -2451,8 +2573,9 @@ int mgbx_hessian_pattern(mgbx_handle *h, int which, int level, int64_t *nnz, int
     if (which < 0 || which > 1 || (which == 1 && !h->has_feas)) throw ArgError("no such AMG");
     Amg &A = h->amg[which];
     if (level < 0 || level >= A.L) throw ArgError("no such level");
-    if (!A.sys_hook) A.sys_hook = build_system(h, A, false, A.L - 1);
-    SysLevel &Lv = A.sys_hook->lev[A.L - 1 - level];
+    Engine E(h);
+    if (!dense_mode(A) && !A.sys_hook) A.sys_hook = build_system(h, A, false, A.L - 1);
+    SysLevel &Lv = dense_mode(A) ? E.system_for(A, level).lev[0] : A.sys_hook->lev[A.L - 1 - level];
     *nnz = Lv.A.nnz;
     if (rowptr) CK(cudaMemcpy(rowptr, Lv.A.ptr, sizeof(int64_t) * (Lv.m + 1), cudaMemcpyDeviceToHost));
     if (colind) {
@@ -2471,6 +2594,14 @@ int mgbx_hessian_values(mgbx_handle *h, int which, int level, double t, const do
     Amg &A = h->amg[which];
     if (level < 0 || level >= A.L) throw ArgError("no such level");
     Engine E(h);
+    if (dense_mode(A)) {   // dense (spectral) systems are assembled directly at the requested level
+      System &S = E.system_for(A, level);
+      CK(cudaMemcpyAsync(A.xn, s, sizeof(double) * A.m[level], cudaMemcpyHostToDevice, h->stream));
+      E.assemble(A, S, level, t, A.z, A.xn);
+      CK(cudaMemcpyAsync(val, S.lev[0].A.val, sizeof(double) * S.lev[0].A.nnz, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      return MGBX_OK;
+    }
     if (!A.sys_hook) A.sys_hook = build_system(h, A, false, A.L - 1);
     System &S = *A.sys_hook;
     CK(cudaMemcpyAsync(A.xn, s, sizeof(double) * A.m[level], cudaMemcpyHostToDevice, h->stream));

@@ -312,6 +312,41 @@ def test_element_kernel_variants_agree(name):
         assert rel(x, res[0][2]) < 1e-8
 
 
+# ------------------------------------------------------------------------------------------ spectral (dense) path
+@pytest.mark.parametrize("name,geom", [("spectral2d_n9", lambda: G.spectral2d(n=9)), ("spectral2d_n16", lambda: G.spectral2d(n=16)),
+                                       ("spectral1d_n96", lambda: G.spectral1d(n=96))])
+def test_spectral_dense_path_matches_oracle(name, geom):
+    """Spectral discretisations with more than 64 nodes take the dense path: per-node Hessian samples, then
+    H = sum D_j' diag(h) D_k and R'HR as FP64 DMMA GEMMs into a full matrix, dense Cholesky solve."""
+    prob = P.assemble(H.amg(geom()), p=1.0)
+    M = prob.M[0]
+    t = 0.7
+    rng = np.random.default_rng(2)
+    h = native.Handle(prob, barrier_weights=O.barrier_weights(M.w))
+    try:
+        B = O.Barrier(prob.Q, O.barrier_weights(M.w))
+        ops = O.operators(M)
+        z0 = prob.g.T.reshape(-1).copy()
+        for J in (len(M.R_fine) - 1, len(M.R_fine) - 2):
+            R = M.R_fine[J]
+            s = 1e-3 * rng.normal(size=R.shape[1])
+            H_o = np.asarray(sp.csr_matrix(B.f2(s, M.w, t * prob.f, R, ops, z0)).todense())
+            g_o = B.f1(s, M.w, t * prob.f, R, ops, z0)
+            assert rel(h.barrier_eval(0, J, t, s, 1), g_o) < 1e-10
+            H_d = np.asarray(h.hessian(0, J, t, s).todense())
+            assert np.abs(H_d - H_o).max() <= 1e-10 * np.abs(H_o).max()
+            x_d, _ = h.solve_newton_system(0, J, t, s, g_o)
+            assert np.linalg.norm(H_o @ x_d - g_o) <= 1e-7 * np.linalg.norm(g_o)
+    finally:
+        h.close()
+    sd = solver.mgb_solve(prob)
+    so = O.mgb_solve(prob)
+    assert rel(sd["z"], so["z"]) < 1e-6
+    assert sd["SOL_main"]["its"].shape == so["SOL_main"]["its"].shape
+    d = np.abs(sd["SOL_main"]["its"].sum(axis=0) - so["SOL_main"]["its"].sum(axis=0))
+    assert np.max(d[:-1], initial=0) <= 1
+
+
 # ------------------------------------------------------------------------------------------ bench-size properties
 @pytest.fixture(scope="module")
 def big_problem():
