@@ -5,7 +5,7 @@
 // matrix, so  H = sum_jk D_j' diag(h_jk) D_k  and  R'HR  (src/convex.jl:181-202, src/BlockMatrices.jl:506-555 with one
 // p x p block) are true dense contractions.  They run here as FP64 DMMA GEMMs (mma.sync m8n8k4 f64, the only FP64
 // tensor-core path on sm_100a; tcgen05 has no FP64 kind).  One kernel form covers all three products:
-//     C[i*ldc + j] (+)= sum_k A[i*lda + k] * s[k] * B[j*ldb + k]          ("NT": both operands contiguous along k)
+//     C[i*ldc + j] (+)= alpha * sum_k A[i*lda + k] * s[k] * B[j*ldb + k]  ("NT": both operands contiguous along k)
 //   (1) Hd[r][c]  += sum_q  D_j[q][r] h[q] D_k[q][c]     A = ops_j, B = ops_k (column-major n x n), s = h
 //   (2) Wt[j][r]   = sum_c  Rt_b[j][c] Hd[r][c]          A = Rt_b (m_b x n),  B = Hd
 //   (3) A_top[i][j] = sum_r Rt_a[i][r] Wt[j][r]          A = Rt_a (m_a x n),  B = Wt, C = a block of the m x m system
@@ -22,7 +22,7 @@ __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, do
 
 // 128 threads = 4 warps in a 2 x 2 arrangement; each warp owns a 32 x 32 sub-tile = 4 x 4 DMMA tiles.
 __global__ void __launch_bounds__(128) k_dgemm_nt(int M, int N, int K, const double *__restrict__ A, int64_t lda, const double *__restrict__ B,
-                                                   int64_t ldb, const double *__restrict__ s, double *C, int64_t ldc, int accumulate) {
+                                                   int64_t ldb, const double *__restrict__ s, double *C, int64_t ldc, int accumulate, double alpha) {
   __shared__ double As[kGemmBM][kGemmLd], Bs[kGemmBN][kGemmLd];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 1, wn = warp & 1;
@@ -70,10 +70,116 @@ __global__ void __launch_bounds__(128) k_dgemm_nt(int M, int N, int K, const dou
       const int j = j0 + wn * 32 + b * 8 + 2 * lk;
       if (i < M) {
         double *c = C + (int64_t)i * ldc + j;
-        if (j < N) c[0] = (accumulate ? c[0] : 0.0) + acc[a][b][0];
-        if (j + 1 < N) c[1] = (accumulate ? c[1] : 0.0) + acc[a][b][1];
+        if (j < N) c[0] = (accumulate ? c[0] : 0.0) + alpha * acc[a][b][0];
+        if (j + 1 < N) c[1] = (accumulate ? c[1] : 0.0) + alpha * acc[a][b][1];
       }
     }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Blocked dense Cholesky (row-major, lower) with panel width 64; the panel solve and the trailing update are
+// DMMA GEMMs (k_dgemm_nt):   L21 = A21 * inv(L11)'   and   A22 -= L21 * L21'.
+// ------------------------------------------------------------------------------------------------
+constexpr int kCholNB = 64;
+constexpr size_t kCholDiagSmem = sizeof(double) * 2 * kCholNB * (kCholNB + 1);
+
+// factor the nb x nb diagonal block at (k0, k0) in shared memory, write L11 back and inv(L11) (row-major, ld 64) to Linv
+__global__ void __launch_bounds__(1024) k_chol_diag_inv(double *A, int m, int k0, double *Linv) {
+  extern __shared__ double chol_sm[];   // 2 x 64 x 65 doubles (dynamic: above the 48 KB static limit)
+  double (*L)[kCholNB + 1] = reinterpret_cast<double (*)[kCholNB + 1]>(chol_sm);
+  double (*Li)[kCholNB + 1] = reinterpret_cast<double (*)[kCholNB + 1]>(chol_sm + kCholNB * (kCholNB + 1));
+  const int nb = min(kCholNB, m - k0);
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int t = tid; t < kCholNB * kCholNB; t += nt) {
+    const int i = t / kCholNB, j = t % kCholNB;
+    L[i][j] = (i < nb && j <= i) ? A[(size_t)(k0 + i) * m + k0 + j] : 0.0;
+    Li[i][j] = 0.0;
+  }
+  __syncthreads();
+  for (int j = 0; j < nb; ++j) {
+    if (tid == 0) L[j][j] = sqrt(L[j][j]);
+    __syncthreads();
+    const double pv = L[j][j];
+    for (int i = j + 1 + tid; i < nb; i += nt) L[i][j] /= pv;
+    __syncthreads();
+    const int rem = nb - j - 1;
+    for (int t = tid; t < rem * rem; t += nt) {
+      const int i = j + 1 + t / rem, k = j + 1 + t % rem;
+      if (k <= i) L[i][k] -= L[i][j] * L[k][j];
+    }
+    __syncthreads();
+  }
+  // inverse of the triangular block, one warp per column
+  const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+  for (int c = wid; c < nb; c += nw) {
+    if (lane == 0) Li[c][c] = 1.0 / L[c][c];
+    __syncwarp();
+    for (int i = c + 1; i < nb; ++i) {
+      double sacc = 0.0;
+      for (int k = c + lane; k < i; k += 32) sacc += L[i][k] * Li[k][c];
+      sacc = warp_sum(sacc);
+      if (lane == 0) Li[i][c] = -sacc / L[i][i];
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int t = tid; t < kCholNB * kCholNB; t += nt) {
+    const int i = t / kCholNB, j = t % kCholNB;
+    if (i < nb && j <= i) A[(size_t)(k0 + i) * m + k0 + j] = L[i][j];
+    Linv[t] = (i < nb && j < nb) ? Li[i][j] : 0.0;
+  }
+}
+
+// x = (L L')^{-1} (d .* b) .* d for ONE right-hand side with the blocked factor and the panel inverses (Linv: panels x 64 x 64).
+// One CTA walks the panels (the dependency is sequential anyway): y_blk = inv(L11) b_blk, then b_rest -= L21 y_blk; and back.
+__global__ void __launch_bounds__(1024) k_chol_solve_blocked(const double *__restrict__ A, int m, const double *__restrict__ Linv,
+                                                              const double *__restrict__ d, const double *__restrict__ b, double *x) {
+  extern __shared__ double v[];   // m
+  __shared__ double blk[kCholNB];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i < m; i += nt) v[i] = b[i] * d[i];
+  __syncthreads();
+  const int npan = (m + kCholNB - 1) / kCholNB;
+  for (int pnl = 0; pnl < npan; ++pnl) {
+    const int k0 = pnl * kCholNB, nb = min(kCholNB, m - k0);
+    const double *Li = Linv + (size_t)pnl * kCholNB * kCholNB;
+    if (tid < nb) {
+      double sacc = 0.0;
+      for (int j = 0; j <= tid; ++j) sacc += Li[tid * kCholNB + j] * v[k0 + j];
+      blk[tid] = sacc;
+    }
+    __syncthreads();
+    if (tid < nb) v[k0 + tid] = blk[tid];
+    for (int i = k0 + nb + tid; i < m; i += nt) {
+      const double *row = A + (size_t)i * m + k0;
+      double sacc = 0.0;
+      for (int j = 0; j < nb; ++j) sacc += row[j] * blk[j];
+      v[i] -= sacc;
+    }
+    __syncthreads();
+  }
+  for (int pnl = npan - 1; pnl >= 0; --pnl) {
+    const int k0 = pnl * kCholNB, nb = min(kCholNB, m - k0);
+    const double *Li = Linv + (size_t)pnl * kCholNB * kCholNB;
+    // y_blk[j] -= sum_{i >= k0+nb} L[i][k0+j] x[i]   (column sums: warp per j, lanes over rows)
+    const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+    for (int j = wid; j < nb; j += nw) {
+      double sacc = 0.0;
+      for (int i = k0 + nb + lane; i < m; i += 32) sacc += A[(size_t)i * m + k0 + j] * v[i];
+      sacc = warp_sum(sacc);
+      if (lane == 0) blk[j] = v[k0 + j] - sacc;
+    }
+    __syncthreads();
+    // x_blk = inv(L11)' y_blk
+    if (tid < nb) {
+      double sacc = 0.0;
+      for (int i = tid; i < nb; ++i) sacc += Li[i * kCholNB + tid] * blk[i];
+      v[k0 + tid] = sacc;
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < m; i += nt) x[i] = v[i] * d[i];
 }
 
 // Hd[r][c] += (ident_j ? delta : D_j[.][r]) ... the three cheap cases of D_j' diag(h) D_k with an identity operand:

@@ -179,43 +179,6 @@ DevCsr upload_csr(Pool &pool, const HostCsr &H, cudaStream_t s, bool with_values
 }
 
 
-// Host term lists (CSR-like: ptr over outputs, 64-bit sources, optional weights) -> sliced-ELL on the device.
-SellPlan upload_sell(Pool &pool, const std::vector<int64_t> &ptr, const std::vector<int64_t> &src, const std::vector<double> *w,
-                     cudaStream_t s) {
-  SellPlan P;
-  P.nout = (int64_t)ptr.size() - 1;
-  P.nslices = (P.nout + 31) / 32;
-  P.nterms = ptr.back();
-  std::vector<int64_t> sptr(P.nslices + 1, 0);
-  std::vector<int32_t> cnt(P.nout);
-  for (int64_t sl = 0; sl < P.nslices; ++sl) {
-    int64_t wmax = 0;
-    for (int64_t nz = sl * 32; nz < std::min(P.nout, sl * 32 + 32); ++nz) {
-      cnt[nz] = (int32_t)(ptr[nz + 1] - ptr[nz]);
-      wmax = std::max<int64_t>(wmax, cnt[nz]);
-    }
-    sptr[sl + 1] = sptr[sl] + 32 * wmax;
-  }
-  const int64_t total = sptr[P.nslices];
-  std::vector<int32_t> hs(total, 0);
-  std::vector<double> hw(w ? total : 0, 0.0);
-  for (int64_t nz = 0; nz < P.nout; ++nz) {
-    const int64_t off = sptr[nz >> 5] + (nz & 31);
-    for (int64_t k = ptr[nz]; k < ptr[nz + 1]; ++k) {
-      if (src[k] > INT32_MAX) throw std::runtime_error("gather plan: source index exceeds 32 bits");
-      hs[off + 32 * (k - ptr[nz])] = (int32_t)src[k];
-      if (w) hw[off + 32 * (k - ptr[nz])] = (*w)[k];
-    }
-  }
-  P.sptr = pool.upload<int64_t>(sptr.data(), sptr.size(), s);
-  P.cnt = pool.upload<int32_t>(cnt.data(), cnt.size(), s);
-  P.src = pool.upload<int32_t>(hs.data(), hs.size(), s);
-  P.w = w ? pool.upload<double>(hw.data(), hw.size(), s) : nullptr;
-  CK(cudaStreamSynchronize(s));
-  return P;
-}
-
-
 // temporary device CSR (plan construction only), freed explicitly
 struct TempCsr {
   DevCsr d;
@@ -939,7 +902,7 @@ struct Engine {
   }
   void assemble(Amg &A, System &S, int J, double t, const double *zbase, const double *x);
   void assemble_dense(Amg &A, System &S, const NodeParams &P);
-  void dgemm_nt(int M, int N, int K, const double *Am, int64_t lda, const double *Bm, int64_t ldb, const double *sc, double *C, int64_t ldc, bool acc);
+  void dgemm_nt(int M, int N, int K, const double *Am, int64_t lda, const double *Bm, int64_t ldb, const double *sc, double *C, int64_t ldc, bool acc, double alpha = 1.0);
   void setup_hierarchy(Amg &A, System &S, int ktop);
   void dense_factor(System &S, SysLevel &Lv, bool want_inverse);
   void dense_apply(SysLevel &Lv, const double *b, double *x);      // x = A^{-1} b via factor (direct)
@@ -1316,10 +1279,10 @@ void Engine::assemble(Amg &A, System &S, int J, double t, const double *zbase, c
 
 
 void Engine::dgemm_nt(int M, int N, int K, const double *Am, int64_t lda, const double *Bm, int64_t ldb, const double *sc, double *C, int64_t ldc,
-                      bool acc) {
+                      bool acc, double alpha) {
   if (M <= 0 || N <= 0) return;
   dim3 grid((N + kGemmBN - 1) / kGemmBN, (M + kGemmBM - 1) / kGemmBM);
-  LAUNCH(KC_DGEMM, k_dgemm_nt<<<grid, 128, 0, s>>>(M, N, K, Am, lda, Bm, ldb, sc, C, ldc, acc ? 1 : 0));
+  LAUNCH(KC_DGEMM, k_dgemm_nt<<<grid, 128, 0, s>>>(M, N, K, Am, lda, Bm, ldb, sc, C, ldc, acc ? 1 : 0, alpha));
   h->dgemm_flops += 2.0 * M * (double)N * K;
 }
 
@@ -1392,34 +1355,36 @@ void Engine::setup_hierarchy(Amg &A, System &S, int ktop) {
 }
 
 void Engine::dense_factor(System &S, SysLevel &Lv, bool want_inverse) {
+  (void)S;
+  (void)want_inverse;
   const int m = (int)Lv.m;
   if (m == 0) return;
+  const int npan = (m + kCholNB - 1) / kCholNB;
   if (!Lv.dense) {
     Lv.dense = h->pool.alloc<double>((size_t)m * m);
     Lv.dscale = h->pool.alloc<double>(m);
+    Lv.dense_inv = h->pool.alloc<double>((size_t)npan * kCholNB * kCholNB);   // inverses of the diagonal blocks
   }
   zero(Lv.dense, (int64_t)m * m);
   LAUNCH(KC_DENSE, k_dense_scale_diag<<<nblk(m), 256, 0, s>>>(Lv.A, Lv.dscale));
   LAUNCH(KC_DENSE, k_csr_to_dense<<<nblk(m), 256, 0, s>>>(Lv.A, Lv.dscale, Lv.dense));
-  for (int k0 = 0; k0 < m; k0 += NB) {
-    LAUNCH(KC_DENSE, k_chol_diag<<<1, 256, 0, s>>>(Lv.dense, m, k0));
-    const int nb = std::min(NB, m - k0);
-    const int rem = m - k0 - nb;
+  // blocked right-looking Cholesky, panel width 64: diagonal block in shared memory, panel and trailing update as DMMA GEMMs
+  for (int p = 0; p < npan; ++p) {
+    const int k0 = p * kCholNB, nb = std::min(kCholNB, m - k0), rem = m - k0 - nb;
+    double *Li = Lv.dense_inv + (size_t)p * kCholNB * kCholNB;
+    LAUNCH(KC_DENSE, k_chol_diag_inv<<<1, 1024, kCholDiagSmem, s>>>(Lv.dense, m, k0, Li));
     if (rem > 0) {
-      LAUNCH(KC_DENSE, k_chol_trsm<<<nblk(rem, 64), 64, 0, s>>>(Lv.dense, m, k0));
-      const int nt = (rem + NB - 1) / NB;
-      LAUNCH(KC_DENSE, k_chol_syrk<<<nt * (nt + 1) / 2, 256, 0, s>>>(Lv.dense, m, k0));
+      double *A21 = Lv.dense + (size_t)(k0 + nb) * m + k0;
+      dgemm_nt(rem, nb, nb, A21, m, Li, kCholNB, nullptr, A21, m, false);                                   // L21 = A21 inv(L11)' (in place: one tile column)
+      dgemm_nt(rem, rem, nb, A21, m, A21, m, nullptr, Lv.dense + (size_t)(k0 + nb) * m + k0 + nb, m, true, -1.0);   // A22 -= L21 L21'
     }
   }
-  (void)want_inverse;
 }
 
 // x = A^{-1} b through the scaled Cholesky factor (one right-hand side), uses Lv.r as scratch
 void Engine::dense_apply(SysLevel &Lv, const double *b, double *x) {
   const int m = (int)Lv.m;
-  LAUNCH(KC_VEC, k_mul<<<nblk(m), 256, 0, s>>>(m, b, Lv.dscale, x));
-  LAUNCH(KC_DENSE, k_chol_solve<<<1, 256, sizeof(double) * m, s>>>(Lv.dense, m, x, 0));
-  LAUNCH(KC_VEC, k_mul<<<nblk(m), 256, 0, s>>>(m, x, Lv.dscale, x));
+  LAUNCH(KC_DENSE, k_chol_solve_blocked<<<1, 1024, sizeof(double) * m, s>>>(Lv.dense, m, Lv.dense_inv, Lv.dscale, b, x));
 }
 
 void Engine::vcycle(System &S, int k) {
@@ -2241,6 +2206,7 @@ int mgbx_create(const mgbx_problem *prob, const mgbx_config *cfg, mgbx_handle **
       h->pcg_grid = std::min(nsm, kPcgMaxGrid);   // one CTA per SM
       CK(cudaFuncSetAttribute(k_coarse_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coarse_inverse_smem(kCoarseMaxDense)));
       CK(cudaFuncSetAttribute(k_dense_solve_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dense_solve_small_smem(kCoarseMaxDense)));
+      CK(cudaFuncSetAttribute(k_chol_diag_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCholDiagSmem));
     }
     CK(cudaEventCreate(&h->ev0));
     CK(cudaEventCreate(&h->ev1));
@@ -2496,9 +2462,10 @@ int mgbx_solver_info(mgbx_handle *h, int which, mgbx_solver_info_t *out) {
   if (!h || !out || which < 0 || which > 1) return MGBX_ERR_ARG;
   return guarded(h, [&]() -> int {
     memset(out, 0, sizeof(*out));
+    out->dgemm_flops = h->dgemm_flops;
     Amg &A = h->amg[which];
     System *S = h->cfg.condense ? A.sys_cond.get() : A.sys_hook.get();
-    if (!S) return MGBX_OK;   // no fine-level system built yet
+    if (!S) return MGBX_OK;   // no fine-level (sparse) system built yet
     out->condensed = S->condensed ? 1 : 0;
     out->assembly_terms = S->top.nterms;
     out->hblk_entries = S->hblk_size;
