@@ -167,50 +167,6 @@ inline int64_t find_in_row(const HostCsr &A, int64_t row, int32_t col) {
   return (int64_t)(it - A.idx.data());
 }
 
-// Gather plan of a sparse product into a fixed pattern C (sorted columns):
-//   variable_left  = true : C = V * W with V's values changing (device), W constant -> entry (nz of V, value of W)
-//   variable_left  = false: C = W * V                                             -> entry (nz of V, value of W)
-// For every nz of C the list of (source nz, weight) pairs, in a fixed order (deterministic numerics).
-struct GatherPlan {
-  std::vector<int64_t> ptr;    // nnz(C) + 1
-  std::vector<int64_t> src;
-  std::vector<double> w;
-};
-
-inline GatherPlan product_plan(const HostCsr &Lm, const HostCsr &Rm, const HostCsr &C, bool variable_left) {
-  GatherPlan G;
-  const int64_t nnzC = C.nnz();
-  G.ptr.assign(nnzC + 1, 0);
-  std::vector<int64_t> posmap(C.cols, -1);
-  for (int pass = 0; pass < 2; ++pass) {
-    std::vector<int64_t> fill;
-    if (pass == 1) {
-      for (int64_t k = 0; k < nnzC; ++k) G.ptr[k + 1] += G.ptr[k];
-      G.src.resize(G.ptr[nnzC]);
-      G.w.resize(G.ptr[nnzC]);
-      fill.assign(G.ptr.begin(), G.ptr.end() - 1);
-    }
-    for (int64_t i = 0; i < C.rows; ++i) {
-      for (int64_t k = C.ptr[i]; k < C.ptr[i + 1]; ++k) posmap[C.idx[k]] = k;
-      for (int64_t a = Lm.ptr[i]; a < Lm.ptr[i + 1]; ++a) {
-        const int64_t j = Lm.idx[a];
-        for (int64_t b = Rm.ptr[j]; b < Rm.ptr[j + 1]; ++b) {
-          const int64_t pos = posmap[Rm.idx[b]];
-          if (pos < 0) throw std::runtime_error("internal: product pattern misses an entry");
-          if (pass == 0) G.ptr[pos + 1]++;
-          else {
-            const int64_t q = fill[pos]++;
-            G.src[q] = variable_left ? a : b;
-            G.w[q] = variable_left ? Rm.val[b] : Lm.val[a];
-          }
-        }
-      }
-      for (int64_t k = C.ptr[i]; k < C.ptr[i + 1]; ++k) posmap[C.idx[k]] = -1;
-    }
-  }
-  return G;
-}
-
 // Element-to-unknown incidence: row e lists the sorted unique columns of R touched by the p rows
 // of element e in the row blocks of the listed variables, shifted by colmap (column -> system
 // unknown, -1 = not in the system).  This is the union over k of the reference plan's col_indices

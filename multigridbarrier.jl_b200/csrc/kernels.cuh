@@ -6,12 +6,10 @@
 //                     block_ops.jl:118-133 (_block_matvec_kernel!)
 //   k_blockgrad       sum_k D_k' y_k                    src/convex.jl:173-178; block_ops.jl:135-148
 //   k_blockhess       sum_{j,k} D_j' diag(y_jk) D_k     src/convex.jl:185-200; block_ops.jl:58-75 (called nD^2 times there)
-//   k_csr_gather      R'HR into the fixed pattern       src/BlockMatrices.jl:506-555; block_ops.jl:229-249 (FP64 atomics there;
-//                                                       here a fixed-order gather, deterministic)
+//   (solver_kernels.cuh: k_sell_gather = R'HR into the fixed pattern and the Galerkin products; k_pcg_persistent = the solve)
 //   k_spmv*           R*s, R'*g                          CUSPARSE in the reference (src/convex.jl:156,178)
-//   k_spgemm_numeric  Galerkin T'(A T) for the V-cycle   (north-star item 3; no counterpart: the reference factorises H directly)
 //   k_jacobi*, k_pcg* multigrid-preconditioned CG        replaces cuDSS LDL' (ext/.../cudss_solver.jl:264-381)
-//   k_chol_*          dense Cholesky at the coarsest level / small systems
+//   (dense_kernels.cuh: DMMA GEMM and blocked Cholesky of the spectral path)
 // All reductions are fixed-order (block tree + last-block pass): results are run-to-run deterministic.
 #pragma once
 #include <cuda_runtime.h>
@@ -190,32 +188,6 @@ __global__ void __launch_bounds__(256) k_l1diag(DevCsr A, double *dinv, double *
   if (lam_bits) {
     ratio = warp_max(ratio);
     if ((threadIdx.x & 31) == 0 && ratio > 0.0) atomicMax(lam_bits, (unsigned long long)__double_as_longlong(ratio));
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Galerkin product, numeric phase into a fixed pattern: C = A * B, one thread per row of C
-// (sequential accumulation per row => deterministic).
-// ------------------------------------------------------------------------------------------------
-__global__ void k_spgemm_numeric(DevCsr A, DevCsr B, DevCsr C) {
-  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= C.rows) return;
-  const int64_t c0 = C.ptr[row], c1 = C.ptr[row + 1];
-  for (int64_t k = c0; k < c1; ++k) C.val[k] = 0.0;
-  for (int64_t k = A.ptr[row]; k < A.ptr[row + 1]; ++k) {
-    const double a = A.val[k];
-    const int64_t r = A.idx[k];
-    int64_t lo = c0;   // B's columns are sorted, so the search window only moves right
-    for (int64_t q = B.ptr[r]; q < B.ptr[r + 1]; ++q) {
-      const int32_t col = B.idx[q];
-      int64_t hi = c1 - 1;
-      while (lo < hi) {
-        const int64_t mid = (lo + hi) >> 1;
-        if (C.idx[mid] < col) lo = mid + 1;
-        else hi = mid;
-      }
-      C.val[lo] += a * B.val[q];
-    }
   }
 }
 
@@ -468,16 +440,6 @@ __global__ void __launch_bounds__(256) k_blockhess(ElemParams P, PairList PL, co
   Hblk[tid] = acc;
 }
 
-// val[nz] = sum_k gw[k] * Hblk[gidx[k]], k in [gptr[nz], gptr[nz+1])   (fixed order)
-__global__ void __launch_bounds__(256) k_csr_gather(int64_t nnz, const int64_t *__restrict__ gptr, const int64_t *__restrict__ gidx,
-                                                     const double *__restrict__ gw, const double *__restrict__ Hblk, double *val) {
-  const int64_t nz = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (nz >= nnz) return;
-  double acc = 0.0;
-  for (int64_t k = gptr[nz]; k < gptr[nz + 1]; ++k) acc += (gw ? gw[k] : 1.0) * Hblk[gidx[k]];
-  val[nz] = acc;
-}
-
 // ------------------------------------------------------------------------------------------------
 // condensation helpers (node-local elimination of the :full variables)
 // ------------------------------------------------------------------------------------------------
@@ -578,10 +540,6 @@ __global__ void k_axpby(int64_t m, double a, const double *__restrict__ x, doubl
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < m) out[i] = a * x[i] + (y ? b * y[i] : 0.0);
 }
-__global__ void k_mul(int64_t m, const double *__restrict__ a, const double *__restrict__ b, double *out) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < m) out[i] = a[i] * b[i];
-}
 
 // PCG: scal = {rz, pAp, rr, rz_new}.
 //  step A: alpha = rz/pAp;  x += alpha p;  r -= alpha Ap;  rr = r.r
@@ -644,10 +602,8 @@ __global__ void k_phase1_slack(int64_t n, const double *slack, double *out) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// dense Cholesky (row-major, lower), blocked right-looking with NB = 32
+// dense helpers (the blocked DMMA Cholesky lives in dense_kernels.cuh)
 // ------------------------------------------------------------------------------------------------
-constexpr int NB = 32;
-
 // Ad = 0 then Ad[i][j] = a_ij * d_i * d_j  with d = 1/sqrt(a_ii)
 __global__ void k_dense_scale_diag(DevCsr A, double *d) {
   const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -662,129 +618,6 @@ __global__ void k_csr_to_dense(DevCsr A, const double *d, double *Ad) {
   if (row >= A.rows) return;
   const double di = d[row];
   for (int64_t k = A.ptr[row]; k < A.ptr[row + 1]; ++k) Ad[row * A.rows + A.idx[k]] = A.val[k] * di * d[A.idx[k]];
-}
-
-// factor the diagonal block [k0, k0+nb) in shared memory (one block)
-__global__ void __launch_bounds__(256) k_chol_diag(double *A, int m, int k0) {
-  __shared__ double L[NB][NB + 1];
-  const int nb = min(NB, m - k0);
-  for (int t = threadIdx.x; t < NB * NB; t += blockDim.x) {
-    const int i = t / NB, j = t % NB;
-    L[i][j] = (i < nb && j < nb && j <= i) ? A[(size_t)(k0 + i) * m + k0 + j] : 0.0;
-  }
-  __syncthreads();
-  for (int j = 0; j < nb; ++j) {
-    if (threadIdx.x == 0) L[j][j] = sqrt(L[j][j]);
-    __syncthreads();
-    if ((int)threadIdx.x > j && (int)threadIdx.x < nb) L[threadIdx.x][j] /= L[j][j];
-    __syncthreads();
-    // trailing update inside the block: L[i][k] -= L[i][j]*L[k][j] for j < k <= i
-    for (int t = threadIdx.x; t < nb * nb; t += blockDim.x) {
-      const int i = t / nb, k = t % nb;
-      if (k > j && i >= k) L[i][k] -= L[i][j] * L[k][j];
-    }
-    __syncthreads();
-  }
-  for (int t = threadIdx.x; t < nb * nb; t += blockDim.x) {
-    const int i = t / nb, j = t % nb;
-    if (j <= i) A[(size_t)(k0 + i) * m + k0 + j] = L[i][j];
-  }
-}
-
-// panel rows below the (already factored) diagonal block: X L' = A21, row-wise forward substitution
-__global__ void __launch_bounds__(64) k_chol_trsm(double *A, int m, int k0) {
-  __shared__ double L[NB][NB + 1];
-  const int nb = min(NB, m - k0);
-  for (int t = threadIdx.x; t < NB * NB; t += blockDim.x) {
-    const int i = t / NB, j = t % NB;
-    L[i][j] = (i < nb && j < nb && j <= i) ? A[(size_t)(k0 + i) * m + k0 + j] : 0.0;
-  }
-  __syncthreads();
-  const int row = k0 + nb + blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= m) return;
-  double x[NB];
-  double *a = A + (size_t)row * m + k0;
-#pragma unroll
-  for (int c = 0; c < NB; ++c) {
-    if (c < nb) {
-      double s = a[c];
-#pragma unroll
-      for (int j = 0; j < NB; ++j)
-        if (j < c) s -= x[j] * L[c][j];
-      x[c] = s / L[c][c];
-    } else {
-      x[c] = 0.0;
-    }
-  }
-#pragma unroll
-  for (int c = 0; c < NB; ++c)
-    if (c < nb) a[c] = x[c];
-}
-
-// trailing update A22[i][j] -= sum_c L21[i][c] L21[j][c], lower tiles only; one 32x32 tile per block (32x8 threads)
-__global__ void __launch_bounds__(256) k_chol_syrk(double *A, int m, int k0) {
-  __shared__ double Li[NB][NB + 1], Lj[NB][NB + 1];
-  const int nb = min(NB, m - k0);
-  const int r0 = k0 + nb;
-  // decode lower-triangular tile index
-  int t = blockIdx.x, ti = 0;
-  while (t >= ti + 1) {
-    t -= ti + 1;
-    ++ti;
-  }
-  const int tj = t;
-  const int i0 = r0 + ti * NB, j0 = r0 + tj * NB;
-  const int tx = threadIdx.x % NB, ty = threadIdx.x / NB;   // 32 x 8
-  for (int rr = ty; rr < NB; rr += 8) {
-    Li[rr][tx] = (i0 + rr < m && tx < nb) ? A[(size_t)(i0 + rr) * m + k0 + tx] : 0.0;
-    Lj[rr][tx] = (j0 + rr < m && tx < nb) ? A[(size_t)(j0 + rr) * m + k0 + tx] : 0.0;
-  }
-  __syncthreads();
-  for (int rr = ty; rr < NB; rr += 8) {
-    const int i = i0 + rr, j = j0 + tx;
-    if (i < m && j < m && j <= i) {
-      double s = 0.0;
-#pragma unroll
-      for (int c = 0; c < NB; ++c) s += Li[rr][c] * Lj[tx][c];
-      A[(size_t)i * m + j] -= s;
-    }
-  }
-}
-
-// Solve L L' x = b for nrhs right-hand sides; one block per right-hand side.  B is m x nrhs column-major
-// (column stride m); eye != 0: the right-hand sides are the columns of the identity (explicit inverse).
-__global__ void __launch_bounds__(256) k_chol_solve(const double *__restrict__ L, int m, double *B, int eye) {
-  extern __shared__ double xs[];
-  double *col = B + (size_t)blockIdx.x * m;
-  for (int i = threadIdx.x; i < m; i += blockDim.x) xs[i] = eye ? (i == (int)blockIdx.x ? 1.0 : 0.0) : col[i];
-  __syncthreads();
-  __shared__ double wsum[8];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  // forward: x_k = (b_k - sum_{j<k} L[k][j] x_j) / L[k][k]
-  for (int k = (eye ? (int)blockIdx.x : 0); k < m; ++k) {
-    const double *row = L + (size_t)k * m;
-    double s = 0.0;
-    for (int j = threadIdx.x; j < k; j += blockDim.x) s += row[j] * xs[j];
-    s = warp_sum(s);
-    if (lane == 0) wsum[wid] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double tot = 0.0;
-      for (int w2 = 0; w2 < (int)(blockDim.x >> 5); ++w2) tot += wsum[w2];
-      xs[k] = (xs[k] - tot) / row[k];
-    }
-    __syncthreads();
-  }
-  // backward: L' x = y, column-oriented: x_k = y_k / L[k][k]; y_j -= L[k][j] x_k for j < k
-  for (int k = m - 1; k >= 0; --k) {
-    const double *row = L + (size_t)k * m;
-    if (threadIdx.x == 0) xs[k] = xs[k] / row[k];
-    __syncthreads();
-    const double xk = xs[k];
-    for (int j = threadIdx.x; j < k; j += blockDim.x) xs[j] -= row[j] * xk;
-    __syncthreads();
-  }
-  for (int i = threadIdx.x; i < m; i += blockDim.x) col[i] = xs[i];
 }
 
 // y = M x for a dense symmetric m x m matrix stored as m columns (coarse inverse); one warp per row

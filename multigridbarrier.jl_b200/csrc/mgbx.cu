@@ -7,7 +7,7 @@
 //   mgb.jl:10-82               divide_and_conquer / mgb_step -> Engine::step
 //   mgb.jl:307-330             _matched_t      -> Engine::matched_t
 //   convex.jl:155-202          f0 / f1 / f2    -> Engine::eval_f01 / assemble
-//   BlockMatrices.jl:322-555   assembly plan   -> build_system (host, once) + k_blockhess/k_csr_gather
+//   BlockMatrices.jl:322-555   assembly plan   -> build_system (once; plans built on the device) + k_elem*/k_sell_gather
 //   utils.jl:142-145           solve           -> Engine::solve (dense Cholesky or V-cycle PCG)
 // The t-ramp (mgb_core) and phase-I control flow (mgb_driver) stay on the host side of the ABI:
 // they only exchange scalars with this library.

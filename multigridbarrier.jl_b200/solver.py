@@ -291,6 +291,7 @@ def parabolic_solve(mg, p=1.0, h=0.2, t0=0.0, t1=1.0, ts=None, f1=None, g=None, 
     U = [np.array([g(ts[k], x[i]) for i in range(n)], dtype=float) for k in range(len(ts))]
     M = prepare_amg(mg, state_variables, D)
     handle = None
+    step_stats = []
     try:
         for k in range(len(ts) - 1):
             j = k + 1
@@ -307,7 +308,9 @@ def parabolic_solve(mg, p=1.0, h=0.2, t0=0.0, t1=1.0, ts=None, f1=None, g=None, 
                 handle.set_grids(fg, U[k + 1])
             sol = mgb_solve(prob, handle=handle, **rest)
             U[k + 1] = sol["z"]
+            step_stats.append(dict(sol["stats"], newton_main=int(sol["SOL_main"]["its"].sum()),
+                                   newton_feas=int(sol["SOL_feasibility"]["its"].sum()) if sol["SOL_feasibility"] else 0))
     finally:
         if handle is not None:
             handle.close()
-    return dict(geometry=geom, ts=np.asarray(ts), u=U)
+    return dict(geometry=geom, ts=np.asarray(ts), u=U, stats=step_stats)
