@@ -894,11 +894,12 @@ struct Engine {
 
   // ---------------------------------------------------------------- system assembly
   System &system_for(Amg &A, int J);
-  // Dense Cholesky for tiny systems and for spectral (dense) discretisations; finite-element systems above the
-  // coarse size go through the V-cycle PCG, which is faster there than a dense factorisation per Newton step.
+  // Systems with at most dense_direct_max unknowns are solved directly (shared-memory solve with pivoted fallback up to
+  // 128, blocked DMMA Cholesky above): faster than PCG at these sizes and robust for the systems that could not be
+  // condensed (e.g. a :broken_P1 slack), whose 1/slack^2 entries make them too ill-conditioned for an iterative solve.
   bool use_direct(const System &S, const SysLevel &Lv) const {
-    if (Lv.m > h->cfg.dense_direct_max) return false;
-    return Lv.m <= kCoarseMaxDense || S.dense_elements || S.lev.size() == 1;
+    (void)S;
+    return Lv.m <= h->cfg.dense_direct_max;
   }
   void assemble(Amg &A, System &S, int J, double t, const double *zbase, const double *x);
   void assemble_dense(Amg &A, System &S, const NodeParams &P);

@@ -232,6 +232,24 @@ def test_parabolic_midsize_matches_oracle():
     assert rel(ud, uo) < 1e-6
 
 
+@pytest.mark.parametrize("L,cfg", [(3, {}), (4, {})])
+def test_pure_p2_masked_barrier_matches_oracle(L, cfg):
+    """Pure P2 (no bubble): the corner nodes carry zero quadrature weight, so the barrier is averaged over the masked node
+    set (`_masked_barrier`, convex.jl:213-257, weights convex.jl:279-304) and the slack lives in :broken_P1 (not node-local:
+    no condensation, the Newton system couples u and s and carries the 1/slack^2 entries: it is solved directly -- forcing
+    the V-cycle PCG onto it degrades the t-ramp, DESIGN.md "known limits").  test/test_pure_p2.jl:53-63 pins this family."""
+    prob = P.assemble(H.amg(G.subdivide(G.fem2d_P2(bubble=False), L)), p=1.5)
+    assert (prob.M[0].w == 0).any()
+    sd = solver.mgb_solve(prob, config=cfg)
+    so = O.mgb_solve(prob)
+    assert rel(sd["z"], so["z"]) < 1e-6
+    od, oo = sd["SOL_main"]["c_dot_Dz"][-1], so["SOL_main"]["c_dot_Dz"][-1]
+    assert abs(od - oo) <= 1e-8 * abs(oo)
+    assert sd["SOL_main"]["its"].shape == so["SOL_main"]["its"].shape
+    d = np.abs(sd["SOL_main"]["its"].sum(axis=0) - so["SOL_main"]["its"].sum(axis=0))
+    assert np.max(d[:-1], initial=0) <= 1
+
+
 # ------------------------------------------------------------------------------------------ persistent solve kernel
 @pytest.mark.parametrize("tail_max", [0, 300, 10 ** 9])
 def test_persistent_pcg_matches_multilaunch_pcg(tail_max):
