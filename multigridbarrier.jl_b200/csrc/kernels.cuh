@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(256) k_jacobi_first2(DevCsr A, const double *_
   }
 }
 
-// dinv = 1 / sum_k |a_ik|  (l1-Jacobi), diag = a_ii, and the Gershgorin bound of lambda_max(D^-1 A),
+// dinv = 1 / sum_k |a_ik|  (l1-Jacobi), diag = 1 / a_ii, and the Gershgorin bound of lambda_max(D^-1 A),
 // max_i sum_k |a_ik| / a_ii, folded with atomicMax on the bit pattern (non-negative doubles order like integers;
 // max is order-independent, so the result is deterministic).  *lam_bits must be zeroed before the launch.
 __global__ void __launch_bounds__(256) k_l1diag(DevCsr A, double *dinv, double *diag, unsigned long long *lam_bits) {
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(256) k_l1diag(DevCsr A, double *dinv, double *
       if (A.idx[k] == row) d = A.val[k];
     }
     dinv[row] = s > 0.0 ? 1.0 / s : 0.0;
-    if (diag) diag[row] = d;
+    if (diag) diag[row] = d > 0.0 ? 1.0 / d : 0.0;   // inverse diagonal (Chebyshev scaling)
     if (d > 0.0 && isfinite(s)) ratio = s / d;
   }
   if (lam_bits) {

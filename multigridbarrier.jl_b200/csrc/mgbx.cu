@@ -910,6 +910,19 @@ struct Engine {
   void vcycle(System &S, int k);
   void pcg_iteration(System &S, int ktop);
   System::PcgDev &pcg_plan(System &S, int ktop);
+  Csr32 csr32(const DevCsr &A) {   // 32-bit row pointers for the persistent kernel (pattern is fixed: converted once)
+    if (A.nnz > INT32_MAX || A.rows >= INT32_MAX) throw std::runtime_error("persistent solve kernel: a level matrix exceeds 32-bit indexing");
+    int *p32 = h->pool.alloc<int>((size_t)A.rows + 1);
+    k_ptr32<<<nblk(A.rows + 1), 256, 0, s>>>(A.rows + 1, A.ptr, p32);
+    CK(cudaGetLastError());
+    Csr32 C;
+    C.rows = (int)A.rows;
+    C.nnz = (int)A.nnz;
+    C.ptr = p32;
+    C.idx = A.idx;
+    C.val = A.val;
+    return C;
+  }
   int pcg_persistent(System &S, int ktop, const double *b, double *x);
   int pcg(System &S, int ktop, const double *b, double *x);
   int solve_compact(System &S, int ktop, const double *b, double *x);
@@ -1485,7 +1498,7 @@ System::PcgDev &Engine::pcg_plan(System &S, int ktop) {
     SysLevel &Lv = S.lev[act[q]];
     PLevel &pl = P.lev[q];
     pl.m = Lv.m;
-    pl.A = Lv.A;
+    pl.A = csr32(Lv.A);
     pl.dinv = Lv.dinv;
     pl.diag = Lv.diag;
     pl.lam = Lv.lam;
@@ -1495,8 +1508,8 @@ System::PcgDev &Engine::pcg_plan(System &S, int ktop) {
     pl.r = Lv.r;
     pl.G = Lv.spmv_group;
     if (q + 1 < P.nlev) {
-      pl.T = Lv.T;
-      pl.Tt = Lv.Tt;
+      pl.T = csr32(Lv.T);
+      pl.Tt = csr32(Lv.Tt);
       pl.GT = group_for(Lv.T);
       pl.GTt = group_for(Lv.Tt);
     }

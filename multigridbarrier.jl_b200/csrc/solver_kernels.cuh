@@ -45,6 +45,11 @@ __global__ void __launch_bounds__(256) k_sell_gather(SellPlan P, const double *_
   out[nz] = acc;
 }
 
+__global__ void k_ptr32(int64_t n, const int64_t *__restrict__ p64, int *p32) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p32[i] = (int)p64[i];
+}
+
 // row index of every non-zero of a CSR pattern
 __global__ void k_csr_rows(DevCsr A, int32_t *rowof) {
   const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -306,11 +311,21 @@ inline size_t dense_solve_small_smem(int m) { return sizeof(double) * ((size_t)m
 constexpr int kPcgThreads = 1024;
 constexpr int kPcgMaxGrid = 1024;   // partial slots per reduction
 
+// 32-bit view of a level matrix inside the persistent kernel: halves the index arithmetic, and the explicit
+// __ldg (matrix data: immutable while the kernel runs) / __ldcg (vectors other CTAs wrote in the previous phase: read
+// at L2, never from a stale L1 line) keep the loads on the global path although the pointers come from shared memory.
+struct Csr32 {
+  int rows, nnz;
+  const int *ptr;
+  const int *idx;
+  const double *val;
+};
+
 struct PLevel {
   int64_t m;
-  DevCsr A, T, Tt;       // T: this level <- next coarser active level; Tt its transpose
+  Csr32 A, T, Tt;        // T: this level <- next coarser active level; Tt its transpose (32-bit row pointers)
   const double *dinv;    // l1-Jacobi: 1 / sum_j |a_ij|
-  const double *diag;    // a_ii (Chebyshev)
+  const double *diag;    // 1 / a_ii (Chebyshev)
   const double *lam;     // Gershgorin bound of lambda_max(D^-1 A), refreshed with the matrix values
   double *b, *x, *x2, *r;
   int G, GT, GTt;        // lanes per row
@@ -361,11 +376,11 @@ struct Scope {
 };
 
 template <int G>
-__device__ __forceinline__ double row_dot(const DevCsr &A, int64_t row, int sub, bool valid, const double *x) {
+__device__ __forceinline__ double row_dot(const Csr32 &A, int row, int sub, bool valid, const double *x) {
   double acc = 0.0;
   if (valid) {
-    const int64_t b = A.ptr[row], e = A.ptr[row + 1];
-    for (int64_t k = b + sub; k < e; k += G) acc += A.val[k] * x[A.idx[k]];
+    const int b = __ldg(A.ptr + row), e = __ldg(A.ptr + row + 1);
+    for (int k = b + sub; k < e; k += G) acc += __ldg(A.val + k) * __ldcg(x + __ldg(A.idx + k));
   }
   if (G > 1) {
 #pragma unroll
@@ -376,31 +391,31 @@ __device__ __forceinline__ double row_dot(const DevCsr &A, int64_t row, int sub,
 
 // y = alpha * A x + (y0 ? y0 : 0)     (y may alias y0; y must not alias x)
 template <int G, class SC>
-__device__ void ph_spmv(const SC &sc, const DevCsr &A, const double *x, const double *y0, double alpha, double *y) {
-  const int64_t step = sc.nthr / G;
-  const int sub = (int)(sc.tid % G);
-  for (int64_t base = 0; base < A.rows; base += step) {
-    const int64_t row = base + sc.tid / G;
+__device__ void ph_spmv(const SC &sc, const Csr32 &A, const double *x, const double *y0, double alpha, double *y) {
+  const int step = (int)(sc.nthr / G);
+  const int sub = (int)(sc.tid % G), r0 = (int)(sc.tid / G);
+  for (int base = 0; base < A.rows; base += step) {
+    const int row = base + r0;
     const bool valid = row < A.rows;
     const double acc = row_dot<G>(A, row, sub, valid, x);
-    if (valid && sub == 0) y[row] = alpha * acc + (y0 ? y0[row] : 0.0);
+    if (valid && sub == 0) y[row] = alpha * acc + (y0 ? __ldcg(y0 + row) : 0.0);
   }
 }
 
 // two l1-Jacobi sweeps from x = 0:  x1 = dinv b;  x = x1 + dinv (b - A x1)
 template <int G, class SC>
-__device__ void ph_jacobi_first2(const SC &sc, const DevCsr &A, const double *dinv, const double *b, double *xnew) {
-  const int64_t step = sc.nthr / G;
-  const int sub = (int)(sc.tid % G);
-  for (int64_t base = 0; base < A.rows; base += step) {
-    const int64_t row = base + sc.tid / G;
+__device__ void ph_jacobi_first2(const SC &sc, const Csr32 &A, const double *dinv, const double *b, double *xnew) {
+  const int step = (int)(sc.nthr / G);
+  const int sub = (int)(sc.tid % G), r0 = (int)(sc.tid / G);
+  for (int base = 0; base < A.rows; base += step) {
+    const int row = base + r0;
     const bool valid = row < A.rows;
     double acc = 0.0;
     if (valid) {
-      const int64_t bb = A.ptr[row], e = A.ptr[row + 1];
-      for (int64_t k = bb + sub; k < e; k += G) {
-        const int32_t j = A.idx[k];
-        acc += A.val[k] * (dinv[j] * b[j]);
+      const int bb = __ldg(A.ptr + row), e = __ldg(A.ptr + row + 1);
+      for (int k = bb + sub; k < e; k += G) {
+        const int j = __ldg(A.idx + k);
+        acc += __ldg(A.val + k) * (__ldg(dinv + j) * __ldcg(b + j));
       }
     }
     if (G > 1) {
@@ -408,7 +423,7 @@ __device__ void ph_jacobi_first2(const SC &sc, const DevCsr &A, const double *di
       for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, G);
     }
     if (valid && sub == 0) {
-      const double d = dinv[row], bi = b[row];
+      const double d = __ldg(dinv + row), bi = __ldcg(b + row);
       const double x1 = d * bi;
       xnew[row] = x1 + d * (bi - acc);
     }
@@ -417,31 +432,30 @@ __device__ void ph_jacobi_first2(const SC &sc, const DevCsr &A, const double *di
 
 // xnew = x + dinv (b - A x); returns this thread's share of sum_i dotw[i] * xnew[i] (0 if dotw == nullptr)
 template <int G, class SC>
-__device__ double ph_jacobi(const SC &sc, const DevCsr &A, const double *dinv, const double *b, const double *x, double *xnew,
+__device__ double ph_jacobi(const SC &sc, const Csr32 &A, const double *dinv, const double *b, const double *x, double *xnew,
                             const double *dotw) {
-  const int64_t step = sc.nthr / G;
-  const int sub = (int)(sc.tid % G);
+  const int step = (int)(sc.nthr / G);
+  const int sub = (int)(sc.tid % G), r0 = (int)(sc.tid / G);
   double part = 0.0;
-  for (int64_t base = 0; base < A.rows; base += step) {
-    const int64_t row = base + sc.tid / G;
+  for (int base = 0; base < A.rows; base += step) {
+    const int row = base + r0;
     const bool valid = row < A.rows;
     const double acc = row_dot<G>(A, row, sub, valid, x);
     if (valid && sub == 0) {
-      const double v = x[row] + dinv[row] * (b[row] - acc);
+      const double v = __ldcg(x + row) + __ldg(dinv + row) * (__ldcg(b + row) - acc);
       xnew[row] = v;
-      if (dotw) part += dotw[row] * v;
+      if (dotw) part += __ldcg(dotw + row) * v;
     }
   }
   return part;
 }
-
 
 // ---- Chebyshev smoothing (degree nu, diagonal preconditioning) -------------------------------------------
 // 3-term recurrence on [a, b] = [lam/ratio, lam]:  theta = (a+b)/2, delta = (b-a)/2, sigma = theta/delta,
 // rho_0 = 1/sigma, rho_k = 1/(2 sigma - rho_{k-1});  d_0 = D^-1 r_0 / theta,
 // d_k = rho_k rho_{k-1} d_{k-1} + (2 rho_k / delta) D^-1 r_k,  x_{k+1} = x_k + d_k.  The error propagator is a
 // polynomial in D^-1 A, hence A-self-adjoint: the same sweeps before and after the coarse correction keep the
-// V-cycle a symmetric preconditioner.
+// V-cycle a symmetric preconditioner.  `idiag` holds 1 / a_ii.
 struct Cheb {
   double th_inv, sigma, delta;
   __device__ __forceinline__ Cheb(double lam, double ratio) {
@@ -462,19 +476,19 @@ struct Cheb {
 
 // steps 0 and 1 from x = 0 in one pass: d0 = th_inv D^-1 b; r1 = b - A d0; d1 = c_dd d0 + c_dr D^-1 r1; x = d0 + d1
 template <int G, class SC>
-__device__ void ph_cheb_first2(const SC &sc, const DevCsr &A, const double *diag, const double *b, double *xnew, double *d,
+__device__ void ph_cheb_first2(const SC &sc, const Csr32 &A, const double *idiag, const double *b, double *xnew, double *d,
                                double th_inv, double c_dd, double c_dr) {
-  const int64_t step = sc.nthr / G;
-  const int sub = (int)(sc.tid % G);
-  for (int64_t base = 0; base < A.rows; base += step) {
-    const int64_t row = base + sc.tid / G;
+  const int step = (int)(sc.nthr / G);
+  const int sub = (int)(sc.tid % G), r0 = (int)(sc.tid / G);
+  for (int base = 0; base < A.rows; base += step) {
+    const int row = base + r0;
     const bool valid = row < A.rows;
     double acc = 0.0;
     if (valid) {
-      const int64_t bb = A.ptr[row], e = A.ptr[row + 1];
-      for (int64_t k = bb + sub; k < e; k += G) {
-        const int32_t j = A.idx[k];
-        acc += A.val[k] * (th_inv * b[j] / diag[j]);
+      const int bb = __ldg(A.ptr + row), e = __ldg(A.ptr + row + 1);
+      for (int k = bb + sub; k < e; k += G) {
+        const int j = __ldg(A.idx + k);
+        acc += __ldg(A.val + k) * (__ldcg(b + j) * __ldg(idiag + j));
       }
     }
     if (G > 1) {
@@ -482,9 +496,9 @@ __device__ void ph_cheb_first2(const SC &sc, const DevCsr &A, const double *diag
       for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, G);
     }
     if (valid && sub == 0) {
-      const double di = 1.0 / diag[row], bi = b[row];
+      const double di = __ldg(idiag + row), bi = __ldcg(b + row);
       const double d0 = th_inv * bi * di;
-      const double d1 = c_dd * d0 + c_dr * (bi - acc) * di;
+      const double d1 = c_dd * d0 + c_dr * (bi - th_inv * acc) * di;
       xnew[row] = d0 + d1;
       d[row] = d1;
     }
@@ -493,22 +507,22 @@ __device__ void ph_cheb_first2(const SC &sc, const DevCsr &A, const double *diag
 
 // one step on an existing iterate: r = b - A x; d = (first ? th_inv D^-1 r : c_dd d + c_dr D^-1 r); xnew = x + d
 template <int G, class SC>
-__device__ double ph_cheb_step(const SC &sc, const DevCsr &A, const double *diag, const double *b, const double *x, double *xnew,
+__device__ double ph_cheb_step(const SC &sc, const Csr32 &A, const double *idiag, const double *b, const double *x, double *xnew,
                                double *d, bool first, double th_inv, double c_dd, double c_dr, const double *dotw) {
-  const int64_t step = sc.nthr / G;
-  const int sub = (int)(sc.tid % G);
+  const int step = (int)(sc.nthr / G);
+  const int sub = (int)(sc.tid % G), r0 = (int)(sc.tid / G);
   double part = 0.0;
-  for (int64_t base = 0; base < A.rows; base += step) {
-    const int64_t row = base + sc.tid / G;
+  for (int base = 0; base < A.rows; base += step) {
+    const int row = base + r0;
     const bool valid = row < A.rows;
     const double acc = row_dot<G>(A, row, sub, valid, x);
     if (valid && sub == 0) {
-      const double rr = (b[row] - acc) / diag[row];
+      const double rr = (__ldcg(b + row) - acc) * __ldg(idiag + row);
       const double dn = first ? th_inv * rr : c_dd * d[row] + c_dr * rr;
-      const double v = x[row] + dn;
+      const double v = __ldcg(x + row) + dn;
       d[row] = dn;
       xnew[row] = v;
-      if (dotw) part += dotw[row] * v;
+      if (dotw) part += __ldcg(dotw + row) * v;
     }
   }
   return part;
@@ -716,7 +730,7 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_persistent(const PcgPlan
       const double *z = P.lev[0].x;
       if (single) {   // one-level "hierarchy": no up-sweep ran, take the dot here
         prz = 0.0;
-        for (int64_t i = tid; i < m; i += nthr) prz += P.r[i] * z[i];
+        for (int64_t i = tid; i < m; i += nthr) prz += P.r[i] * __ldcg(z + i);
       }
       const double rz = grid_sum(prz, slot1, P.bar);
       const double beta = rz / rz_old;
@@ -732,15 +746,15 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_persistent(const PcgPlan
           const bool valid = row < m;
           double acc = 0.0;
           if (valid) {
-            const int64_t b0 = top.A.ptr[row], e0 = top.A.ptr[row + 1];
-            for (int64_t k = b0 + sub; k < e0; k += G) {
-              const int32_t j = top.A.idx[k];
-              acc += top.A.val[k] * (z[j] + beta * pv[j]);
+            const int b0 = __ldg(top.A.ptr + row), e0 = __ldg(top.A.ptr + row + 1);
+            for (int k = b0 + sub; k < e0; k += G) {
+              const int j = __ldg(top.A.idx + k);
+              acc += __ldg(top.A.val + k) * (__ldcg(z + j) + beta * __ldcg(pv + j));
             }
           }
           for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, G);
           if (valid && sub == 0) {
-            const double pn = z[row] + beta * pv[row];
+            const double pn = __ldcg(z + row) + beta * __ldcg(pv + row);
             pv2[row] = pn;
             P.Ap[row] = acc;
             ppap += pn * acc;
@@ -761,8 +775,8 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_persistent(const PcgPlan
       const double alpha = rz / pAp;
       double prr = 0.0;
       for (int64_t i = tid; i < m; i += nthr) {
-        P.x[i] += alpha * pv[i];
-        const double ri = P.r[i] - alpha * P.Ap[i];
+        P.x[i] += alpha * __ldcg(pv + i);
+        const double ri = P.r[i] - alpha * __ldcg(P.Ap + i);
         P.r[i] = ri;
         prr += ri * ri;
       }

@@ -10,7 +10,9 @@ for kv in sys.argv[2:]:
     k, v = kv.split("=")
     cfg[k] = float(v) if "." in v or "e" in v else int(v)
 pp = cfg.pop("p", None)
-if case.startswith("q1c"):
+if case.startswith("q1L"):
+    prob = P.assemble(H.amg(G.subdivide(G.fem3d(k=1), int(case[3:]))), p=float(pp or 1.0))
+elif case.startswith("q1c"):
     prob = P.assemble(H.amg(G.structured_box(3, int(case[3:]), k=1)), p=float(pp or 1.0))
 else:
     prob = P.assemble(H.amg(G.subdivide(G.fem2d_P1(), int(case))), p=float(pp or 1.5))
