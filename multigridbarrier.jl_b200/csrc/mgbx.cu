@@ -77,7 +77,8 @@ struct HostTimer {
   }
 };
 
-inline unsigned int nblk(int64_t work, int threads = 256) { return (unsigned int)((work + threads - 1) / threads); }
+// at least one block: every kernel bounds-checks its index, and an empty level (e.g. no interior unknown) must not be a launch error
+inline unsigned int nblk(int64_t work, int threads = 256) { return (unsigned int)std::max<int64_t>(1, (work + threads - 1) / threads); }
 
 
 // ------------------------------------------------------------------------------------------------

@@ -74,6 +74,68 @@ def test_tiny_tolerance_is_a_convergence_failure():
         solver.mgb_solve(default_problem("fem1d_3nodes", 1.0), tol=1e-50, maxit=40)
 
 
+# ------------------------------------------------------------------------------------------ edge cases and argument errors
+def test_smallest_problems_and_single_level():
+    """One element / two nodes (fem1d with 2 nodes: no interior unknown of u, only the slack) and a hierarchy of one level."""
+    mg = H.amg(G.fem1d(nodes=np.linspace(-1, 1, 2)))
+    prob = P.assemble(mg, p=1.0)
+    sd = solver.mgb_solve(prob)
+    so = O.mgb_solve(prob)
+    assert rel(sd["z"], so["z"]) < 1e-6
+    # a u-only problem (no slack at all): linear barrier, one state variable, one D row
+    sol = solver.mgb_solve(lower_bound_problem(-3.0, nodes=2))
+    assert np.all(np.isfinite(sol["z"]))
+
+
+def test_bad_arguments_are_errors_not_crashes():
+    prob = default_problem("fem1d_5nodes", 1.0)
+    h = native.Handle(prob)
+    try:
+        o = h.step_opts()
+        r = native.StepResult()
+        L = native.lib()
+        import ctypes as C
+        assert L.mgbx_step(h._h, 5, 0.1, C.byref(o), C.byref(r)) == native.ERR_ARG          # no such AMG
+        assert L.mgbx_step(h._h, 1, 0.1, C.byref(o), C.byref(r)) == native.ERR_ARG          # feasibility AMG not attached
+        o.line_search = 7
+        assert L.mgbx_step(h._h, 0, 0.1, C.byref(o), C.byref(r)) == native.ERR_ARG
+        assert b"line_search" in L.mgbx_last_error(h._h)
+        assert L.mgbx_level_size(h._h, 0, 99) == -1
+        s = np.zeros(3)
+        out = np.zeros(3)
+        assert L.mgbx_barrier_eval(h._h, 0, 99, 1.0, native._ptr(s), 0, native._ptr(out)) == native.ERR_ARG
+        assert L.mgbx_barrier_eval(h._h, 0, 0, 1.0, native._ptr(s), 2, native._ptr(out)) == native.ERR_ARG
+        # the handle is still usable after the errors
+        o = h.step_opts(initial_step=1)
+        rc, r = h.step(0, 0.1, o)
+        assert rc in (native.OK, native.NOT_CONVERGED)
+    finally:
+        h.close()
+    # inconsistent problem descriptions are rejected at create time
+    bad = default_problem("fem1d_5nodes", 1.0)
+    bad.Q.pieces[0].idx = (0, 7)          # D row 7 does not exist
+    with pytest.raises(native.MgbxError) as e:
+        native.Handle(bad)
+    assert e.value.code == native.ERR_ARG and "D row" in str(e.value)
+
+
+def test_start_outside_the_domain_is_reported_by_value():
+    """A starting point outside the barrier's domain: mgbx_step returns MGBX_NON_FINITE (the reference raises from newton)."""
+    prob = default_problem("fem2d_P1_L2", 1.0)
+    h = native.Handle(prob)
+    try:
+        n = prob.geometry.n
+        z = prob.g.T.reshape(-1).copy()
+        z[n:] = -1.0                         # slack below zero everywhere
+        h.set_z(z, 0)
+        rc, r = h.step(0, 0.1, h.step_opts(initial_step=1))
+        assert rc == native.NON_FINITE and r.converged == 0
+        need, b, zabs = h.phase1_init()      # ... and phase I is what the driver does about it
+        assert need and b >= 2.0
+    finally:
+        h.close()
+
+
 # ------------------------------------------------------------------------------------------ stage-by-stage vs oracle
 def _obstacle_problem():
     """two-sided obstacle + p-Laplace cone as an intersection (linear + EP pieces, select grid)."""
