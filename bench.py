@@ -271,7 +271,8 @@ def main():
                             "of all levels, ~%.0f MB) is L2-resident, so the HBM peak is a reference line, not a ceiling; "
                             "the kernel is bound by grid-barrier and dependent-load latency (see DESIGN.md)"
                             % (info["nlev"], info["m"], sum(12 * z for z in info["nnz"]) / 1e6))
-        roof_all = {c: line(c) for c in ("elem_f01", "elem_f2", "csr_gather", "spgemm", "pcg_persistent") if kstats.get(c, (0, 0))[0]}
+        roof_all = {c: line(c) for c in ("elem_f01", "elem_f2", "elem_generic_f01", "elem_generic_f2", "csr_gather", "spgemm", "pcg_persistent")
+                    if kstats.get(c, (0, 0))[0]}
     h.close()
 
     tmax = torch.tensor([dev_s, wall, float(np.mean(e2e_times))], dtype=torch.float64, device="cuda")
@@ -336,6 +337,8 @@ def algorithmic_bytes(prob, h, counts):
     # fused element kernels: zf (nu), f grid (nD), w, operator blocks once; write gb (nu)  /  hEEinv, hKE, Hblk
     out["elem_f01"] = 8 * (n * (nu + nD + 1) + ops_b + nu * n)
     out["elem_f2"] = 8 * (n * nu + ops_b + n * (nE * (nE + 1) // 2 + nK * nE) + pairs * N * p * p)
+    out["elem_generic_f01"] = out["elem_f01"]
+    out["elem_generic_f2"] = 8 * (n * nu + ops_b + nu * nu * N * p * p)      # coarse-level systems: nothing eliminated, nu^2 block pairs
     out["node_f01"] = 8 * (n * (nu + nD + 1 + nD) + ops_b)
     out["node_f2"] = 8 * (n * (nu + nK * (nK + 1) // 2 + nE * (nE + 1) // 2 + nK * nE) + ops_b)
     out["blockgrad"] = 8 * (n * nD + ops_b + nu * n)

@@ -241,7 +241,7 @@ typedef struct {
 int mgbx_solver_info(mgbx_handle *h, int which, mgbx_solver_info_t *out);
 
 /* per-kernel-class launch counts and (with profile on) summed device time in ms; names[k] are static strings.
- * Arrays must hold at least 16 entries. */
+ * Arrays must hold at least 32 entries. */
 int mgbx_kernel_stats(mgbx_handle *h, int reset, int32_t *nclasses, const char **names, int64_t *launches, double *ms);
 int mgbx_set_profile(mgbx_handle *h, int on);
 

@@ -925,42 +925,88 @@ struct PlapParams {
   double *hEEinv, *hKE, *Hblk;
 };
 
+// shared memory: two input buffers (operator blocks + the tile's node inputs, filled by cp.async one tile ahead) + exchange rows
 inline size_t elem_plap_smem(int dim, int epb, int ES, int p) {
-  return sizeof(double) * ((size_t)dim * epb * ES + (size_t)(1 + (dim * (dim + 1)) / 2) * epb * p);
+  const size_t tm = (size_t)epb * p;
+  const size_t buf = (size_t)dim * epb * ES + (size_t)(4 + dim + 2) * tm;
+  return sizeof(double) * (2 * buf + (size_t)((dim * (dim + 1)) / 2 > dim ? (dim * (dim + 1)) / 2 : dim) * tm);
 }
 
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
+  const unsigned int sa = (unsigned int)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// Tiles are software-pipelined: while tile k is evaluated, the operator blocks and node inputs of tile k+1 stream into the
+// other shared-memory buffer with cp.async (LDGSTS), so the evaluation never waits on HBM latency after the first tile.
 template <int MODE, int DIM>
-__global__ void __launch_bounds__(256, 4) k_elem_plap(PlapParams P) {
+__global__ void __launch_bounds__(256, 3) k_elem_plap(PlapParams P) {
   extern __shared__ double esm[];
   constexpr int NH = (DIM * (DIM + 1)) / 2;
+  constexpr int NEX = NH > DIM ? NH : DIM;
+  constexpr int NF = DIM + 2;
   const int p = P.p, pp = p * p, p1 = P.p1, ES = P.ES, epb = P.epb;
   const int TM = epb * p;
-  double *ops_s = esm;                             // [a][el][c][r] padded
-  double *us = ops_s + (size_t)DIM * epb * ES;     // [slot]
-  double *ex = us + TM;                            // [row][slot]: F01 DIM rows, F2 NH rows
+  const size_t bufsz = (size_t)DIM * epb * ES + (size_t)(4 + NF) * TM;
+  double *ex = esm + 2 * bufsz;                    // [row][slot]: F01 DIM rows, F2 NH rows
+  (void)NEX;
   const int tid = threadIdx.x;
   double red[4] = {0.0, 0.0, 0.0, -INFINITY};
   const int op4[4] = {0, 0, 0, 1};
   const int64_t ntiles = (P.N + epb - 1) / epb;
   const double al = 2.0 / P.pexp;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  // buffer layout: ops [a][el][c][r] padded | us | ss | ws | bws | fs[NF]
+  auto issue = [&](int64_t tile, int b) {
+    double *buf = esm + (size_t)b * bufsz;
     const int64_t e0 = tile * epb;
     const int ne = (int)min((int64_t)epb, P.N - e0);
     const int T = ne * p;
     const int64_t node0 = e0 * p;
-    __syncthreads();
 #pragma unroll
     for (int a = 0; a < DIM; ++a) {
       const double *src = P.ops[a] + e0 * (int64_t)pp;
-      double *dst = ops_s + (size_t)a * epb * ES;
+      double *dst = buf + (size_t)a * epb * ES;
       for (int t = tid; t < ne * pp; t += 256) {
         const int el = (int)fdiv((unsigned int)t, P.dpp), rem = t - el * pp;
         const int c = (int)fdiv((unsigned int)rem, P.dp), r = rem - c * p;
-        dst[el * ES + c * p1 + r] = src[t];
+        cp_async8(dst + el * ES + c * p1 + r, src + t);
       }
     }
-    if (tid < T) us[tid] = P.zu[node0 + tid];
+    double *nd = buf + (size_t)DIM * epb * ES;
+    if (tid < T) {
+      const int64_t i = node0 + tid;
+      cp_async8(nd + tid, P.zu + i);
+      cp_async8(nd + TM + tid, P.zs + i);
+      cp_async8(nd + 2 * TM + tid, P.w + i);
+      if (P.bw) cp_async8(nd + 3 * TM + tid, P.bw + i);
+#pragma unroll
+      for (int j = 0; j < NF; ++j) cp_async8(nd + (4 + j) * TM + tid, P.f + i + (int64_t)j * P.n);
+    }
+    cp_async_commit();
+  };
+  int b = 0;
+  if ((int64_t)blockIdx.x < ntiles) issue(blockIdx.x, 0);
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t next = tile + gridDim.x;
+    if (next < ntiles) {
+      issue(next, b ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
     __syncthreads();
+    const double *ops_s = esm + (size_t)b * bufsz;
+    const double *us = ops_s + (size_t)DIM * epb * ES;
+    const double *ss = us + TM, *ws = us + 2 * TM, *bws = us + 3 * TM, *fs = us + 4 * TM;
+    const int64_t e0 = tile * epb;
+    const int ne = (int)min((int64_t)epb, P.N - e0);
+    const int T = ne * p;
+    const int64_t node0 = e0 * p;
     const int el = (int)fdiv((unsigned int)tid, P.dp), qn = tid - el * p;
     const bool on = tid < T;
     const int64_t i = node0 + tid;
@@ -976,11 +1022,11 @@ __global__ void __launch_bounds__(256, 4) k_elem_plap(PlapParams P) {
         q[a] = acc;
       }
       const double uu = ue[qn];
-      const double s = P.zs[i];
-      const double bwi = P.bw ? P.bw[i] : 1.0;
+      const double s = ss[tid];
+      const double bwi = P.bw ? bws[tid] : 1.0;
       const bool active = !(P.bw && bwi == 0.0);
       const double sc = P.bw ? bwi : P.inv_n;
-      const double wi = P.w[i];
+      const double wi = ws[tid];
       double qsq = 0.0;
 #pragma unroll
       for (int a = 0; a < DIM; ++a) qsq += q[a] * q[a];
@@ -992,15 +1038,15 @@ __global__ void __launch_bounds__(256, 4) k_elem_plap(PlapParams P) {
       const double sam1 = in ? sa / s : safe_pow(s, al - 1.0);
       if (MODE == NODE_F01) {
         const double F0 = active ? (-Log(r) - P.mu * ls) : 0.0;
-        const double c0 = P.t * P.f[i];
-        const double cs = P.t * P.f[i + (int64_t)(DIM + 1) * P.n];
+        const double c0 = P.t * fs[tid];
+        const double cs = P.t * fs[(DIM + 1) * TM + tid];
         double lin = c0 * uu + cs * s;
         G0 = wi * c0;
         const double gs = -al * sam1 * inv_r - P.mu / s;
         Gs = (active ? sc * gs : 0.0) + wi * cs;
 #pragma unroll
         for (int a = 0; a < DIM; ++a) {
-          const double ca = P.t * P.f[i + (int64_t)(a + 1) * P.n];
+          const double ca = P.t * fs[(a + 1) * TM + tid];
           lin += ca * q[a];
           ex[a * TM + tid] = (active ? sc * 2.0 * inv_r * q[a] : 0.0) + wi * ca;
         }
@@ -1027,9 +1073,9 @@ __global__ void __launch_bounds__(256, 4) k_elem_plap(PlapParams P) {
 #pragma unroll
           for (int a = 0; a < DIM; ++a)
 #pragma unroll
-            for (int b = a; b < DIM; ++b, ++k) {
-              const double hab = sc * (4.0 * q[a] * q[b] * inv_r2 + (a == b ? 2.0 * inv_r : 0.0));
-              ex[k * TM + tid] = hab - hqs[a] * hqs[b] * ihs;
+            for (int bb = a; bb < DIM; ++bb, ++k) {
+              const double hab = sc * (4.0 * q[a] * q[bb] * inv_r2 + (a == bb ? 2.0 * inv_r : 0.0));
+              ex[k * TM + tid] = hab - hqs[a] * hqs[bb] * ihs;
             }
         } else {
           P.hEEinv[i] = 0.0;
@@ -1072,14 +1118,16 @@ __global__ void __launch_bounds__(256, 4) k_elem_plap(PlapParams P) {
 #pragma unroll
           for (int a = 0; a < DIM; ++a)
 #pragma unroll
-            for (int b = a; b < DIM; ++b, ++kk) {
+            for (int bb = a; bb < DIM; ++bb, ++kk) {
               const double hv = h[kk * TM + k];
-              acc += (a == b) ? dr[a] * hv * dc[a] : hv * (dr[a] * dc[b] + dr[b] * dc[a]);
+              acc += (a == bb) ? dr[a] * hv * dc[a] : hv * (dr[a] * dc[bb] + dr[bb] * dc[a]);
             }
         }
         out[t] = acc;
       }
     }
+    __syncthreads();   // the exchange rows and (two tiles later) this input buffer are reused
+    b ^= 1;
   }
   if (MODE == NODE_F01) grid_reduce<4>(red, op4, P.partials, P.ticket, P.red_out);
 }

@@ -44,9 +44,9 @@ static thread_local std::string g_last_error;
 
 // kernel classes for the optional per-class device timing (cfg.profile) and launch statistics
 enum KClass { KC_NODE_F01 = 0, KC_NODE_F2, KC_BLOCKGRAD, KC_BLOCKHESS, KC_GATHER, KC_SPMV, KC_JACOBI, KC_SPGEMM, KC_VEC, KC_COND,
-              KC_DENSE, KC_PCG, KC_ELEM_F01, KC_ELEM_F2, KC_DGEMM, KC_COUNT };
+              KC_DENSE, KC_PCG, KC_ELEM_F01, KC_ELEM_F2, KC_DGEMM, KC_ELEMG_F01, KC_ELEMG_F2, KC_COUNT };
 static const char *kKClassNames[KC_COUNT] = {"node_f01", "node_f2", "blockgrad", "blockhess", "csr_gather", "spmv", "jacobi",
-                                             "spgemm", "vector", "condense", "dense", "pcg_persistent", "elem_f01", "elem_f2", "dgemm_dmma"};
+                                             "spgemm", "vector", "condense", "dense", "pcg_persistent", "elem_f01", "elem_f2", "dgemm_dmma", "elem_generic_f01", "elem_generic_f2"};
 enum { STAGE_F01 = -1, STAGE_F2 = -2, STAGE_SOLVE = -3 };
 #define LAUNCH(kc, ...)   \
   do {                    \
@@ -809,7 +809,8 @@ struct Engine {
     Q.p1 = A.p | 1;
     Q.ES = (A.p * Q.p1) | 1;
     int epb = std::max(1, 256 / A.p);
-    const size_t cap = 216 * 1024;
+    const size_t cap = 216 * 1024, want = 72 * 1024;   // aim at 3 resident CTAs per SM (double-buffered tiles)
+    while (epb > 1 && elem_plap_smem(dim, epb, Q.ES, A.p) > want && epb * A.p > 128) epb = (epb + 1) / 2;
     while (epb > 1 && elem_plap_smem(dim, epb, Q.ES, A.p) > cap) epb = (epb + 1) / 2;
     smem = elem_plap_smem(dim, epb, Q.ES, A.p);
     if (smem > cap) return false;
@@ -857,7 +858,7 @@ struct Engine {
       LAUNCH(KC_ELEM_F01, launch_plap<NODE_F01>(pdim, PQ, grid, smem, s));
     } else if (elem_fused_setup(A, P, A.nD, Q, smem, grid)) {
       Q.gb = A.gb;
-      LAUNCH(KC_ELEM_F01, launch_elem<NODE_F01>(Q, grid, smem, s));
+      LAUNCH(KC_ELEMG_F01, launch_elem<NODE_F01>(Q, grid, smem, s));
     } else {
       LAUNCH(KC_NODE_F01, launch_node<NODE_F01>(P, red_grid(A.n), s));
       ElemParams E = elem_params(A);
@@ -1275,7 +1276,7 @@ void Engine::assemble(Amg &A, System &S, int J, double t, const double *zbase, c
   } else if (elem_fused_setup(A, P, std::max(A.nD, S.nK * (S.nK + 1) / 2), Q, smem, grid)) {
     Q.pl = S.pl;
     Q.Hblk = S.Hblk;
-    LAUNCH(KC_ELEM_F2, launch_elem<NODE_F2>(Q, grid, smem, s));
+    LAUNCH(KC_ELEMG_F2, launch_elem<NODE_F2>(Q, grid, smem, s));
   } else {
     LAUNCH(KC_NODE_F2, launch_node<NODE_F2>(P, red_grid(A.n), s));
     ElemParams E = elem_params(A);

@@ -394,9 +394,9 @@ class Handle:
     def kernel_stats(self, reset=False):
         """{class: (launches, device ms)}; ms are only accumulated while profiling is on."""
         nc = C.c_int32()
-        names = (C.c_char_p * 16)()
-        launches = np.zeros(16, np.int64)
-        ms = np.zeros(16)
+        names = (C.c_char_p * 32)()
+        launches = np.zeros(32, np.int64)
+        ms = np.zeros(32)
         self._check(lib().mgbx_kernel_stats(self._h, int(reset), C.byref(nc), names, _ptr(launches, c_i64p), _ptr(ms)))
         return {names[k].decode(): (int(launches[k]), float(ms[k])) for k in range(nc.value)}
 
