@@ -139,7 +139,7 @@ typedef struct {
                                 when a block does not fit in shared memory) */
   int32_t smoother;          /* V-cycle smoother of the persistent kernel: 1 (default) Chebyshev of degree smoother_sweeps
                                 with diagonal scaling on [lam/cheb_ratio, lam], lam = Gershgorin bound; 0 l1-Jacobi */
-  double cheb_ratio;         /* default 4 */
+  double cheb_ratio;         /* default 8 (sweep in profiles/r01z_smoother_sweep.jsonl) */
 } mgbx_config;
 
 /* options of one mgb_step (src/mgb.jl:16-30; defaults src/mgb.jl:360-363) */

@@ -1493,7 +1493,7 @@ System::PcgDev &Engine::pcg_plan(System &S, int ktop) {
   P.nu = std::max(1, h->cfg.smoother_sweeps);
   P.nu_bottom = 30;
   P.smoother = h->cfg.smoother;
-  P.cheb_ratio = h->cfg.cheb_ratio > 1.0 ? h->cfg.cheb_ratio : 4.0;
+  P.cheb_ratio = h->cfg.cheb_ratio > 1.0 ? h->cfg.cheb_ratio : 8.0;
   P.maxit = h->cfg.pcg_maxit;
   P.rtol2 = h->cfg.pcg_rtol * h->cfg.pcg_rtol;
   for (int q = 0; q < P.nlev; ++q) {
@@ -2159,7 +2159,7 @@ void mgbx_default_config(mgbx_config *c) {
   c->pcg_rtol_final = 1e-15;
   c->fused = 1;
   c->smoother = 1;
-  c->cheb_ratio = 4.0;
+  c->cheb_ratio = 8.0;
 }
 
 void mgbx_default_step_opts(mgbx_step_opts *o, int64_t n) {
