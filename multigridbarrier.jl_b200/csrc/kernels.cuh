@@ -926,10 +926,12 @@ struct PlapParams {
 };
 
 // shared memory: two input buffers (operator blocks + the tile's node inputs, filled by cp.async one tile ahead) + exchange rows
-inline size_t elem_plap_smem(int dim, int epb, int ES, int p) {
+inline size_t elem_plap_smem(int dim, int epb, int ES, int p, bool condensed = true) {
   const size_t tm = (size_t)epb * p;
   const size_t buf = (size_t)dim * epb * ES + (size_t)(4 + dim + 2) * tm;
-  return sizeof(double) * (2 * buf + (size_t)((dim * (dim + 1)) / 2 > dim ? (dim * (dim + 1)) / 2 : dim) * tm);
+  const int nh = (dim * (dim + 1)) / 2;
+  const int nex = condensed ? (nh > dim ? nh : dim) : nh + dim + 1;
+  return sizeof(double) * (2 * buf + (size_t)nex * tm);
 }
 
 __device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
@@ -944,7 +946,9 @@ __device__ __forceinline__ void cp_async_wait() {
 
 // Tiles are software-pipelined: while tile k is evaluated, the operator blocks and node inputs of tile k+1 stream into the
 // other shared-memory buffer with cp.async (LDGSTS), so the evaluation never waits on HBM latency after the first tile.
-template <int MODE, int DIM>
+// COND: the slack is condensed node-locally (fine-level systems); !COND: nothing is eliminated and the four block pairs
+// (u,u), (u,s), (s,u), (s,s) are written (the coarse-level systems of the mgb_step recovery path).
+template <int MODE, int DIM, bool COND>
 __global__ void __launch_bounds__(256, 3) k_elem_plap(PlapParams P) {
   extern __shared__ double esm[];
   constexpr int NH = (DIM * (DIM + 1)) / 2;
@@ -1060,14 +1064,19 @@ __global__ void __launch_bounds__(256, 3) k_elem_plap(PlapParams P) {
           const double sam2 = in ? sam1 / s : safe_pow(s, al - 2.0);
           const double s2am2 = in ? sam1 * sam1 : safe_pow(s, 2.0 * al - 2.0);
           const double hss = sc * (-al * (al - 1.0) * sam2 * inv_r + al * al * s2am2 * inv_r2 + P.mu / (s * s));
-          const double ihs = 1.0 / hss;
-          P.hEEinv[i] = ihs;
-          P.hKE[i] = 0.0;
+          const double ihs = COND ? 1.0 / hss : 0.0;
           double hqs[DIM];
 #pragma unroll
-          for (int a = 0; a < DIM; ++a) {
-            hqs[a] = sc * coef * q[a];
-            P.hKE[i + (int64_t)(a + 1) * P.n] = hqs[a];
+          for (int a = 0; a < DIM; ++a) hqs[a] = sc * coef * q[a];
+          if (COND) {
+            P.hEEinv[i] = ihs;
+            P.hKE[i] = 0.0;
+#pragma unroll
+            for (int a = 0; a < DIM; ++a) P.hKE[i + (int64_t)(a + 1) * P.n] = hqs[a];
+          } else {
+#pragma unroll
+            for (int a = 0; a < DIM; ++a) ex[(NH + a) * TM + tid] = hqs[a];
+            ex[(NH + DIM) * TM + tid] = hss;
           }
           int k = 0;
 #pragma unroll
@@ -1075,14 +1084,16 @@ __global__ void __launch_bounds__(256, 3) k_elem_plap(PlapParams P) {
 #pragma unroll
             for (int bb = a; bb < DIM; ++bb, ++k) {
               const double hab = sc * (4.0 * q[a] * q[bb] * inv_r2 + (a == bb ? 2.0 * inv_r : 0.0));
-              ex[k * TM + tid] = hab - hqs[a] * hqs[bb] * ihs;
+              ex[k * TM + tid] = COND ? hab - hqs[a] * hqs[bb] * ihs : hab;
             }
         } else {
-          P.hEEinv[i] = 0.0;
+          if (COND) {
+            P.hEEinv[i] = 0.0;
 #pragma unroll
-          for (int a = 0; a <= DIM; ++a) P.hKE[i + (int64_t)a * P.n] = 0.0;
+            for (int a = 0; a <= DIM; ++a) P.hKE[i + (int64_t)a * P.n] = 0.0;
+          }
 #pragma unroll
-          for (int k = 0; k < NH; ++k) ex[k * TM + tid] = 0.0;
+          for (int k = 0; k < (COND ? NH : NH + DIM + 1); ++k) ex[k * TM + tid] = 0.0;
         }
       }
     }
@@ -1124,6 +1135,19 @@ __global__ void __launch_bounds__(256, 3) k_elem_plap(PlapParams P) {
             }
         }
         out[t] = acc;
+        if (!COND) {
+          // (u,s): sum_a D_a[c][r] h_as[c];  (s,u): its transpose;  (s,s): diag(h_ss)
+          double us_ = 0.0, su_ = 0.0;
+#pragma unroll
+          for (int a = 0; a < DIM; ++a) {
+            us_ += base[(size_t)a * epb * ES + r * p1 + c] * h[(NH + a) * TM + c];
+            su_ += h[(NH + a) * TM + r] * base[(size_t)a * epb * ES + c * p1 + r];
+          }
+          const int64_t pstride = P.N * (int64_t)pp;
+          out[pstride + t] = us_;
+          out[2 * pstride + t] = su_;
+          out[3 * pstride + t] = (r == c) ? h[(NH + DIM) * TM + r] : 0.0;
+        }
       }
     }
     __syncthreads();   // the exchange rows and (two tiles later) this input buffer are reused

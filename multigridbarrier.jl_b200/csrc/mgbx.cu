@@ -521,12 +521,12 @@ void launch_elem(const ElemFused &Q, unsigned int grid, size_t smem, cudaStream_
 }
 
 // specialised fused kernel of the default problem family (k_elem_plap)
-template <int MODE, int DIM>
+template <int MODE, int DIM, bool COND>
 void launch_plap_inst(const PlapParams &Q, unsigned int grid, size_t smem, cudaStream_t s) {
   static bool attr_done = false;
   static int nsm = 0;
   if (!attr_done) {
-    CK(cudaFuncSetAttribute(k_elem_plap<MODE, DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    CK(cudaFuncSetAttribute(k_elem_plap<MODE, DIM, COND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     int dev = 0;
     CK(cudaGetDevice(&dev));
     CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
@@ -534,15 +534,21 @@ void launch_plap_inst(const PlapParams &Q, unsigned int grid, size_t smem, cudaS
   }
   // persistent tiles: exactly one wave of resident CTAs (grid = SMs x occupancy), never more than the reduction slots
   int occ = 1;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_elem_plap<MODE, DIM>, 256, smem));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_elem_plap<MODE, DIM, COND>, 256, smem));
   const unsigned int wave = (unsigned int)std::min(std::max(1, occ) * nsm, kRedBlocks);
-  k_elem_plap<MODE, DIM><<<std::min(grid, wave), 256, smem, s>>>(Q);
+  k_elem_plap<MODE, DIM, COND><<<std::min(grid, wave), 256, smem, s>>>(Q);
 }
 template <int MODE>
-void launch_plap(int dim, const PlapParams &Q, unsigned int grid, size_t smem, cudaStream_t s) {
-  if (dim == 1) launch_plap_inst<MODE, 1>(Q, grid, smem, s);
-  else if (dim == 2) launch_plap_inst<MODE, 2>(Q, grid, smem, s);
-  else launch_plap_inst<MODE, 3>(Q, grid, smem, s);
+void launch_plap(int dim, bool cond, const PlapParams &Q, unsigned int grid, size_t smem, cudaStream_t s) {
+  if (cond || MODE == NODE_F01) {
+    if (dim == 1) launch_plap_inst<MODE, 1, true>(Q, grid, smem, s);
+    else if (dim == 2) launch_plap_inst<MODE, 2, true>(Q, grid, smem, s);
+    else launch_plap_inst<MODE, 3, true>(Q, grid, smem, s);
+  } else {
+    if (dim == 1) launch_plap_inst<NODE_F2, 1, false>(Q, grid, smem, s);
+    else if (dim == 2) launch_plap_inst<NODE_F2, 2, false>(Q, grid, smem, s);
+    else launch_plap_inst<NODE_F2, 3, false>(Q, grid, smem, s);
+  }
 }
 
 struct Engine {
@@ -801,7 +807,7 @@ struct Engine {
       if (pc.idx[c] != c + 1) return 0;
     return dim;
   }
-  bool plap_setup(Amg &A, int dim, double t, bool use_bw, PlapParams &Q, size_t &smem, unsigned int &grid) {
+  bool plap_setup(Amg &A, int dim, double t, bool use_bw, PlapParams &Q, size_t &smem, unsigned int &grid, bool cond = true) {
     memset(&Q, 0, sizeof(Q));
     Q.n = A.n;
     Q.N = A.N;
@@ -810,9 +816,9 @@ struct Engine {
     Q.ES = (A.p * Q.p1) | 1;
     int epb = std::max(1, 256 / A.p);
     const size_t cap = 216 * 1024, want = 72 * 1024;   // aim at 3 resident CTAs per SM (double-buffered tiles)
-    while (epb > 1 && elem_plap_smem(dim, epb, Q.ES, A.p) > want && epb * A.p > 128) epb = (epb + 1) / 2;
-    while (epb > 1 && elem_plap_smem(dim, epb, Q.ES, A.p) > cap) epb = (epb + 1) / 2;
-    smem = elem_plap_smem(dim, epb, Q.ES, A.p);
+    while (epb > 1 && elem_plap_smem(dim, epb, Q.ES, A.p, cond) > want && epb * A.p > 128) epb = (epb + 1) / 2;
+    while (epb > 1 && elem_plap_smem(dim, epb, Q.ES, A.p, cond) > cap) epb = (epb + 1) / 2;
+    smem = elem_plap_smem(dim, epb, Q.ES, A.p, cond);
     if (smem > cap) return false;
     Q.epb = epb;
     Q.dp = make_fastdiv((unsigned int)A.p);
@@ -855,7 +861,7 @@ struct Engine {
     if (pdim && plap_setup(A, pdim, t, use_bw, PQ, smem, grid)) {
       PQ.gbu = A.gb + (int64_t)A.D_var[0] * A.n;
       PQ.gbs = A.gb + (int64_t)A.D_var[pdim + 1] * A.n;
-      LAUNCH(KC_ELEM_F01, launch_plap<NODE_F01>(pdim, PQ, grid, smem, s));
+      LAUNCH(KC_ELEM_F01, launch_plap<NODE_F01>(pdim, true, PQ, grid, smem, s));
     } else if (elem_fused_setup(A, P, A.nD, Q, smem, grid)) {
       Q.gb = A.gb;
       LAUNCH(KC_ELEMG_F01, launch_elem<NODE_F01>(Q, grid, smem, s));
@@ -1268,11 +1274,16 @@ void Engine::assemble(Amg &A, System &S, int J, double t, const double *zbase, c
   // the specialised kernel needs exactly: s eliminated node-locally, u kept with all of its rows
   const bool plap_ok = pdim && S.nE == 1 && S.kept.size() == 1 && S.kept[0] == A.D_var[0] && S.elim[0] == A.D_var[pdim + 1] &&
                        S.nK == pdim + 1 && S.pl.npairs == 1 && plap_setup(A, pdim, t, true, PQ, smem, grid);
-  if (plap_ok) {
+  // ... or nothing eliminated and the four pairs (u,u), (u,s), (s,u), (s,s) in this order (coarse-level systems)
+  const bool plap_unc = !plap_ok && pdim && S.nE == 0 && S.kept.size() == 2 && S.nK == pdim + 2 && S.pl.npairs == 4 &&
+                        S.pl.va[0] == A.D_var[0] && S.pl.vb[0] == A.D_var[0] && S.pl.va[1] == A.D_var[0] && S.pl.vb[1] == A.D_var[pdim + 1] &&
+                        S.pl.va[2] == A.D_var[pdim + 1] && S.pl.vb[2] == A.D_var[0] && S.pl.va[3] == A.D_var[pdim + 1] &&
+                        S.pl.vb[3] == A.D_var[pdim + 1] && plap_setup(A, pdim, t, true, PQ, smem, grid, false);
+  if (plap_ok || plap_unc) {
     PQ.hEEinv = A.hEEinv;
     PQ.hKE = A.hKE;
     PQ.Hblk = S.Hblk;
-    LAUNCH(KC_ELEM_F2, launch_plap<NODE_F2>(pdim, PQ, grid, smem, s));
+    LAUNCH(KC_ELEM_F2, launch_plap<NODE_F2>(pdim, plap_ok, PQ, grid, smem, s));
   } else if (elem_fused_setup(A, P, std::max(A.nD, S.nK * (S.nK + 1) / 2), Q, smem, grid)) {
     Q.pl = S.pl;
     Q.Hblk = S.Hblk;
