@@ -374,6 +374,7 @@ struct SysLevel {
   // Galerkin gather plans: AT = A*T  and  A_coarse = T'*AT, one fixed-order sliced-ELL gather each
   SellPlan s1, s2;
   bool has_coarser = false, T_identity = false;
+  float *val32 = nullptr;      // FP32 copy of A.val for the preconditioner passes (cfg.precond_fp32)
   double *dinv = nullptr, *diag = nullptr, *lam = nullptr;   // lam: Gershgorin bound of lambda_max(D^-1 A) (device scalar)
   double *b = nullptr, *x = nullptr, *x2 = nullptr, *r = nullptr;   // V-cycle work
   double *dense = nullptr, *dense_inv = nullptr, *dscale = nullptr;
@@ -929,6 +930,7 @@ struct Engine {
     C.ptr = p32;
     C.idx = A.idx;
     C.val = A.val;
+    C.valf = nullptr;
     return C;
   }
   int pcg_persistent(System &S, int ktop, const double *b, double *x);
@@ -1372,6 +1374,10 @@ void Engine::setup_hierarchy(Amg &A, System &S, int ktop) {
     SysLevel &Lv = S.lev[k];
     CK(cudaMemsetAsync(Lv.lam, 0, sizeof(double), s));
     LAUNCH(KC_VEC, k_l1diag<<<nblk(Lv.m), 256, 0, s>>>(Lv.A, Lv.dinv, Lv.diag, (unsigned long long *)Lv.lam));
+    if (h->cfg.precond_fp32) {
+      if (!Lv.val32) Lv.val32 = h->pool.alloc<float>(Lv.A.nnz);
+      LAUNCH(KC_VEC, k_f64_to_f32<<<nblk(Lv.A.nnz), 256, 0, s>>>(Lv.A.nnz, Lv.A.val, Lv.val32));
+    }
   }
   if (S.cut >= 0 && S.cut >= ktop) {
     SysLevel &Lc = S.lev[S.cut];
@@ -1512,6 +1518,7 @@ System::PcgDev &Engine::pcg_plan(System &S, int ktop) {
     PLevel &pl = P.lev[q];
     pl.m = Lv.m;
     pl.A = csr32(Lv.A);
+    pl.A.valf = h->cfg.precond_fp32 ? Lv.val32 : nullptr;
     pl.dinv = Lv.dinv;
     pl.diag = Lv.diag;
     pl.lam = Lv.lam;
@@ -2171,6 +2178,7 @@ void mgbx_default_config(mgbx_config *c) {
   c->fused = 1;
   c->smoother = 1;
   c->cheb_ratio = 8.0;
+  c->precond_fp32 = 0;
 }
 
 void mgbx_default_step_opts(mgbx_step_opts *o, int64_t n) {

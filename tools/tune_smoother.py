@@ -10,7 +10,7 @@ if case.startswith("q1c"):
 else:
     prob = P.assemble(H.amg(G.subdivide(G.fem2d_P1(), int(case))), p=1.5); kw = {}
 base = None
-for cfg in (dict(), dict(cheb_ratio=8.0), dict(cheb_ratio=16.0), dict(smoother_sweeps=3), dict(smoother=0), dict(tail_max=2100)):
+for cfg in (dict(), dict(precond_fp32=1), dict(precond_fp32=1, smoother=0), dict(smoother=0)):
     try:
         for rep in range(2):
             t0 = time.time(); sol = solver.mgb_solve(prob, config=cfg, **kw); dt = time.time() - t0
