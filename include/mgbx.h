@@ -141,7 +141,8 @@ typedef struct {
                                 with diagonal scaling on [lam/cheb_ratio, lam], lam = Gershgorin bound; 0 l1-Jacobi */
   double cheb_ratio;         /* default 8 (sweep in profiles/r01z_smoother_sweep.jsonl) */
   int32_t precond_fp32;      /* 1: the V-cycle (preconditioner) reads FP32 copies of the level matrices (8 instead of 12 bytes per
-                                non-zero); the PCG operator, vectors and all reductions stay FP64.  Default 0 */
+                                non-zero); the PCG operator, vectors and all reductions stay FP64.  0 off, 2 (default) automatic: only when
+                                the top matrix has >= 8 M non-zeros (V-cycle HBM-bound) */
 } mgbx_config;
 
 /* options of one mgb_step (src/mgb.jl:16-30; defaults src/mgb.jl:360-363) */
