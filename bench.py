@@ -207,12 +207,13 @@ def main():
         h2d += sum(T.data.nbytes + T.indices.nbytes * 2 + T.indptr.nbytes * 2 for T in M.T)
     h2d += lprob.f.nbytes + lprob.g.nbytes + sum(pc.A.nbytes + pc.b.nbytes for pc in lprob.Q.pieces)
     d2h = lprob.g.nbytes
-    for k in range(max(1, min(args.steps, 2))):
+    for k in range(1 + max(1, min(args.steps, 3))):      # one untimed warm-up call (first-use costs of a fresh handle), then the timed ones
         barrier()
         t1 = time.time()
         sol_e = solver.mgb_solve(prob, comm=new_comm(), config=dict(device=local_rank))
         barrier()
-        e2e_times.append(time.time() - t1)
+        if k > 0:
+            e2e_times.append(time.time() - t1)
         e2e_create = sol_e["stats"]["create_s"]
     its_e = int(sol_e["SOL_main"]["its"].sum())
 
