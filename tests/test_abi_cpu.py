@@ -70,3 +70,27 @@ def test_bad_arguments_are_reported():
     rc = native.lib().mgbx_plan_pattern(C.byref(Rc), 2, 2, 1, 1, native._ptr(dv, native.c_i32p), C.byref(nnz), None, None)
     assert rc == native.ERR_ARG
     assert b"out of range" in native.lib().mgbx_last_error(None)
+
+
+def test_ctypes_layouts_match_the_c_header(tmp_path):
+    """sizeof / offsetof of every struct that crosses the ABI, computed by the C compiler from include/mgbx.h, against the
+    ctypes mirrors in native.py (guards against silent ABI drift between the header, the library and the binding)."""
+    import subprocess
+    structs = {"mgbx_csr": native.Csr, "mgbx_piece": native.Piece, "mgbx_convex": native.Convex, "mgbx_amg": native.Amg,
+               "mgbx_problem": native.Problem, "mgbx_config": native.Config, "mgbx_step_opts": native.StepOpts,
+               "mgbx_step_result": native.StepResult, "mgbx_scalars_out": native.ScalarsOut, "mgbx_solver_info_t": native.SolverInfo}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "mgbx.h"', 'int main(void) {']
+    for cname, ct in structs.items():
+        lines.append('  printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in ct._fields_:
+            lines.append('  printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ['  return 0;', '}']
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, ct in structs.items():
+        assert int(out[cname]) == C.sizeof(ct), cname
+        for fname, _ in ct._fields_:
+            assert int(out["%s.%s" % (cname, fname)]) == getattr(ct, fname).offset, (cname, fname)
