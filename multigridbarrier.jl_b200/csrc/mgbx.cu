@@ -913,8 +913,7 @@ struct Engine {
     return h->cfg.precond_fp32 == 1 || (h->cfg.precond_fp32 == 2 && !S.lev.empty() && S.lev[0].A.nnz >= 8000000);
   }
   bool use_direct(const System &S, const SysLevel &Lv) const {
-    (void)S;
-    return Lv.m <= h->cfg.dense_direct_max;
+    return S.dense || Lv.m <= h->cfg.dense_direct_max;   // dense (spectral) systems have no hierarchy: always direct
   }
   void assemble(Amg &A, System &S, int J, double t, const double *zbase, const double *x);
   void assemble_dense(Amg &A, System &S, const NodeParams &P);
@@ -969,6 +968,7 @@ struct Engine {
 // every coarser level by Galerkin gather plans.
 // spectral discretisations: one dense "element" (N == 1) with more nodes than a finite element ever has
 inline bool dense_mode(const Amg &A) { return A.N == 1 && A.p > 64; }
+constexpr int kDenseMaxUnknowns = 8192;   // blocked Cholesky: the triangular solve keeps the right-hand side in shared memory (64 KB)
 
 std::unique_ptr<System> build_system(mgbx_handle *h, Amg &A, bool condensed, int ltop) {
   auto S = std::make_unique<System>();
@@ -1056,7 +1056,7 @@ std::unique_ptr<System> build_system(mgbx_handle *h, Amg &A, bool condensed, int
     S->lev.resize(1);
     SysLevel &Lv = S->lev[0];
     const int64_t m = Lv.m;
-    if (m > 4096) throw std::runtime_error("dense (spectral) Newton systems are limited to 4096 unknowns in this build");
+    if (m > kDenseMaxUnknowns) throw std::runtime_error("dense (spectral) Newton systems are limited to 8192 unknowns in this build");
     HostCsr full;
     full.rows = full.cols = m;
     full.ptr.resize(m + 1);
@@ -2220,7 +2220,7 @@ int mgbx_create(const mgbx_problem *prob, const mgbx_config *cfg, mgbx_handle **
   mgbx_handle *h = new mgbx_handle();
   if (cfg) h->cfg = *cfg;
   else mgbx_default_config(&h->cfg);
-  if (h->cfg.dense_direct_max > 4096) h->cfg.dense_direct_max = 4096;
+  if (h->cfg.dense_direct_max > kDenseMaxUnknowns) h->cfg.dense_direct_max = kDenseMaxUnknowns;
   if (h->cfg.coarse_max > kCoarseMaxDense) h->cfg.coarse_max = kCoarseMaxDense;
   if (h->cfg.coarse_max < 0) h->cfg.coarse_max = 0;
   h->cur_rtol2 = h->cfg.pcg_rtol * h->cfg.pcg_rtol;
@@ -2248,6 +2248,7 @@ int mgbx_create(const mgbx_problem *prob, const mgbx_config *cfg, mgbx_handle **
       CK(cudaFuncSetAttribute(k_coarse_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coarse_inverse_smem(kCoarseMaxDense)));
       CK(cudaFuncSetAttribute(k_dense_solve_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dense_solve_small_smem(kCoarseMaxDense)));
       CK(cudaFuncSetAttribute(k_chol_diag_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCholDiagSmem));
+      CK(cudaFuncSetAttribute(k_chol_solve_blocked, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * kDenseMaxUnknowns)));
     }
     CK(cudaEventCreate(&h->ev0));
     CK(cudaEventCreate(&h->ev1));
