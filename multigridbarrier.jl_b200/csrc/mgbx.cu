@@ -618,6 +618,45 @@ struct Engine {
   }
 
   // ---------------------------------------------------------------- sparse helpers
+  // lanes per row of a level matrix inside the persistent kernel (cfg.pcg_lanes); nthr = threads that share the phase,
+  // from_end = distance of the level from the coarsest level of the plan
+  int pcg_lanes(const DevCsr &A, int64_t nthr, int from_end) const {
+    const int mode = h->cfg.pcg_lanes;
+    if (mode == 1 || mode == 2 || mode == 4 || mode == 8 || mode == 16 || mode == 32) return mode;
+    if (mode == -1 || A.rows == 0) return group_for(A);
+    if (const char *env = getenv("MGBX_TUNE_LANES")) {   // tuning hook: comma-separated widths, aligned to the COARSEST plan level
+      std::vector<int> vals;
+      for (const char *c = env; *c;) {
+        vals.push_back(atoi(c));
+        while (*c && *c != ',') ++c;
+        if (*c == ',') ++c;
+      }
+      const int k = (int)vals.size() - 1 - from_end;
+      if (k >= 0) {
+        const int v = vals[k];
+        if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) return v;
+      }
+    }
+    // dependent loads per thread: every pass over the rows costs the row pointer plus one index -> value chain per
+    // batch of 4 unrolled entries; ties go to the wider (better coalesced) mapping
+    const double avg = (double)A.nnz / (double)A.rows;
+    int best = 1;
+    double best_cost = 1e300;
+    const int wide[6] = {1, 2, 4, 8, 16, 32}, narrow[3] = {1, 4, 32};
+    const int *cand = (mode == -2) ? wide : narrow;
+    const int ncand = (mode == -2) ? 6 : 3;
+    for (int c = 0; c < ncand; ++c) {
+      const int G = cand[c];
+      const double passes = std::ceil((double)A.rows * G / (double)nthr);
+      const double iters = std::ceil(avg / G);
+      const double cost = passes * (1.0 + 2.0 * std::ceil(iters / 4.0));
+      if (cost <= best_cost) {
+        best_cost = cost;
+        best = G;
+      }
+    }
+    return best;
+  }
   static int group_for(const DevCsr &A) {
     const double avg = A.rows ? (double)A.nnz / (double)A.rows : 0.0;
     return avg > 48.0 ? 32 : (avg > 6.0 ? 4 : 1);
@@ -1532,7 +1571,7 @@ System::PcgDev &Engine::pcg_plan(System &S, int ktop) {
     pl.x = Lv.x;
     pl.x2 = Lv.x2;
     pl.r = Lv.r;
-    pl.G = Lv.spmv_group;
+    pl.G = pcg_lanes(Lv.A, q < P.nbig ? (int64_t)h->pcg_grid * kPcgThreads : (int64_t)kPcgThreads, P.nlev - 1 - q);
     if (q + 1 < P.nlev) {
       pl.T = csr32(Lv.T);
       pl.Tt = csr32(Lv.Tt);
@@ -2185,6 +2224,7 @@ void mgbx_default_config(mgbx_config *c) {
   c->smoother = 1;
   c->cheb_ratio = 8.0;
   c->precond_fp32 = 2;
+  c->pcg_lanes = 0;
 }
 
 void mgbx_default_step_opts(mgbx_step_opts *o, int64_t n) {

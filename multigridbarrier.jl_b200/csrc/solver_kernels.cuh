@@ -541,7 +541,10 @@ __device__ double ph_cheb_step(const SC &sc, const Csr32 &A, const double *idiag
 #define MGBX_G_DISPATCH(G, CALL) \
   do {                            \
     if ((G) == 32) { constexpr int GG = 32; CALL; } \
+    else if ((G) == 16) { constexpr int GG = 16; CALL; } \
+    else if ((G) == 8) { constexpr int GG = 8; CALL; } \
     else if ((G) == 4) { constexpr int GG = 4; CALL; } \
+    else if ((G) == 2) { constexpr int GG = 2; CALL; } \
     else { constexpr int GG = 1; CALL; } \
   } while (0)
 
