@@ -144,7 +144,8 @@ typedef struct {
                                 non-zero); the PCG operator, vectors and all reductions stay FP64.  0 off, 2 (default) automatic: only when
                                 the top matrix has >= 8 M non-zeros (V-cycle HBM-bound) */
   int32_t pcg_lanes;         /* lanes per matrix row in the persistent kernel's level mat-vecs.  0 (default): per level, the width
-                                in {1, 4, 32} with the shortest dependent-load chain (passes over the rows x loads per pass);
+                                in {1, 4, 32} with the shortest dependent-load chain (passes over the rows x loads per pass) when rows average
+                                <= 16 entries, else by average row length;
                                 -2: the same over {1, 2, 4, 8, 16, 32}; -1: by average row length only; 1 / 2 / 4 / 8 / 16 / 32
                                 forces that width on every level.  (Tuning hook: environment variable MGBX_TUNE_LANES =
                                 comma-separated widths per plan level, the last entry being the coarsest level, overrides modes 0 and -2.) */

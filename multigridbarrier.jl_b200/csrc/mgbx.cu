@@ -640,6 +640,9 @@ struct Engine {
     // dependent loads per thread: every pass over the rows costs the row pointer plus one index -> value chain per
     // batch of 4 unrolled entries; ties go to the wider (better coalesced) mapping
     const double avg = (double)A.nnz / (double)A.rows;
+    // long rows (3-D hexahedra, Galerkin levels of 3-D meshes): one lane per row would stride through more matrix
+    // bytes per warp than L1 holds, so the chain model is only trusted up to 16 entries per row (the measured regime)
+    if (mode == 0 && avg > 16.0) return group_for(A);
     int best = 1;
     double best_cost = 1e300;
     const int wide[6] = {1, 2, 4, 8, 16, 32}, narrow[3] = {1, 4, 32};
