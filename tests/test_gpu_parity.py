@@ -341,6 +341,33 @@ def test_persistent_pcg_matches_multilaunch_pcg(tail_max):
     assert rel(out[1][0], out[0][0]) < 1e-8
 
 
+def test_persistent_pcg_lane_widths_agree():
+    """cfg.pcg_lanes only changes how many lanes share a matrix row inside the persistent kernel (the order of the row
+    sums), never the algorithm: every mode solves the same system to the PCG tolerance, deterministically."""
+    prob = P.assemble(H.amg(G.subdivide(G.fem2d_P1(), 6)), p=1.5)
+    M = prob.M[0]
+    J = len(M.R_fine) - 1
+    m = M.R_fine[J].shape[1]
+    rng = np.random.default_rng(5)
+    s = 1e-3 * rng.normal(size=m)
+    g = rng.normal(size=m)
+    out = []
+    for lanes in (-1, 0, -2, 1, 2, 8, 16, 32):
+        h = native.Handle(prob, dense_direct_max=0, coarse_max=40, tail_max=300, pcg_lanes=lanes, pcg_rtol=1e-11)
+        try:
+            x, its = h.solve_newton_system(0, J, 2.0, s, g)
+            Hm = h.hessian(0, J, 2.0, s)
+            assert np.linalg.norm(Hm @ x - g) <= 1e-9 * np.linalg.norm(g)
+            x2, its2 = h.solve_newton_system(0, J, 2.0, s, g)
+            assert np.array_equal(x, x2) and its == its2
+            out.append((x, its))
+        finally:
+            h.close()
+    for x, its in out[1:]:
+        assert abs(its - out[0][1]) <= 1
+        assert rel(x, out[0][0]) < 1e-8
+
+
 def test_persistent_pcg_uncondensed_and_coarse_levels():
     """Newton systems on coarse levels (the recovery path of mgb_step) and without node-local condensation."""
     prob = P.assemble(H.amg(G.subdivide(G.fem2d_P1(), 5)), p=1.0)
