@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmgbx.so")
 SOURCES = ["mgbx.cu"]
-DEPS = ["mgbx.cu", "kernels.cuh", "node_barrier.cuh", "host_sparse.hpp", os.path.join("..", "..", "include", "mgbx.h")]
+DEPS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".hpp", ".h"))) + [os.path.join("..", "..", "include", "mgbx.h")]
 
 
 def nvcc_path():
