@@ -149,6 +149,10 @@ typedef struct {
                                 -2: the same over {1, 2, 4, 8, 16, 32}; -1: by average row length only; 1 / 2 / 4 / 8 / 16 / 32
                                 forces that width on every level.  (Tuning hook: environment variable MGBX_TUNE_LANES =
                                 comma-separated widths per plan level, the last entry being the coarsest level, overrides modes 0 and -2.) */
+  int32_t lambda_power;      /* > 0: that many power iterations on D^-1 A per level and Newton system (warm-started) replace the
+                                Gershgorin bound of lambda_max in the Chebyshev interval (the bound stays as an upper clamp).  Default 0
+                                (off): measured on CPU only so far (tools/smoother_lab.py: 14-38 % fewer PCG iterations on 3-D
+                                problems, none in 2-D); to be enabled once run on hardware */
 } mgbx_config;
 
 /* options of one mgb_step (src/mgb.jl:16-30; defaults src/mgb.jl:360-363) */

@@ -376,6 +376,7 @@ struct SysLevel {
   bool has_coarser = false, T_identity = false;
   float *val32 = nullptr;      // FP32 copy of A.val for the preconditioner passes (cfg.precond_fp32)
   double *dinv = nullptr, *diag = nullptr, *lam = nullptr;   // lam: Gershgorin bound of lambda_max(D^-1 A) (device scalar)
+  double *pw = nullptr, *pw_nrm = nullptr;   // power-iteration vector (kept across Newton iterations: warm start) and |D^-1 A v|^2 (cfg.lambda_power)
   double *b = nullptr, *x = nullptr, *x2 = nullptr, *r = nullptr;   // V-cycle work
   double *dense = nullptr, *dense_inv = nullptr, *dscale = nullptr;
   int spmv_group = 1;
@@ -618,6 +619,22 @@ struct Engine {
   }
 
   // ---------------------------------------------------------------- sparse helpers
+  // lam <- min(Gershgorin, 1.2 |D^-1 A v|) after `iters` power iterations on D^-1 A, warm-started from the previous Newton
+  // iteration's vector.  The Gershgorin bound overestimates lambda_max by 1.3-2.5x on 3-D (27-point) Hessians, which
+  // misplaces the Chebyshev interval (tools/smoother_lab.py).  Lv.r is free scratch before a solve.
+  void lambda_power(SysLevel &Lv, int iters) {
+    if (!Lv.pw) {
+      Lv.pw = h->pool.alloc<double>(Lv.m);
+      Lv.pw_nrm = h->pool.zeros<double>(1, s);
+      LAUNCH(KC_VEC, k_pw_init<<<nblk(Lv.m), 256, 0, s>>>(Lv.m, Lv.pw));
+    }
+    for (int it = 0; it < iters; ++it) {
+      spmv(Lv.A, Lv.pw, nullptr, 1.0, Lv.r, Lv.spmv_group);
+      LAUNCH(KC_VEC, k_pw_scale_norm<<<red_grid(Lv.m), kRedThreads, 0, s>>>(Lv.m, Lv.diag, Lv.r, h->partials, h->ticket, Lv.pw_nrm));
+      LAUNCH(KC_VEC, k_pw_normalize<<<nblk(Lv.m), 256, 0, s>>>(Lv.m, Lv.r, Lv.pw_nrm, Lv.pw));
+    }
+    LAUNCH(KC_VEC, k_pw_store<<<1, 1, 0, s>>>(Lv.pw_nrm, 1.2, Lv.lam));
+  }
   // lanes per row of a level matrix inside the persistent kernel (cfg.pcg_lanes); nthr = threads that share the phase,
   // from_end = distance of the level from the coarsest level of the plan
   int pcg_lanes(const DevCsr &A, int64_t nthr, int from_end) const {
@@ -1422,6 +1439,7 @@ void Engine::setup_hierarchy(Amg &A, System &S, int ktop) {
     SysLevel &Lv = S.lev[k];
     CK(cudaMemsetAsync(Lv.lam, 0, sizeof(double), s));
     LAUNCH(KC_VEC, k_l1diag<<<nblk(Lv.m), 256, 0, s>>>(Lv.A, Lv.dinv, Lv.diag, (unsigned long long *)Lv.lam));
+    if (h->cfg.lambda_power > 0 && Lv.m > 1) lambda_power(Lv, h->cfg.lambda_power);
     if (precond_fp32(S)) {
       if (!Lv.val32) Lv.val32 = h->pool.alloc<float>(Lv.A.nnz);
       LAUNCH(KC_VEC, k_f64_to_f32<<<nblk(Lv.A.nnz), 256, 0, s>>>(Lv.A.nnz, Lv.A.val, Lv.val32));
@@ -2228,6 +2246,7 @@ void mgbx_default_config(mgbx_config *c) {
   c->cheb_ratio = 8.0;
   c->precond_fp32 = 2;
   c->pcg_lanes = 0;
+  c->lambda_power = 0;
 }
 
 void mgbx_default_step_opts(mgbx_step_opts *o, int64_t n) {

@@ -59,7 +59,7 @@ class Config(C.Structure):
                 ("device", C.c_int32), ("verbose", C.c_int32), ("use_graphs", C.c_int32), ("profile", C.c_int32),
                 ("persistent", C.c_int32), ("tail_max", C.c_int32), ("pcg_rtol_final", C.c_double),
                 ("fused", C.c_int32), ("smoother", C.c_int32), ("cheb_ratio", C.c_double),
-                ("precond_fp32", C.c_int32), ("pcg_lanes", C.c_int32)]
+                ("precond_fp32", C.c_int32), ("pcg_lanes", C.c_int32), ("lambda_power", C.c_int32)]
 
 
 class StepOpts(C.Structure):
