@@ -18,7 +18,7 @@
  *   mgbx_get_z / mgbx_set_z <- device_to_native / warm starts         src/mgb.jl:841
  *   mgbx_destroy       <- mgb_cleanup                                 src/mgb.jl:840
  *   mgbx_barrier_eval, mgbx_hessian_pattern, mgbx_hessian_values, mgbx_solve_newton_system,
- *   mgbx_plan_pattern  <- fine-grained parity hooks for barrier(Q).f0/f1/f2 (src/convex.jl:155-202),
+ *   mgbx_plan_pattern, mgbx_recover_transfer  <- fine-grained parity hooks for barrier(Q).f0/f1/f2 (src/convex.jl:155-202),
  *                         _make_block_assembly_plan (src/BlockMatrices.jl:322-491) and solve (src/utils.jl:142-145)
  *
  * Conventions
@@ -99,10 +99,15 @@ typedef struct {
   const double *const *op_data;  /* nops arrays p x p x N (BlockDiag.data) */
   const int32_t *D_var;    /* nD: state variable of D row k */
   const int32_t *D_op;     /* nD: operator id, -1 = identity */
-  const mgbx_csr *R_fine;  /* L entries; only R_fine[L-1] ((nu*n) x m_L) is read: the coarser ones are
-                              R_fine[l] = R_fine[l+1]*T[l] and may be left zero-initialised */
-  const mgbx_csr *T;       /* L-1 level transfers m_{l+1} x m_l with R_fine[l] = R_fine[l+1]*T[l] */
-  const int64_t *var_offsets;    /* L x (nu+1): first column of variable k at level l */
+  const mgbx_csr *R_fine;  /* L entries, AMG.R_fine of the reference (src/multigrid.jl:278-288).  With T given only
+                              R_fine[L-1] ((nu*n) x m_L) is read: the coarser ones are R_fine[l] = R_fine[l+1]*T[l] and
+                              may be left zero-initialised.  With T == NULL all L entries are read */
+  const mgbx_csr *T;       /* L-1 level transfers m_{l+1} x m_l with R_fine[l] = R_fine[l+1]*T[l], or NULL: the reference
+                              discards them after composing R_fine (src/multigrid.jl:166-170), so the library recovers
+                              them from R_fine[0..L-1] itself (selector rows / matching columns / normal equations,
+                              csrc/host_sparse.hpp recover_transfer; mgbx_recover_transfer is the host-only hook) */
+  const int64_t *var_offsets;    /* L x (nu+1): first column of variable k at level l, or NULL (needs all R_fine[l]):
+                                    read off the block-diagonal structure of R_fine[l] */
   /* multi-GPU element partition (zero / NULL for a single-rank problem): this rank holds a contiguous block of
    * elements; n above is the LOCAL node count */
   int64_t n_global;              /* nodes of the whole mesh (the 1/n of the barrier average, src/convex.jl:155-164) */
@@ -262,6 +267,11 @@ int mgbx_set_profile(mgbx_handle *h, int on);
  * (src/BlockMatrices.jl:344-446) from R (CSR, rows = nu blocks of N elements x p nodes). */
 int mgbx_plan_pattern(const mgbx_csr *R, int64_t N, int32_t p, int32_t nu, int32_t nD,
                       const int32_t *D_var, int64_t *nnz, int64_t *rowptr, int64_t *colind);
+
+/* host-only (no GPU needed): T with R_next * T = R_cur, exactly as mgbx_create recovers the level transfers when
+ * mgbx_amg.T == NULL.  val / rowptr / colind may be NULL to query nnz (rowptr holds R_next->cols + 1 entries). */
+int mgbx_recover_transfer(const mgbx_csr *R_next, const mgbx_csr *R_cur, int64_t *nnz, int64_t *rowptr, int64_t *colind,
+                          double *val);
 
 #ifdef __cplusplus
 }

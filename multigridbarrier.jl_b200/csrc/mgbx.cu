@@ -2115,10 +2115,16 @@ void create_amg(mgbx_handle *h, const mgbx_amg &in, Amg &A) {
   A.w = pool.upload<double>(in.w, in.n, s);
   A.voff.resize(in.L);
   A.m.resize(in.L);
+  if (!in.R_fine) throw ArgError("amg: R_fine missing");
   for (int l = 0; l < in.L; ++l) {
-    A.voff[l].assign(in.var_offsets + (size_t)l * (in.nu + 1), in.var_offsets + (size_t)(l + 1) * (in.nu + 1));
+    // var_offsets == NULL: read the per-variable column blocks off R_fine[l] (what a shim that only sees the reference's
+    // `AMG` struct can provide, src/multigrid.jl:278-288)
+    if (in.var_offsets) A.voff[l].assign(in.var_offsets + (size_t)l * (in.nu + 1), in.var_offsets + (size_t)(l + 1) * (in.nu + 1));
+    else A.voff[l] = derive_var_offsets(in.R_fine[l], in.nu, in.n);
     A.m[l] = A.voff[l][in.nu];
     if (A.voff[l][0] != 0) throw ArgError("amg: var_offsets must start at 0");
+    for (int v = 0; v < in.nu; ++v)
+      if (A.voff[l][v + 1] < A.voff[l][v]) throw ArgError("amg: var_offsets must be non-decreasing");
     if (l == in.L - 1 && (in.R_fine[l].cols != A.m[l] || in.R_fine[l].rows != (int64_t)in.nu * in.n))
       throw ArgError("amg: R_fine dimension mismatch (rows must be nu*n, cols must match var_offsets)");
   }
@@ -2134,9 +2140,14 @@ void create_amg(mgbx_handle *h, const mgbx_amg &in, Amg &A) {
   A.T.resize(A.hT.size());
   A.Tt.resize(A.hT.size());
   for (int l = 0; l + 1 < in.L; ++l) {
-    if (!in.T) throw ArgError("amg: level transfers T are required when L > 1");
-    if (in.T[l].rows != A.m[l + 1] || in.T[l].cols != A.m[l]) throw ArgError("amg: T dimension mismatch");
-    A.hT[l] = csr_from_abi(in.T[l]);
+    if (in.T) {
+      if (in.T[l].rows != A.m[l + 1] || in.T[l].cols != A.m[l]) throw ArgError("amg: T dimension mismatch");
+      A.hT[l] = csr_from_abi(in.T[l]);
+    } else {
+      // the reference discards the level transfers (src/multigrid.jl:166-170): recover them from R_fine[l] = R_fine[l+1] T[l]
+      if (in.R_fine[l].cols != A.m[l] || in.R_fine[l + 1].cols != A.m[l + 1]) throw ArgError("amg: R_fine[l] columns do not match var_offsets");
+      A.hT[l] = recover_transfer(in.R_fine[l + 1], in.R_fine[l]);
+    }
     A.T[l] = upload_csr(pool, A.hT[l], s);
     A.Tt[l] = upload_csr(pool, transpose(A.hT[l]), s);
   }
@@ -2748,6 +2759,19 @@ int mgbx_plan_pattern(const mgbx_csr *R, int64_t N, int32_t p, int32_t nu, int32
     if (rowptr) std::copy(pat.ptr.begin(), pat.ptr.end(), rowptr);
     if (colind)
       for (int64_t k = 0; k < pat.nnz(); ++k) colind[k] = pat.idx[k];
+    return MGBX_OK;
+  });
+}
+
+int mgbx_recover_transfer(const mgbx_csr *R_next, const mgbx_csr *R_cur, int64_t *nnz, int64_t *rowptr, int64_t *colind, double *val) {
+  if (!R_next || !R_cur || !nnz) return MGBX_ERR_ARG;
+  return guarded(nullptr, [&]() -> int {
+    HostCsr T = recover_transfer(*R_next, *R_cur);
+    *nnz = T.nnz();
+    if (rowptr) std::copy(T.ptr.begin(), T.ptr.end(), rowptr);
+    if (colind)
+      for (int64_t k = 0; k < T.nnz(); ++k) colind[k] = T.idx[k];
+    if (val) std::copy(T.val.begin(), T.val.end(), val);
     return MGBX_OK;
   });
 }

@@ -95,7 +95,7 @@ EXPORTS = [
     "mgbx_phase1_init", "mgbx_attach_feasibility", "mgbx_set_feasibility_box", "mgbx_reset_feasibility_state", "mgbx_handoff",
     "mgbx_matched_t", "mgbx_get_z", "mgbx_set_z", "mgbx_set_grids", "mgbx_level_size",
     "mgbx_barrier_eval", "mgbx_hessian_pattern", "mgbx_hessian_values", "mgbx_solve_newton_system",
-    "mgbx_plan_pattern", "mgbx_launch_count", "mgbx_kernel_stats", "mgbx_set_profile", "mgbx_solver_info",
+    "mgbx_plan_pattern", "mgbx_recover_transfer", "mgbx_launch_count", "mgbx_kernel_stats", "mgbx_set_profile", "mgbx_solver_info",
 ]
 
 _lib = None
@@ -149,6 +149,7 @@ def lib():
     L.mgbx_solve_newton_system.argtypes = [H, C.c_int, C.c_int, C.c_double, c_f64p, c_f64p, c_f64p, c_i32p]
     L.mgbx_plan_pattern.argtypes = [C.POINTER(Csr), C.c_int64, C.c_int32, C.c_int32, C.c_int32, c_i32p,
                                     c_i64p, c_i64p, c_i64p]
+    L.mgbx_recover_transfer.argtypes = [C.POINTER(Csr), C.POINTER(Csr), c_i64p, c_i64p, c_i64p, c_f64p]
     L.mgbx_launch_count.argtypes = [H]
     L.mgbx_launch_count.restype = C.c_int64
     L.mgbx_kernel_stats.argtypes = [H, C.c_int, c_i32p, C.POINTER(C.c_char_p), c_i64p, c_f64p]
@@ -208,7 +209,7 @@ class _Keep:
         return Csr(M.shape[0], M.shape[1], self.i64(M.indptr), self.i64(M.indices), self.f64(M.data))
 
 
-def _pack_amg(keep: _Keep, M) -> Amg:
+def _pack_amg(keep: _Keep, M, recover_transfers=False) -> Amg:
     geom = M.geometry
     n, N, p = geom.n, geom.N, geom.V
     names, D_var, D_op = [], [], []
@@ -230,14 +231,22 @@ def _pack_amg(keep: _Keep, M) -> Amg:
     keep.bufs.append(ops)
     L = len(M.R_fine)
     # only R_fine[L-1] crosses the boundary with data: the library composes the coarser ones from T (mgbx.h)
-    Rs = (Csr * L)(*([Csr(R.shape[0], R.shape[1], None, None, None) for R in M.R_fine[:-1]] + [keep.csr(M.R_fine[-1])]))
-    Ts = (Csr * max(1, L - 1))(*[keep.csr(T) for T in M.T])
-    keep.bufs += [Rs, Ts]
-    voff = np.asarray(M.var_offsets, dtype=np.int64).reshape(L, M.nu + 1)
+    if recover_transfers:
+        # what a shim over the UNMODIFIED reference can provide (src/multigrid.jl:278-288: AMG keeps R_fine only):
+        # every R_fine[l], no level transfers, no var_offsets -- the library recovers both (mgbx.h)
+        Rs = (Csr * L)(*[keep.csr(R) for R in M.R_fine])
+        Tp, voffp = None, None
+        keep.bufs += [Rs]
+    else:
+        Rs = (Csr * L)(*([Csr(R.shape[0], R.shape[1], None, None, None) for R in M.R_fine[:-1]] + [keep.csr(M.R_fine[-1])]))
+        Ts = (Csr * max(1, L - 1))(*[keep.csr(T) for T in M.T])
+        keep.bufs += [Rs, Ts]
+        Tp = C.cast(Ts, C.POINTER(Csr))
+        voffp = keep.i64(np.asarray(M.var_offsets, dtype=np.int64).reshape(L, M.nu + 1))
     vl = getattr(M, "var_local", None)
     return Amg(n, N, p, M.nu, M.nD, L, keep.f64(M.w), len(names),
                C.cast(ops, C.POINTER(c_f64p)), keep.i32(D_var), keep.i32(D_op),
-               C.cast(Rs, C.POINTER(Csr)), C.cast(Ts, C.POINTER(Csr)), keep.i64(voff),
+               C.cast(Rs, C.POINTER(Csr)), Tp, voffp,
                int(getattr(M, "n_global", 0)), keep.i32(vl) if vl is not None else None)
 
 
@@ -271,11 +280,12 @@ def default_config(**kw) -> Config:
 class Handle:
     """Device-resident problem (the result of native_to_device in the reference)."""
 
-    def __init__(self, prob, barrier_weights=None, with_feasibility=True, comm=None, **cfg):
+    def __init__(self, prob, barrier_weights=None, with_feasibility=True, comm=None, recover_transfers=False, **cfg):
         L = lib()
         keep = _Keep()
         P = Problem()
-        P.amg[0] = _pack_amg(keep, prob.M[0])
+        self._recover = bool(recover_transfers)
+        P.amg[0] = _pack_amg(keep, prob.M[0], self._recover)
         # the feasibility AMG is attached lazily, only when phase1_init reports that phase I must run
         self._feas_M = prob.M[1] if with_feasibility else None
         self._feas_attached = False
@@ -339,7 +349,7 @@ class Handle:
         if self._feas_M is None:
             raise MgbxError(ERR_ARG, "phase I needed but the problem carries no feasibility AMG")
         keep = _Keep()
-        a = _pack_amg(keep, self._feas_M)
+        a = _pack_amg(keep, self._feas_M, self._recover)
         self._check(lib().mgbx_attach_feasibility(self._h, C.byref(a)))
         self._feas_attached = True
 
@@ -467,3 +477,20 @@ def plan_pattern(R, N, p, nu, D_var):
     if rc != OK:
         raise MgbxError(rc, (lib().mgbx_last_error(None) or b"").decode())
     return ptr, ind
+
+
+def recover_transfer(R_next, R_cur):
+    """Host-only: T (scipy CSR) with R_next @ T = R_cur, as mgbx_create recovers the level transfers when none are given."""
+    keep = _Keep()
+    Rn, Rc = keep.csr(R_next), keep.csr(R_cur)
+    nnz = C.c_int64()
+    rc = lib().mgbx_recover_transfer(C.byref(Rn), C.byref(Rc), C.byref(nnz), None, None, None)
+    if rc != OK:
+        raise MgbxError(rc, (lib().mgbx_last_error(None) or b"").decode())
+    ptr = np.empty(R_next.shape[1] + 1, np.int64)
+    ind = np.empty(nnz.value, np.int64)
+    val = np.empty(nnz.value, np.float64)
+    rc = lib().mgbx_recover_transfer(C.byref(Rn), C.byref(Rc), C.byref(nnz), _ptr(ptr, c_i64p), _ptr(ind, c_i64p), _ptr(val))
+    if rc != OK:
+        raise MgbxError(rc, (lib().mgbx_last_error(None) or b"").decode())
+    return sp.csr_matrix((val, ind, ptr), shape=(R_next.shape[1], R_cur.shape[1]))

@@ -48,6 +48,35 @@ def test_plan_pattern_bit_exact(geom):
             assert np.array_equal(ptr, optr) and np.array_equal(ind, oind)
 
 
+@pytest.mark.parametrize("geom", ["fem1d_5nodes", "fem2d_P2_quickstart", "fem2d_P1_L2", "fem2d_P2_L2", "fem3d_k1_L2", "spectral1d_n5", "spectral2d_n5"])
+def test_level_transfers_recovered_from_R_fine(geom):
+    """The reference keeps only the composed R_fine[l] (src/multigrid.jl:166-170); the library recovers the level transfers
+    with R_fine[l] = R_fine[l+1] T[l] (mgbx_amg.T == NULL).  Checked against the ladder the host mirror retains, for both
+    AMGs (main, feasibility) of every discretisation family: selector rows (FEM) and matching columns (spectral)."""
+    prob = default_problem(geom, 1.0)
+    for M in prob.M:
+        for l in range(len(M.R_fine) - 1):
+            Rn, Rc = sp.csr_matrix(M.R_fine[l + 1]), sp.csr_matrix(M.R_fine[l])
+            T = native.recover_transfer(Rn, Rc)
+            assert T.shape == (Rn.shape[1], Rc.shape[1])
+            assert abs(Rn @ T - Rc).max() <= 1e-13 * max(1.0, abs(Rc).max())
+            d = abs(T - sp.csr_matrix(M.T[l]))
+            assert (d.max() if d.nnz else 0.0) <= 1e-13
+
+
+def test_level_transfer_recovery_fallbacks_and_errors():
+    rng = np.random.default_rng(0)
+    # no selector rows, no matching columns (a smoothed-aggregation-like prolongation): dense normal equations
+    Rn = sp.random(60, 12, density=0.5, random_state=1, format="csr") + sp.csr_matrix(np.ones((60, 12)) * 0.01)
+    T0 = sp.random(12, 5, density=0.4, random_state=2, format="csr")
+    T = native.recover_transfer(sp.csr_matrix(Rn), sp.csr_matrix(Rn @ T0))
+    assert abs(T - T0).max() < 1e-10
+    # a coarse space that is not nested in the fine one is refused
+    with pytest.raises(native.MgbxError) as e:
+        native.recover_transfer(sp.csr_matrix(Rn), sp.csr_matrix(rng.normal(size=(60, 3))))
+    assert e.value.code == native.ERR_ARG and "nested" in str(e.value)
+
+
 def test_no_gpu_is_a_loud_error():
     import torch
     if torch.cuda.is_available():
