@@ -16,6 +16,7 @@
  *   mgbx_handoff       <- z2 = SOL_feas.z[1:len]                      src/mgb.jl:566
  *   mgbx_matched_t     <- _matched_t                                  src/mgb.jl:307-330
  *   mgbx_get_z / mgbx_set_z <- device_to_native / warm starts         src/mgb.jl:841
+ *   mgbx_get_z_unfinalized  <- SOL.z_unfinalized                      src/mgb.jl:76-80
  *   mgbx_destroy       <- mgb_cleanup                                 src/mgb.jl:840
  *   mgbx_barrier_eval, mgbx_hessian_pattern, mgbx_hessian_values, mgbx_solve_newton_system,
  *   mgbx_plan_pattern, mgbx_recover_transfer  <- fine-grained parity hooks for barrier(Q).f0/f1/f2 (src/convex.jl:155-202),
@@ -158,6 +159,10 @@ typedef struct {
                                 Gershgorin bound of lambda_max in the Chebyshev interval (the bound stays as an upper clamp).  Default 0
                                 (off): measured on CPU only so far (tools/smoother_lab.py: 14-38 % fewer PCG iterations on 3-D
                                 problems, none in 2-D); to be enabled once run on hardware */
+  double pcg_fail_rtol;      /* a PCG solve that breaks down, or ends (stagnation / pcg_maxit) with |r|/|b| above this, is a FAILED
+                                solve: the Newton run reports "not converged" (as a failed factorisation would in the reference,
+                                src/utils.jl:142-145) instead of continuing with an under-converged direction.  Default 1e-5: Newton
+                                counts are unchanged down to 1e-7 and within +-1 at 1e-6 (tools/inexact_newton_lab.py) */
 } mgbx_config;
 
 /* options of one mgb_step (src/mgb.jl:16-30; defaults src/mgb.jl:360-363) */
@@ -182,6 +187,8 @@ typedef struct {
   double inc;                     /* last Newton decrement squared */
   int32_t f01_evals, f2_evals, linear_solves, pcg_iters;
   double ms_f01, ms_f2, ms_solve; /* device time (CUDA events) spent per stage */
+  int32_t solve_failures;         /* Newton runs abandoned because the linear solve failed (see pcg_fail_rtol) */
+  int32_t its_finalize;           /* the part of its[L-1] spent in the finalize pass (the reference adds it into its[L], src/mgb.jl:76-80) */
 } mgbx_step_result;
 
 typedef struct {
@@ -229,6 +236,8 @@ int mgbx_matched_t(mgbx_handle *h, double t_default, double *t_out, double *tsta
 /* state I/O: z is the stacked state vector, length nu*n of the selected AMG */
 int mgbx_get_z(mgbx_handle *h, int which, double *z_host);
 int mgbx_set_z(mgbx_handle *h, int which, const double *z_host);
+/* the state of the last successful mgbx_step BEFORE its finalize pass (SOL.z_unfinalized, src/mgb.jl:76-80) */
+int mgbx_get_z_unfinalized(mgbx_handle *h, int which, double *z_host);
 /* replace the cost / boundary-data grids in place (parabolic_solve re-assembly, src/Parabolic.jl:162-167) */
 int mgbx_set_grids(mgbx_handle *h, const double *f_grid, const double *g_grid);
 

@@ -31,6 +31,7 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-DNDEBUG", "-lineinfo", "-std=c++17",
+           "-Xptxas", "--split-compile=0",          # ptxas compiles the kernels of the one translation unit on all host cores
            "-shared", "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "-cudart", "static",
            "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:

@@ -418,7 +418,7 @@ struct Amg {
   int64_t n = 0, N = 0;
   int p = 0, nu = 0, nD = 0, L = 0, nops = 0;
   int D_var[MGBX_MAX_ND], D_op[MGBX_MAX_ND];
-  double *w = nullptr, *f = nullptr, *bw = nullptr, *z = nullptr, *zsave = nullptr, *zinit = nullptr;
+  double *w = nullptr, *f = nullptr, *bw = nullptr, *z = nullptr, *zsave = nullptr, *zinit = nullptr, *zunfin = nullptr;
   const double *ops[MGBX_MAX_OPS];
   HostCsr hRL;
   std::vector<HostCsr> hT;
@@ -480,9 +480,12 @@ struct mgbx_handle {
   double dgemm_flops = 0.0;   // FP64 tensor-core flops issued so far (spectral path)
   double cur_rtol2 = 1e-22;
   int cur_window = 25;       // PCG stagnation window (iterations without a new best residual)
+  int last_solve_status = 1;       // 1 converged / direct, 2 stagnated above the tolerance, 3 iteration limit, -1 breakdown
+  double last_solve_rel = 0.0;     // final relative residual |r| / |b| of the last PCG solve (0 for a direct solve)
   // multi-GPU
   int rank = 0, nranks = 1;
   void *comm = nullptr;
+  int device = -1;           // CUDA device ordinal the handle lives on (made current at every ABI entry point)
 };
 
 namespace {
@@ -1634,6 +1637,8 @@ int Engine::pcg_persistent(System &S, int ktop, const double *b, double *x) {
   sync();
   const int it = (int)h->hscal[8];
   const double status = h->hscal[10];
+  h->last_solve_status = (int)status;
+  h->last_solve_rel = (h->hscal[11] > 0.0) ? std::sqrt(h->hscal[9] / h->hscal[11]) : 0.0;
   if (x != S.pc_x) copy(x, S.pc_x, m);
   return status < 0 ? -std::max(it, 1) : it;
 }
@@ -1653,6 +1658,8 @@ int Engine::pcg(System &S, int ktop, const double *b, double *x) {
   CK(cudaMemcpyAsync(h->hscal + 8, scal, sizeof(double) * 5, cudaMemcpyDeviceToHost, s));
   sync();
   const double bb = h->hscal[10];
+  h->last_solve_status = 1;
+  h->last_solve_rel = 0.0;
   if (!(bb > 0.0) || !std::isfinite(bb)) {
     zero(x, m);
     return 0;
@@ -1703,21 +1710,27 @@ int Engine::pcg(System &S, int ktop, const double *b, double *x) {
       status = -1;
       break;
     }
+    h->last_solve_rel = std::sqrt(rr / bb);
     if (rr <= target) break;
     if (rr < best * 0.999) {
       best = rr;
       since_best = 0;
     } else if (++since_best >= h->cur_window) {
-      break;   // stagnation at the attainable accuracy
+      status = 2;   // stagnation at the attainable accuracy
+      break;
     }
   }
+  if (status == 1 && it >= h->cfg.pcg_maxit && h->last_solve_rel * h->last_solve_rel > h->cur_rtol2) status = 3;
+  h->last_solve_status = status;
   copy(x, S.pc_x, m);
-  return status * it;
+  return (status < 0 ? -1 : 1) * it;
 }
 
 int Engine::solve_compact(System &S, int ktop, const double *b, double *x) {
   SysLevel &Lv = S.lev[ktop];
   if (use_direct(S, Lv)) {
+    h->last_solve_status = 1;
+    h->last_solve_rel = 0.0;
     const bool small = Lv.m <= kCoarseMaxDense;
     auto apply = [&](const double *rhs, double *out) {
       if (small) LAUNCH(KC_DENSE, k_dense_solve_small<<<1, 1024, dense_solve_small_smem((int)Lv.m), s>>>(Lv.A, rhs, out, nullptr));
@@ -1824,6 +1837,17 @@ Engine::NewtonOut Engine::newton(Amg &A, int J, double t, int maxit, int stop_ki
     out.inc = inc;
     if (h->cfg.verbose > 1)
       fprintf(stderr, "[mgbx] newton J=%d m=%lld k=%d y=%.17g |g|=%.6g lam2=%.6g pcg=%d t=%g\n", J, (long long)m, k, y, gnorm, inc, pit, t);
+    // An iterative solve that broke down or stopped far from the requested residual is a FAILED solve, as a failed
+    // factorisation is for the reference's direct `H \\ g` (src/utils.jl:142-145): for a CG iterate g.x_k <= g.H^-1 g, so an
+    // under-converged direction under-estimates the Newton decrement and could end the iteration early with a wrong z.
+    // The Newton run is reported as not converged; mgb_core then shrinks kappa (or phase I grows the box).
+    if (h->last_solve_status < 0 || h->last_solve_rel > h->cfg.pcg_fail_rtol) {
+      if (h->cfg.verbose > 0)
+        fprintf(stderr, "[mgbx] newton J=%d m=%lld k=%d: linear solve failed (status %d, |r|/|b| = %.3g after %d PCG iterations)\n", J, (long long)m, k,
+                h->last_solve_status, h->last_solve_rel, pit < 0 ? -pit : pit);
+      if (h->res) h->res->solve_failures++;
+      break;
+    }
     if (!dir_finite) {
       if (h->cfg.verbose > 0)
         fprintf(stderr, "[mgbx] newton J=%d m=%lld k=%d: non-finite direction (g.d=%g |d|^2=%g non-finite entries=%g, pcg=%d, |r|^2=%g |b|^2=%g)\n", J,
@@ -1965,8 +1989,11 @@ int Engine::step(int which, double t, const mgbx_step_opts &o, mgbx_step_result 
     return dac(j, jmid) && dac(jmid, J);
   };
   bool converged = dac(0, L);
+  copy(A.zunfin, A.z, (int64_t)A.nu * A.n);   // SOL.z_unfinalized (mgb.jl:76-80)
   if (o.finalize && status == MGBX_OK) {
+    const int before = r->its[L - 1];
     const bool foo = eta(L - 1, L, 0, 0.0, o.finalize_theta, o.maxit);
+    r->its_finalize = r->its[L - 1] - before;   // bookkeeping: the reference adds the finalize pass into its[L]
     converged = converged && foo;
   }
   r->converged = converged ? 1 : 0;
@@ -2156,6 +2183,7 @@ void create_amg(mgbx_handle *h, const mgbx_amg &in, Amg &A) {
   A.z = pool.zeros<double>(nun, s);
   A.zsave = pool.zeros<double>(nun, s);
   A.zinit = pool.zeros<double>(nun, s);
+  A.zunfin = pool.zeros<double>(nun, s);
   A.zf = pool.zeros<double>(nun, s);
   A.gb = pool.zeros<double>(nun, s);
   A.G = pool.zeros<double>((size_t)in.n * in.nD, s);
@@ -2210,6 +2238,8 @@ void attach_feasibility(mgbx_handle *h, const mgbx_amg &a1) {
 
 int guarded(mgbx_handle *h, const std::function<int()> &fn) {
   try {
+    // several handles (or torch) may have changed the calling thread's current device since this handle was created
+    if (h && h->device >= 0) CK(cudaSetDevice(h->device));
     return fn();
   } catch (const ArgError &e) {
     if (h) h->err = e.what();
@@ -2258,6 +2288,7 @@ void mgbx_default_config(mgbx_config *c) {
   c->precond_fp32 = 2;
   c->pcg_lanes = 0;
   c->lambda_power = 0;
+  c->pcg_fail_rtol = 1e-5;
 }
 
 void mgbx_default_step_opts(mgbx_step_opts *o, int64_t n) {
@@ -2304,6 +2335,7 @@ int mgbx_create(const mgbx_problem *prob, const mgbx_config *cfg, mgbx_handle **
       throw std::runtime_error("CUDA device required: libmgbx has no CPU fallback (cudaGetDeviceCount: " +
                                std::string(cudaGetErrorString(e)) + ")");
     if (h->cfg.device >= 0) CK(cudaSetDevice(h->cfg.device));
+    CK(cudaGetDevice(&h->device));
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     h->pool.stream = h->stream;
     {
@@ -2353,8 +2385,16 @@ int mgbx_create(const mgbx_problem *prob, const mgbx_config *cfg, mgbx_handle **
   return MGBX_OK;
 }
 
+// The communicator is process-wide: creating one costs about a second, so handles share it.  id != NULL creates
+// (or replaces) it; id == NULL reuses the existing one for the same (rank, nranks).
+static void *g_comm = nullptr;
+static int g_comm_rank = -1, g_comm_nranks = 0;
+static int g_comm_users = 0;   // live handles holding g_comm: it is neither replaced nor destroyed under them
+
 void mgbx_destroy(mgbx_handle *h) {
   if (!h) return;
+  if (h->device >= 0) cudaSetDevice(h->device);
+  if (h->comm && h->comm == g_comm && g_comm_users > 0) --g_comm_users;
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (int w = 0; w < 2; ++w)
     for (System *S : {h->amg[w].sys_cond.get(), h->amg[w].sys_coarse.get(), h->amg[w].sys_hook.get()})
@@ -2383,10 +2423,6 @@ int mgbx_nccl_unique_id(char id[128]) {
   });
 }
 
-// The communicator is process-wide: creating one costs about a second, so handles share it.  id != NULL creates
-// (or replaces) it; id == NULL reuses the existing one for the same (rank, nranks).
-static void *g_comm = nullptr;
-static int g_comm_rank = -1, g_comm_nranks = 0;
 
 int mgbx_comm_init(mgbx_handle *h, int rank, int nranks, const char id[128]) {
   if (!h || nranks < 1 || rank < 0 || rank >= nranks) return MGBX_ERR_ARG;
@@ -2400,6 +2436,10 @@ int mgbx_comm_init(mgbx_handle *h, int rank, int nranks, const char id[128]) {
       memcpy(u.internal, id, 128);
       void *comm = nullptr;
       NCK(nccl_api().CommInitRank(&comm, nranks, u, rank));
+      if (g_comm && g_comm_users > 0) {
+        nccl_api().CommDestroy(comm);
+        throw ArgError("mgbx_comm_init: live handles still use the process-wide communicator; destroy them before passing a new NCCL id");
+      }
       if (g_comm) nccl_api().CommDestroy(g_comm);
       g_comm = comm;
       g_comm_rank = rank;
@@ -2408,6 +2448,7 @@ int mgbx_comm_init(mgbx_handle *h, int rank, int nranks, const char id[128]) {
       throw ArgError("mgbx_comm_init: no process-wide communicator for this (rank, nranks); pass an NCCL id first");
     }
     h->comm = g_comm;
+    ++g_comm_users;
     h->rank = rank;
     h->nranks = nranks;
     return MGBX_OK;
@@ -2415,6 +2456,10 @@ int mgbx_comm_init(mgbx_handle *h, int rank, int nranks, const char id[128]) {
 }
 
 int mgbx_comm_finalize(void) {
+  if (g_comm && g_comm_users > 0) {
+    g_last_error = "mgbx_comm_finalize: live handles still use the communicator";
+    return MGBX_ERR_ARG;
+  }
   if (g_comm) nccl_api().CommDestroy(g_comm);
   g_comm = nullptr;
   g_comm_rank = -1;
@@ -2542,6 +2587,16 @@ int mgbx_get_z(mgbx_handle *h, int which, double *z_host) {
   return guarded(h, [&]() -> int {
     Amg &A = h->amg[which];
     CK(cudaMemcpyAsync(z_host, A.z, sizeof(double) * A.nu * A.n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MGBX_OK;
+  });
+}
+
+int mgbx_get_z_unfinalized(mgbx_handle *h, int which, double *z_host) {
+  if (!h || !z_host || which < 0 || which > 1) return MGBX_ERR_ARG;
+  return guarded(h, [&]() -> int {
+    Amg &A = h->amg[which];
+    CK(cudaMemcpyAsync(z_host, A.zunfin, sizeof(double) * A.nu * A.n, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return MGBX_OK;
   });

@@ -351,7 +351,7 @@ struct PcgPlan {
   const double *b;
   double *partials;      // 3 x kPcgMaxGrid
   unsigned int *bar;
-  double *out;           // [0] iterations, [1] |r|^2, [2] status (1 converged/stagnated, -1 breakdown), [3] |b|^2
+  double *out;           // [0] iterations, [1] |r|^2, [2] status (1 converged, 2 stagnated above the tolerance, 3 iteration limit, -1 breakdown), [3] |b|^2
 };
 
 __device__ __forceinline__ void grid_barrier(unsigned int *bar) {
@@ -803,9 +803,11 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_persistent(const PcgPlan
         best = rr;
         since_best = 0;
       } else if (++since_best >= stall_window) {
-        break;   // stagnation at the attainable accuracy
+        status = 2.0;   // stagnation at the attainable accuracy (above the requested tolerance)
+        break;
       }
     }
+    if (status == 1.0 && rr > target) status = 3.0;   // iteration limit
   }
   if (tid == 0) {
     P.out[0] = (double)it;

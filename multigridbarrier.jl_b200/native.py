@@ -59,7 +59,8 @@ class Config(C.Structure):
                 ("device", C.c_int32), ("verbose", C.c_int32), ("use_graphs", C.c_int32), ("profile", C.c_int32),
                 ("persistent", C.c_int32), ("tail_max", C.c_int32), ("pcg_rtol_final", C.c_double),
                 ("fused", C.c_int32), ("smoother", C.c_int32), ("cheb_ratio", C.c_double),
-                ("precond_fp32", C.c_int32), ("pcg_lanes", C.c_int32), ("lambda_power", C.c_int32)]
+                ("precond_fp32", C.c_int32), ("pcg_lanes", C.c_int32), ("lambda_power", C.c_int32),
+                ("pcg_fail_rtol", C.c_double)]
 
 
 class StepOpts(C.Structure):
@@ -73,7 +74,8 @@ class StepResult(C.Structure):
     _fields_ = [("converged", C.c_int32), ("its", C.c_int32 * MAX_LEVELS), ("y", C.c_double),
                 ("gnorm", C.c_double), ("inc", C.c_double), ("f01_evals", C.c_int32),
                 ("f2_evals", C.c_int32), ("linear_solves", C.c_int32), ("pcg_iters", C.c_int32),
-                ("ms_f01", C.c_double), ("ms_f2", C.c_double), ("ms_solve", C.c_double)]
+                ("ms_f01", C.c_double), ("ms_f2", C.c_double), ("ms_solve", C.c_double),
+                ("solve_failures", C.c_int32), ("its_finalize", C.c_int32)]
 
 
 class ScalarsOut(C.Structure):
@@ -93,7 +95,7 @@ EXPORTS = [
     "mgbx_create", "mgbx_destroy", "mgbx_last_error", "mgbx_step", "mgbx_scalars",
     "mgbx_nccl_unique_id", "mgbx_comm_init", "mgbx_comm_finalize",
     "mgbx_phase1_init", "mgbx_attach_feasibility", "mgbx_set_feasibility_box", "mgbx_reset_feasibility_state", "mgbx_handoff",
-    "mgbx_matched_t", "mgbx_get_z", "mgbx_set_z", "mgbx_set_grids", "mgbx_level_size",
+    "mgbx_matched_t", "mgbx_get_z", "mgbx_get_z_unfinalized", "mgbx_set_z", "mgbx_set_grids", "mgbx_level_size",
     "mgbx_barrier_eval", "mgbx_hessian_pattern", "mgbx_hessian_values", "mgbx_solve_newton_system",
     "mgbx_plan_pattern", "mgbx_recover_transfer", "mgbx_launch_count", "mgbx_kernel_stats", "mgbx_set_profile", "mgbx_solver_info",
 ]
@@ -140,6 +142,7 @@ def lib():
     L.mgbx_matched_t.argtypes = [H, C.c_double, c_f64p, c_f64p]
     L.mgbx_get_z.argtypes = [H, C.c_int, c_f64p]
     L.mgbx_set_z.argtypes = [H, C.c_int, c_f64p]
+    L.mgbx_get_z_unfinalized.argtypes = [H, C.c_int, c_f64p]
     L.mgbx_set_grids.argtypes = [H, c_f64p, c_f64p]
     L.mgbx_level_size.argtypes = [H, C.c_int, C.c_int]
     L.mgbx_level_size.restype = C.c_int64
@@ -301,7 +304,11 @@ class Handle:
             raise MgbxError(rc, (L.mgbx_last_error(None) or b"").decode())
         if comm is not None:
             rank, world, uid = comm
-            self._check(L.mgbx_comm_init(self._h, int(rank), int(world), uid))
+            try:
+                self._check(L.mgbx_comm_init(self._h, int(rank), int(world), uid))
+            except Exception:
+                self.close()      # the device handle exists already: do not leak it
+                raise
         self.n = n
         self.nu = [prob.M[0].nu, prob.M[1].nu if prob.M[1] is not None else 0]
         self.nD = [prob.M[0].nD, prob.M[1].nD if prob.M[1] is not None else 0]
@@ -379,6 +386,11 @@ class Handle:
     def get_z(self, which=MAIN):
         z = np.empty(self.nu[which] * self.n)
         self._check(lib().mgbx_get_z(self._h, which, _ptr(z)))
+        return z
+
+    def get_z_unfinalized(self, which=MAIN):
+        z = np.empty(self.nu[which] * self.n)
+        self._check(lib().mgbx_get_z_unfinalized(self._h, which, _ptr(z)))
         return z
 
     def set_z(self, z, which=MAIN):

@@ -75,6 +75,7 @@ def mgb_core(h: native.Handle, which, L, tol=math.sqrt(EPS), t=0.1, maxit=10000,
     target = 1.0 / tol
     kappa0 = kappa
     its, ts, kappas, cdz, times = [], [], [], [], []
+    fin = [0]                 # Newton iterations of the finalize pass of the last accepted step
     t_begin = time.time()
 
     def opts(tt, initial):
@@ -92,11 +93,14 @@ def mgb_core(h: native.Handle, which, L, tol=math.sqrt(EPS), t=0.1, maxit=10000,
             stats["f2_evals"] += r.f2_evals
             stats["linear_solves"] += r.linear_solves
             stats["pcg_iters"] += r.pcg_iters
+            stats["solve_failures"] = stats.get("solve_failures", 0) + r.solve_failures
             stats["ms_f01"] += r.ms_f01
             stats["ms_f2"] += r.ms_f2
             stats["ms_solve"] += r.ms_solve
         if rc == native.NON_FINITE:
             raise FloatingPointError("newton: non-finite objective, gradient or direction at t=%g" % tt)
+        if rc == native.OK:
+            fin[0] = int(r.its_finalize)
         return rc == native.OK, np.array(r.its[:L], dtype=np.int64)
 
     ok, it0 = run(t, True)
@@ -136,7 +140,7 @@ def mgb_core(h: native.Handle, which, L, tol=math.sqrt(EPS), t=0.1, maxit=10000,
                                     % (t, k, kappa, tol, maxit), code)
     return dict(its=np.stack(its, axis=1), ts=np.array(ts), kappas=np.array(kappas),
                 c_dot_Dz=np.array(cdz), times=np.array(times), t_begin=t_begin,
-                t_elapsed=time.time() - t_begin)
+                t_elapsed=time.time() - t_begin, its_finalize=fin[0])
 
 
 def mgb_driver(h: native.Handle, M, t=0.1, t_feasibility=None, feasibility_Rmax=1.0 / math.sqrt(EPS),
@@ -217,6 +221,7 @@ def mgb_driver(h: native.Handle, M, t=0.1, t_feasibility=None, feasibility_Rmax=
         t = min(t, tm)
     SOL_main = mgb_core(h, native.MAIN, L1, t=t, finalize=finalize, log=log, stats=stats, **rest)
     z = h.get_z(native.MAIN).reshape(ncomp, n_loc).T.copy()
+    SOL_main["z_unfinalized"] = h.get_z_unfinalized(native.MAIN).reshape(ncomp, n_loc).T.copy()   # src/mgb.jl:76-80
     return dict(z=z, SOL_feasibility=SOL_feas, SOL_main=SOL_main)
 
 
@@ -247,7 +252,7 @@ def mgb_solve(prob, barrier_nodes=None, config=None, log=None, handle=None, comm
     t0 = time.time()
     h = handle if handle is not None else native.Handle(prob, barrier_weights=bw, comm=comm, **(config or {}))
     t_create = time.time() - t0
-    stats = dict(f01_evals=0, f2_evals=0, linear_solves=0, pcg_iters=0, ms_f01=0.0, ms_f2=0.0, ms_solve=0.0)
+    stats = dict(f01_evals=0, f2_evals=0, linear_solves=0, pcg_iters=0, solve_failures=0, ms_f01=0.0, ms_f2=0.0, ms_solve=0.0)
     try:
         l0 = h.launch_count()
         sol = mgb_driver(h, prob.M, log=_log, stats=stats, **kw)

@@ -630,10 +630,13 @@ def mgb_step(Q, M, z, c, maxit, max_newton, line_search, stopping_criterion, fin
 
     converged = divide_and_conquer(lambda j, J: eta(j, J, stopping_criterion, mn(j, J), line_search), 0, L)
     z_unfinalized = state["z"]
+    its_finalize = 0
     if finalize is not None:
+        before = int(its[L - 1])
         foo = eta(L - 1, L, finalize, maxit, line_search)
+        its_finalize = int(its[L - 1]) - before        # bookkeeping only: the reference adds the finalize pass into its[L]
         converged = converged and foo
-    return dict(z=state["z"], z_unfinalized=z_unfinalized, its=its, converged=converged)
+    return dict(z=state["z"], z_unfinalized=z_unfinalized, its=its, converged=converged, its_finalize=its_finalize)
 
 
 def c_dot_Dz(M, c, z):
@@ -666,6 +669,7 @@ def mgb_core(Q, M, z, c, tol=math.sqrt(EPS), t=0.1, maxit=10000, kappa=10.0, ear
     ts.append(t)
     z = SOL["z"]
     z_unfinalized = SOL["z_unfinalized"]
+    its_finalize = SOL["its_finalize"]
     cdz.append(c_dot_Dz(M, c, z))
     while t < target and kappa > 1 and k < maxit and not early_stop(z, t):
         k += 1
@@ -679,6 +683,7 @@ def mgb_core(Q, M, z, c, tol=math.sqrt(EPS), t=0.1, maxit=10000, kappa=10.0, ear
                     kappa = min(kappa0, kappa ** 2)
                 z = SOL["z"]
                 z_unfinalized = SOL["z_unfinalized"]
+                its_finalize = SOL["its_finalize"]
                 t = t1
                 break
             kappa = math.sqrt(kappa)
@@ -692,7 +697,7 @@ def mgb_core(Q, M, z, c, tol=math.sqrt(EPS), t=0.1, maxit=10000, kappa=10.0, ear
         raise MGBConvergenceFailure("Convergence failure in mgb_solve at t=%g, k=%d, kappa=%g, tol=%g, maxit=%d."
                                     % (t, k, kappa, tol, maxit), code)
     return dict(z=z, z_unfinalized=z_unfinalized, c=c, its=np.stack(its, axis=1), ts=np.array(ts),
-                kappas=np.array(kappas), c_dot_Dz=np.array(cdz))
+                kappas=np.array(kappas), c_dot_Dz=np.array(cdz), its_finalize=its_finalize)
 
 
 def matched_t(Q, M, z, c, t_default, barrier_weights=None, log=None):

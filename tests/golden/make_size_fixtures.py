@@ -12,7 +12,8 @@ the north-star's gates need:
     z           final state (n x nu), possibly strided (every `stride`-th node) to keep the file small
     z_unfin     the state before the finalize pass (SOL.z_unfinalized, src/mgb.jl:76-80), same stride
     znorm, znorm_unfin   full-vector L2 norms
-    its         Newton iterations per level and barrier step (SOL_main.its)
+    its         Newton iterations per level and barrier step (SOL_main.its); its_finalize = the part of its[L, end] spent in
+                the finalize pass (bookkeeping added to the oracle; the reference adds it into its[L])
     ts, kappas, c_dot_Dz  the t-schedule and the objective history (final objective = c_dot_Dz[-1])
     meta        JSON: case description, sizes, oracle wall time, outcome ("ok" or the MGBConvergenceFailure code)
 
@@ -54,7 +55,8 @@ def _solve_case(build, stride=1, **kw):
         nu = sol["z"].shape[1]
         zu = S["z_unfinalized"].reshape(nu, n).T
         out.update(z=sol["z"][::stride].copy(), z_unfin=zu[::stride].copy(), znorm=float(np.linalg.norm(sol["z"])),
-                   znorm_unfin=float(np.linalg.norm(zu)), its=S["its"], ts=S["ts"], kappas=S["kappas"], c_dot_Dz=S["c_dot_Dz"])
+                   znorm_unfin=float(np.linalg.norm(zu)), its=S["its"], ts=S["ts"], kappas=S["kappas"], c_dot_Dz=S["c_dot_Dz"],
+                   its_finalize=S["its_finalize"])
         if sol["SOL_feasibility"] is not None:
             F = sol["SOL_feasibility"]
             out.update(feas_its=F["its"], feas_ts=F["ts"])
@@ -71,35 +73,35 @@ def case_fem2d_P1(L, p, stride):
     return lambda: _solve_case(lambda: P.assemble(H.amg(G.subdivide(G.fem2d_P1(), L)), p=p), stride=stride)
 
 
-def case_fem3d(c, t, p=1.0, maxit=10000):
+def case_fem3d(c, t, p=1.0, maxit=10000, stride=1):
     kw = dict(t=t)
     if maxit != 10000:
         kw["maxit"] = maxit
-    return lambda: _solve_case(lambda: P.assemble(H.amg(G.structured_box(3, c, k=1)), p=p), **kw)
+    return lambda: _solve_case(lambda: P.assemble(H.amg(G.structured_box(3, c, k=1)), p=p), stride=stride, **kw)
 
 
 def case_spectral2d(n1):
     return lambda: _solve_case(lambda: P.assemble(H.amg(G.spectral2d(n=n1)), p=1.0))
 
 
-def case_pure_p2(L):
+def case_pure_p2(L, stride=1):
     """test/test_pure_p2.jl:53-63 at size: bubble-free P2, slack in :broken_P1 (the un-condensable family)."""
     def build():
         mg = H.amg(G.subdivide(G.fem2d_P2(bubble=False), L))
         return P.assemble(mg, p=1.0)
-    return lambda: _solve_case(build)
+    return lambda: _solve_case(build, stride=stride)
 
 
-def case_parabolic(L, h=0.2, p=1.0):
+def case_parabolic(L, h=0.2, p=1.0, stride=1):
     def run():
         t0 = time.time()
         mg = H.amg(G.subdivide(G.fem2d_P2(), L))
         t_build = time.time() - t0
         t0 = time.time()
         sol = O.parabolic_solve(mg, P.assemble, P.intersect, P.convex_Euclidian_power, H.prepare_amg, P.default_slack_space, p=p, h=h)
-        U = np.stack(sol["u"], axis=0)           # (steps+1, n, 3)
+        U = np.stack(sol["u"], axis=0)[:, ::stride]           # (steps+1, n/stride, 3)
         out = dict(n=mg.geometry.n, u=U, ts_time=sol["ts"], unorm=np.array([np.linalg.norm(u) for u in sol["u"]]))
-        meta = dict(outcome="ok", n=int(mg.geometry.n), stride=1, oracle_wall_s=round(time.time() - t0, 1), host_build_s=round(t_build, 1),
+        meta = dict(outcome="ok", n=int(mg.geometry.n), stride=stride, oracle_wall_s=round(time.time() - t0, 1), host_build_s=round(t_build, 1),
                     solve_kwargs=dict(h=h, p=p))
         return out, meta
     return run
@@ -116,15 +118,20 @@ CASES = {
     "fem3d_k1_c16_t0.01": ("mgb_solve(assemble(amg(fem3d(k=1, K=16^3 box)); p=1.0); t=0.01)", case_fem3d(16, 0.01)),
     "fem3d_k1_c24_t0.1": ("mgb_solve(assemble(amg(fem3d(k=1, K=24^3 box)); p=1.0); t=0.1)", case_fem3d(24, 0.1)),
     "fem3d_k1_c24_t0.01": ("mgb_solve(assemble(amg(fem3d(k=1, K=24^3 box)); p=1.0); t=0.01)", case_fem3d(24, 0.01)),
+    "fem3d_k1_c32_t0.01": ("mgb_solve(assemble(amg(fem3d(k=1, K=32^3 box)); p=1.0); t=0.01)", case_fem3d(32, 0.01, stride=4)),
     # config C3 family
     "spectral2d_n32_p1": ("mgb_solve(assemble(amg(spectral2d(n=32)); p=1.0))", case_spectral2d(32)),
     # config C5 family
     "parabolic_fem2d_P2_L4": ("parabolic_solve(amg(subdivide(fem2d_P2(),4)); p=1, h=0.2)", case_parabolic(4)),
     "parabolic_fem2d_P2_L5": ("parabolic_solve(amg(subdivide(fem2d_P2(),5)); p=1, h=0.2)", case_parabolic(5)),
     "parabolic_fem2d_P2_L6": ("parabolic_solve(amg(subdivide(fem2d_P2(),6)); p=1, h=0.2)", case_parabolic(6)),
+    "parabolic_fem2d_P2_L7": ("parabolic_solve(amg(subdivide(fem2d_P2(),7)); p=1, h=0.2)", case_parabolic(7, stride=4)),
+    "parabolic_fem2d_P2_L8": ("parabolic_solve(amg(subdivide(fem2d_P2(),8)); p=1, h=0.2)", case_parabolic(8, stride=16)),
     # un-condensable family (test/test_pure_p2.jl) at size
     "pure_p2_L4_p1": ("mgb_solve(assemble(amg(subdivide(fem2d_P2(bubble=false),4)); p=1.0))", case_pure_p2(4)),
     "pure_p2_L6_p1": ("mgb_solve(assemble(amg(subdivide(fem2d_P2(bubble=false),6)); p=1.0))", case_pure_p2(6)),
+    "pure_p2_L7_p1": ("mgb_solve(assemble(amg(subdivide(fem2d_P2(bubble=false),7)); p=1.0))", case_pure_p2(7, stride=2)),
+    "pure_p2_L8_p1": ("mgb_solve(assemble(amg(subdivide(fem2d_P2(bubble=false),8)); p=1.0))", case_pure_p2(8, stride=8)),
 }
 
 

@@ -25,6 +25,7 @@ class OracleHandle:
         self.bw = barrier_weights
         self.f = prob.f.copy()
         self.z = [prob.g.T.reshape(-1).copy(), None]
+        self.zunfin = [self.z[0].copy(), None]
         self.zinit_feas = None
         self.box = (1.0, 10.0)
         self.steps = 0
@@ -53,7 +54,7 @@ class OracleHandle:
         fin = O.stopping_exact(o.finalize_theta) if o.finalize else None
         self.steps += 1
         r = types.SimpleNamespace(its=[0] * 32, f01_evals=0, f2_evals=0, linear_solves=0, pcg_iters=0, ms_f01=0.0, ms_f2=0.0, ms_solve=0.0,
-                                  converged=0)
+                                  converged=0, solve_failures=0, its_finalize=0)
         try:
             SOL = O.mgb_step(Q, M, self.z[which], t * cost, o.maxit, o.max_newton, ls, sc, fin, initial_step=bool(o.initial_step),
                              barrier_weights=bw)
@@ -63,6 +64,8 @@ class OracleHandle:
             r.its[k] = int(v)
         if SOL["converged"]:
             self.z[which] = SOL["z"]
+            self.zunfin[which] = SOL["z_unfinalized"]
+            r.its_finalize = int(SOL["its_finalize"])
             r.converged = 1
             return native.OK, r
         return native.NOT_CONVERGED, r
@@ -105,6 +108,9 @@ class OracleHandle:
 
     def get_z(self, which=native.MAIN):
         return self.z[which].copy()
+
+    def get_z_unfinalized(self, which=native.MAIN):
+        return self.zunfin[which].copy()
 
     def set_grids(self, f_grid=None, g_grid=None):
         if f_grid is not None:
