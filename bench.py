@@ -9,11 +9,18 @@ t-ramp with every Newton iteration, Hessian assembly, V-cycle PCG solve and line
            region; each step restarts from the boundary data g).
   e2e    = the same metric through the public API `mgbx.solver.mgb_solve(prob)` with HOST buffers: handle
            creation (H2D of every grid / operator / hierarchy + plan build), the solve, and the D2H of z.
+  parity = the timed solve against the committed CPU-oracle fixture of the SAME workload
+           (tests/golden/size_fem2d_P1_L<L>_p1.5.npz): relative L2 error of z, relative error of the final
+           objective, Newton-step totals.  For N > 1 the same, from the partitioned solve.
   roofline     = the dominant kernel class, timed live with CUDA events on the library's stream (profile pass).
-  cpu_baseline = the CPU oracle (NumPy/SciPy, SuperLU; 1 thread) on a bounded sample of the same workload family.
+  same_config  = this GPU path at the levels the CPU arms run (L = 7 for cpu_baseline, L = 8 for `--impl reference`),
+                 so that like-for-like pairs exist beside the L = 10 headline.
+  cpu_baseline = the CPU oracle (NumPy/SciPy, SuperLU; 1 thread), ONE full-tolerance solve at L = 7 (about 30 s).
 
-`--impl reference` times that CPU oracle arm alone (the reference itself is Julia; there is no Julia here).
-N > 1 (torchrun): one independent replica of the workload per GPU ("replicas only" in round 1), max-over-ranks time.
+`--impl reference` times the CPU oracle arm alone: ONE full-tolerance solve at L = 8 (n = 98 304, about 2 minutes; the
+path is deterministic, so it is run once, not warmup + steps times).  The reference itself is Julia; there is no Julia here
+(baseline/run_reference.jl is the script for a box that has it).
+N > 1 (torchrun): ONE solve, elements partitioned over the ranks (partition.py), max-over-ranks time ("strong").
 """
 from __future__ import annotations
 
@@ -32,12 +39,18 @@ import numpy as np
 
 METRIC = "mgb_solve DOF*Newton-steps/s (fem2d_P1 ~1.6M DOF, p=1.5)"
 UNIT = "DOF*Newton-steps/s"
+REF_L = 8          # --impl reference: largest level whose single full-ramp oracle solve takes ~2 minutes
+CPU_L = 7          # cpu_baseline leg of the default run (~30 s)
 
 
 def build_problem(L, p):
     import mgbx  # noqa: F401
     from mgbx import geometry as G, hierarchy as H, problem as P
     return P.assemble(H.amg(G.subdivide(G.fem2d_P1(), L)), p=p)
+
+
+def workload_name(L, p, n=None):
+    return "mgb_solve(assemble(amg(subdivide(fem2d_P1(),%d)); p=%g))%s" % (L, p, "" if n is None else ": n=%d broken nodes" % n)
 
 
 class ClockSampler(threading.Thread):
@@ -71,38 +84,92 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def oracle_sample(L, p, tol):
+def load_fixture(L, p):
+    path = os.path.join(ROOT, "tests", "golden", "size_fem2d_P1_L%d_p%g.npz" % (L, p))
+    if not os.path.exists(path):
+        return None, path
+    return np.load(path, allow_pickle=False), path
+
+
+def step_count_diff(its_a, fin_a, its_b, fin_b):
+    """max over barrier steps of |Newton steps a - b|, the finalize pass (added into the last step) excluded; None if the
+    t-schedules differ in length."""
+    if its_a.shape != its_b.shape:
+        return None
+    ca, cb = its_a.sum(axis=0).astype(np.int64), its_b.sum(axis=0).astype(np.int64)
+    ca[-1] -= fin_a
+    cb[-1] -= fin_b
+    return int(np.max(np.abs(ca - cb)))
+
+
+def parity_record(sol, L, p, reduce_sum=None):
+    """Timed solve vs the committed oracle fixture of the same workload.  reduce_sum: all-reduce (sum) of a float64 array
+    over the ranks of a partitioned solve (sol["z"] then holds this rank's nodes, sol["node_range"] their global range)."""
+    fx, path = load_fixture(L, p)
+    S = sol["SOL_main"]
+    rec = {"objective": float(S["c_dot_Dz"][-1]), "its_sum": int(S["its"].sum()), "its_finalize": int(S.get("its_finalize", 0))}
+    if fx is None:
+        rec["fixture"] = None
+        return rec
+    meta = json.loads(str(fx["meta"]))
+    st = int(meta["stride"])
+    z = sol["z"]
+    i0 = sol["node_range"][0] if sol.get("node_range") else 0
+    first = (-i0) % st                                      # first local node that the strided fixture holds
+    zs = z[first::st]
+    ref = fx["z"][(i0 + first) // st:(i0 + first) // st + zs.shape[0]]
+    sums = np.array([float(np.sum((zs - ref) ** 2)), float(np.sum(ref ** 2)), float(np.sum(z ** 2))])
+    if reduce_sum is not None:
+        sums = reduce_sum(sums)
+    rec.update({
+        "fixture": os.path.relpath(path, ROOT), "oracle": "oracle/mgb_oracle.py via tests/golden/make_size_fixtures.py",
+        "rel_vs_fixture": float(np.sqrt(sums[0] / sums[1])),
+        "znorm_rel_vs_fixture": float(abs(np.sqrt(sums[2]) - float(fx["znorm"])) / float(fx["znorm"])),
+        "objective_rel_vs_fixture": float(abs(rec["objective"] - float(fx["c_dot_Dz"][-1])) / abs(float(fx["c_dot_Dz"][-1]))),
+        "its_sum_oracle": int(fx["its"].sum()), "its_finalize_oracle": int(fx["its_finalize"]),
+        "barrier_steps": [int(S["its"].shape[1]), int(fx["its"].shape[1])],
+        "max_step_count_diff_excl_finalize": step_count_diff(S["its"], rec["its_finalize"], fx["its"], int(fx["its_finalize"])),
+    })
+    rec["pass"] = bool(rec["rel_vs_fixture"] < 1e-6 and rec["objective_rel_vs_fixture"] < 1e-8 and
+                       rec["max_step_count_diff_excl_finalize"] is not None and rec["max_step_count_diff_excl_finalize"] <= 1)
+    return rec
+
+
+def oracle_solve(L, p):
+    """ONE full-tolerance oracle solve; returns (value, seconds, Newton steps, n, objective)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import mgb_oracle as O
     prob = build_problem(L, p)
     t0 = time.time()
-    sol = O.mgb_solve(prob, tol=tol)
+    sol = O.mgb_solve(prob)
     dt = time.time() - t0
     its = int(sol["SOL_main"]["its"].sum())
     n = prob.geometry.n
-    return n * its / dt, dt, its, n
+    return n * its / dt, dt, its, n, float(sol["SOL_main"]["c_dot_Dz"][-1])
+
+
+def cpu_sample_text(L, n, p, its, dt):
+    return ("CPU oracle (NumPy/SciPy SuperLU restatement of the reference path, 1 thread): ONE full-tolerance solve of %s, "
+            "t-ramp to t >= 1/sqrt(eps) incl. finalize: %d Newton steps in %.1f s" % (workload_name(L, p, n), its, dt))
 
 
 def reference_arm(args, rank, world):
     if rank != 0:
         return
-    L, tol = args.ref_L, args.ref_tol
-    vals, times = [], []
-    for k in range(args.warmup + args.steps):
-        v, dt, its, n = oracle_sample(L, args.p, tol)
-        if k >= args.warmup:
-            vals.append(v)
-            times.append(dt)
-    v = float(np.mean(vals))
-    sample = "CPU oracle (NumPy/SciPy SuperLU restatement, 1 thread) on fem2d_P1 L=%d n=%d p=%g, t-ramp to t>=%g" % (L, n, args.p, 1 / tol)
+    v, dt, its, n, obj = oracle_solve(args.ref_L, args.p)
+    sample = cpu_sample_text(args.ref_L, n, args.p, its, dt)
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": 1,
+        "warmup": 0, "ms_per_step": 1e3 * dt, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "fem2d_P1 subdivide L=10 p=1.5 (n=1572864); reference arm runs a bounded sample", "sample": sample},
+        "config": {"workload": workload_name(args.ref_L, args.p, n) + " -- the bounded sample of the headline workload (L=10, n=1572864) the CPU path "
+                               "finishes in about two minutes; the GPU arm reports the same L in `same_config`",
+                   "sample": sample, "objective": obj, "newton_steps": its,
+                   "requested_steps_warmup": [args.steps, args.warmup],
+                   "note": "deterministic CPU path: run once, not warmup+steps times"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "the reference is Julia (absent here); its CPU path is represented by the oracle port",
+        "note": "the reference is Julia (absent here, baseline/run_reference.jl is its script); its CPU path is represented by the oracle port",
     }))
 
 
@@ -114,11 +181,13 @@ def main():
     ap.add_argument("--impl", default="mgbx")
     ap.add_argument("--L", type=int, default=10, help="fem2d_P1 subdivision level (10: n = 1 572 864)")
     ap.add_argument("--p", type=float, default=1.5)
-    ap.add_argument("--ref-L", type=int, default=7)
-    ap.add_argument("--ref-tol", type=float, default=1e-3)
+    ap.add_argument("--ref-L", type=int, default=REF_L)
+    ap.add_argument("--cpu-L", type=int, default=CPU_L)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-same-config", action="store_true")
     ap.add_argument("--replicas", action="store_true", help="N > 1: N independent solves instead of one element-partitioned solve")
     ap.add_argument("--no-profile-pass", action="store_true")
+    ap.add_argument("--config", action="append", default=[], help="mgbx_config override key=value (repeatable)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -128,6 +197,11 @@ def main():
     if args.impl == "reference":
         reference_arm(args, rank, world)
         return
+
+    cfg = {}
+    for kv in args.config:
+        k, v = kv.split("=")
+        cfg[k] = float(v) if ("." in v or "e" in v.lower()) else int(v)
 
     import torch
     import torch.distributed as dist
@@ -145,6 +219,13 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def reduce_sum(a):
+        if world == 1:
+            return a
+        t = torch.tensor(a, dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        return t.cpu().numpy()
 
     prob = build_problem(args.L, args.p)
     n = prob.geometry.n
@@ -169,7 +250,7 @@ def main():
         lbw = partition.shard_barrier_weights(bw, *lprob.node_range)
     else:
         lprob, lbw = prob, bw
-    h = native.Handle(lprob, barrier_weights=lbw, device=local_rank, comm=new_comm())
+    h = native.Handle(lprob, barrier_weights=lbw, device=local_rank, comm=new_comm(), **cfg)
     g0 = lprob.g
 
     def resident_step():
@@ -197,6 +278,9 @@ def main():
     launches = h.launch_count() - l0
     sampler.stop_flag = True
     stats = sol["stats"]
+    if sharded:
+        sol["node_range"] = lprob.node_range
+    parity = parity_record(sol, args.L, args.p, reduce_sum if sharded else None)
 
     # end-to-end through the public API with host buffers (handle creation + solve + z back), every step
     e2e_times = []
@@ -206,11 +290,11 @@ def main():
         h2d += sum(R.data.nbytes + R.indices.nbytes * 2 + R.indptr.nbytes * 2 for R in M.R_fine[-1:])
         h2d += sum(T.data.nbytes + T.indices.nbytes * 2 + T.indptr.nbytes * 2 for T in M.T)
     h2d += lprob.f.nbytes + lprob.g.nbytes + sum(pc.A.nbytes + pc.b.nbytes for pc in lprob.Q.pieces)
-    d2h = lprob.g.nbytes
+    d2h = 2 * lprob.g.nbytes                              # z and z_unfinalized
     for k in range(1 + max(1, min(args.steps, 3))):      # one untimed warm-up call (first-use costs of a fresh handle), then the timed ones
         barrier()
         t1 = time.time()
-        sol_e = solver.mgb_solve(prob, comm=new_comm(), config=dict(device=local_rank))
+        sol_e = solver.mgb_solve(prob, comm=new_comm(), config=dict(device=local_rank, **cfg))
         barrier()
         if k > 0:
             e2e_times.append(time.time() - t1)
@@ -241,14 +325,19 @@ def main():
             ncu_tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
         except Exception:
             ncu_tr = {}
+        gen = int(h.cfg.persistent)
 
         def traffic(cls, nl):
-            """DRAM bytes per launch from the committed `ncu --set full` capture of the same kernel on this workload."""
-            if cls == "pcg_persistent" and "k_pcg_persistent" in ncu_tr:
-                e = ncu_tr["k_pcg_persistent"]
-                return 1e6 * e["dram_mb_per_launch"] / e["pcg_iterations_in_launch"] * pstats["pcg_iters"] / nl
-            key = {"elem_f01": "k_elem_f01", "elem_f2": "k_elem_f2"}.get(cls)
-            return 1e6 * ncu_tr[key]["dram_mb_per_launch"] if key in ncu_tr else None
+            """DRAM bytes per launch from a committed `ncu --set full` capture of the SAME kernel on this workload (never
+            measured in this run: ncu numbers cannot be taken inside a timed bench).  Returns (bytes, source) or (None, why)."""
+            key = {"elem_f01": "k_elem_f01", "elem_f2": "k_elem_f2", "pcg_persistent": "k_pcg2" if gen == 2 else "k_pcg_persistent"}.get(cls)
+            e = ncu_tr.get(key)
+            if e is None:
+                return None, "no committed ncu capture of %s" % key
+            src = "committed ncu --set full capture %s (%s)" % (e.get("capture", "?"), e.get("build", "build not recorded"))
+            if cls == "pcg_persistent":
+                return 1e6 * e["dram_mb_per_launch"] / e["pcg_iterations_in_launch"] * pstats["pcg_iters"] / nl, src + ", scaled by PCG iterations"
+            return 1e6 * e["dram_mb_per_launch"], src
 
         def line(cls):
             nl, ms = kstats[cls]
@@ -260,21 +349,47 @@ def main():
             else:
                 bpl = ab.get(cls)
             ach = bpl / (ms * 1e-3 / nl) / 1e9 if bpl else None
+            tr, tr_src = traffic(cls, nl)
             return {"bound": "hbm", "kernel": cls, "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": (ach / peak) if ach else None, "traffic": traffic(cls, nl),
+                    "frac": (ach / peak) if ach else None, "traffic": tr, "traffic_source": tr_src,
                     "algorithmic_bytes_per_launch": bpl, "launches": nl, "avg_launch_us": 1e3 * ms / nl,
                     "share_of_device_time": ms / total_ms}
         dom = max(kstats, key=lambda k: kstats[k][1])
         roof = line(dom)
         roof["peak_source"] = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s"
         if dom == "pcg_persistent":
-            roof["note"] = ("one launch = one whole V-cycle-PCG solve (%d levels: %s unknowns); its working set (matrices + vectors "
-                            "of all levels, ~%.0f MB) is L2-resident, so the HBM peak is a reference line, not a ceiling; "
+            roof["note"] = ("one launch = one whole V-cycle-PCG solve (%d levels: %s unknowns, %.1f PCG iterations per launch); its working set "
+                            "(matrices + vectors of all levels, ~%.0f MB) is L2-resident, so the HBM peak is a reference line, not a ceiling; "
                             "the kernel is bound by grid-barrier and dependent-load latency (see DESIGN.md)"
-                            % (info["nlev"], info["m"], sum(12 * z for z in info["nnz"]) / 1e6))
+                            % (info["nlev"], info["m"], pstats["pcg_iters"] / max(1, kstats[dom][0]), sum(12 * z for z in info["nnz"]) / 1e6))
         roof_all = {c: line(c) for c in ("elem_f01", "elem_f2", "elem_generic_f01", "elem_generic_f2", "csr_gather", "spgemm", "pcg_persistent")
                     if kstats.get(c, (0, 0))[0]}
     h.close()
+
+    # the same GPU path at the levels the CPU arms run: like-for-like pairs for cpu_baseline / --impl reference
+    same = None
+    if world == 1 and not args.no_same_config:
+        same = {}
+        for Ls in sorted({args.cpu_L, args.ref_L}):
+            ps = build_problem(Ls, args.p)
+            hs = native.Handle(ps, barrier_weights=solver.barrier_weights(ps.M[0].w), device=local_rank, **cfg)
+            try:
+                for rep in range(3):
+                    hs.set_grids(None, ps.g)
+                    torch.cuda.synchronize()
+                    t1 = time.time()
+                    ss = solver.mgb_solve(ps, handle=hs)
+                    torch.cuda.synchronize()
+                    dts = time.time() - t1
+            finally:
+                hs.close()
+            t1 = time.time()
+            se = solver.mgb_solve(ps, config=dict(device=local_rank, **cfg))
+            dte = time.time() - t1
+            its_s = int(ss["SOL_main"]["its"].sum())
+            same["L%d" % Ls] = {"workload": workload_name(Ls, args.p, ps.geometry.n), "newton_steps": its_s, "s_per_solve_resident": dts,
+                                "value": ps.geometry.n * its_s / dts, "e2e_s": dte, "e2e_value": ps.geometry.n * int(se["SOL_main"]["its"].sum()) / dte,
+                                "parity": parity_record(ss, Ls, args.p)}
 
     tmax = torch.tensor([dev_s, wall, float(np.mean(e2e_times))], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -288,34 +403,35 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "mgb_solve(assemble(amg(subdivide(fem2d_P1(),%d)); p=%g)): n=%d broken nodes, nu=2, nD=4, "
-                               "fine unknowns %d" % (args.L, args.p, n, prob.M[0].R_fine[-1].shape[1]),
+        "config": {"workload": workload_name(args.L, args.p, n) + ", nu=2, nD=4, fine unknowns %d" % prob.M[0].R_fine[-1].shape[1],
                    "newton_steps_per_solve": its_total, "time_to_solution_s": dev_s / args.steps,
                    "parallelism": ("1 GPU" if world == 1 else
                                    ("element partition over %d GPUs: barrier / gradient / Hessian kernels sharded by element block, NCCL all-reduce "
                                     "of R'g, Hessian values and scalars, replicated deterministic multigrid-PCG (strong scaling: ONE solve)" % world)
                                    if sharded else "replicas: %d independent solves, no data-path collective" % world),
                    "l2_policy": "working set (>= 600 MB of grids, operators and CSR values) exceeds the 126 MB L2; no flush needed",
-                   "wall_s_timed_region": wall},
+                   "wall_s_timed_region": wall, "mgbx_config_overrides": cfg},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * (world if sharded else 1), "d2h_bytes_per_step": int(d2h) * (world if sharded else 1),
                 "s_per_step": e2e_s, "create_s": e2e_create,
-                "includes": "handle creation (layout conversion + H2D), plan build, solve, z D2H"},
+                "includes": "handle creation (layout conversion + H2D), plan build, solve, z and z_unfinalized D2H"},
+        "parity": parity,
         "gpu_launches": int(launches),
         "stage_ms_per_solve": {k: stats[k] for k in ("ms_f01", "ms_f2", "ms_solve")},
-        "counts_per_solve": {k: stats[k] for k in ("f01_evals", "f2_evals", "linear_solves", "pcg_iters")},
+        "counts_per_solve": {k: stats[k] for k in ("f01_evals", "f2_evals", "linear_solves", "pcg_iters", "solve_failures")},
         "clocks": sampler.summary(),
     }
     if roof:
         out["roofline"] = roof
-        out["roofline_by_kernel"] = {k: {kk: v[kk] for kk in ("achieved", "frac", "traffic", "avg_launch_us", "share_of_device_time", "algorithmic_bytes_per_launch")}
+        out["roofline_by_kernel"] = {k: {kk: v[kk] for kk in ("achieved", "frac", "traffic", "traffic_source", "avg_launch_us", "share_of_device_time", "algorithmic_bytes_per_launch")}
                                      for k, v in roof_all.items() if v}
         out["solver_plan"] = info
         out["kernel_classes"] = {k: {"launches": v[0], "ms": round(v[1], 3)} for k, v in kstats.items()}
+    if same:
+        out["same_config"] = same
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, dt, its, nn = oracle_sample(args.ref_L, args.p, args.ref_tol)
-        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-                               "sample": "CPU oracle (NumPy/SciPy SuperLU, 1 thread) on fem2d_P1 L=%d n=%d p=%g, t-ramp to t>=%g: "
-                                         "%d Newton steps in %.1f s" % (args.ref_L, nn, args.p, 1 / args.ref_tol, its, dt)}
+        v, dt, its, nn, obj = oracle_solve(args.cpu_L, args.p)
+        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": cpu_sample_text(args.cpu_L, nn, args.p, its, dt),
+                               "same_config_gpu": "same_config.L%d" % args.cpu_L}
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
@@ -356,18 +472,18 @@ def algorithmic_bytes(prob, h, counts):
 
 
 def pcg_iteration_bytes(info, nu_sweeps=2):
-    """One PCG iteration of the persistent kernel: per non-bottom level 1 fused pre-smoothing pass + 1 residual +
-    nu post passes over A (12 B per non-zero + 8 B row pointer per row + 4 vector streams), one pass over T and T'
-    each; the PCG mat-vec on the top level; 6 vector streams of the PCG update."""
+    """One PCG iteration of the persistent kernel, with SURVEY.md section 8(d)'s SpMV figure `12 nnz + 20 rows` per pass:
+    per non-bottom level 1 fused pre-smoothing pass + 1 residual + nu post passes over A, one pass over T and T' each; the PCG
+    mat-vec on the top level; 5 vector streams of the PCG update."""
     b = 0
     L = info["nlev"]
     for q in range(L):
         m, nnz, nnzT = info["m"][q], info["nnz"][q], info["nnzT"][q]
         if q == L - 1:
-            b += 8 * m * m if info["bottom_dense"] else 30 * (12 * nnz + 40 * m)
+            b += 8 * m * m if info["bottom_dense"] else 30 * (12 * nnz + 20 * m)
             continue
-        b += (2 + nu_sweeps) * (12 * nnz + 40 * m) + 2 * (12 * nnzT + 8 * (m + info["m"][q + 1]) + 16 * m)
-    b += 12 * info["nnz"][0] + 40 * info["m"][0] + 6 * 8 * info["m"][0]
+        b += (2 + nu_sweeps) * (12 * nnz + 20 * m) + (12 * nnzT + 20 * m) + (12 * nnzT + 20 * info["m"][q + 1])
+    b += 12 * info["nnz"][0] + 20 * info["m"][0] + 5 * 8 * info["m"][0]
     return b
 
 

@@ -136,7 +136,9 @@ typedef struct {
   int32_t verbose;
   int32_t use_graphs;        /* 1 (default): replay each PCG iteration (V-cycle + vector updates) as one CUDA graph */
   int32_t profile;           /* 1: time every kernel launch with CUDA events on the handle's stream (mgbx_kernel_stats) */
-  int32_t persistent;        /* 1 (default): each PCG solve is ONE cooperative persistent kernel (one CTA per SM, grid barriers) */
+  int32_t persistent;        /* each PCG solve is ONE cooperative persistent kernel (one CTA per SM, grid barriers): 2 (default) the
+                                second-generation kernel (csrc/pcg2.cu: sliced-ELL level matrices, row ownership, tail levels in
+                                CTA 0's shared memory); 1 the first-generation CSR kernel; 0 one kernel per phase (CUDA graph) */
   int32_t tail_max;          /* V-cycle levels with <= this many unknowns run inside CTA 0 of that kernel (default 1200) */
   double pcg_rtol_final;     /* relative residual during the finalize pass (stopping_exact), default 1e-15 (i.e. to stagnation) */
   int32_t fused;             /* 1 (default): fused element kernels (operator blocks staged once in shared memory), with the
@@ -159,10 +161,15 @@ typedef struct {
                                 Gershgorin bound of lambda_max in the Chebyshev interval (the bound stays as an upper clamp).  Default 0
                                 (off): measured on CPU only so far (tools/smoother_lab.py: 14-38 % fewer PCG iterations on 3-D
                                 problems, none in 2-D); to be enabled once run on hardware */
-  double pcg_fail_rtol;      /* a PCG solve that breaks down, or ends (stagnation / pcg_maxit) with |r|/|b| above this, is a FAILED
-                                solve: the Newton run reports "not converged" (as a failed factorisation would in the reference,
-                                src/utils.jl:142-145) instead of continuing with an under-converged direction.  Default 1e-5: Newton
-                                counts are unchanged down to 1e-7 and within +-1 at 1e-6 (tools/inexact_newton_lab.py) */
+  double pcg_fail_rtol;      /* a PCG solve that breaks down, or ends (stagnation / pcg_maxit) with |r|/|b| above this AND with the
+                                direction's energy still growing (pcg_fail_etol), is a FAILED solve: the Newton run reports "not
+                                converged" (as a failed factorisation would in the reference, src/utils.jl:142-145) instead of
+                                continuing with an under-converged direction.  Default 1e-5: Newton counts are unchanged down to
+                                1e-7 and within +-1 at 1e-6 (tools/inexact_newton_lab.py) */
+  double pcg_fail_etol;      /* for CG from x = 0, g.x_k = |x_k|_A^2 grows monotonically to the Newton decrement g.H^-1 g.  Late in
+                                the t-ramp (conditioning ~ t^2) the residual norm can stall above pcg_fail_rtol although that
+                                energy -- what the stop rule and the Armijo test consume -- has converged: a stagnated solve is
+                                accepted when its last four iterations added less than this share of the energy.  Default 1e-8 */
 } mgbx_config;
 
 /* options of one mgb_step (src/mgb.jl:16-30; defaults src/mgb.jl:360-363) */

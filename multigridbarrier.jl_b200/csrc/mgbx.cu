@@ -29,6 +29,7 @@
 #include "solver_kernels.cuh"
 #include "setup_kernels.cuh"
 #include "dense_kernels.cuh"
+#include "pcg2.hpp"
 
 using namespace mgbx;
 
@@ -381,6 +382,10 @@ struct SysLevel {
   double *dense = nullptr, *dense_inv = nullptr, *dscale = nullptr;
   int spmv_group = 1;
   std::vector<int64_t> off;  // system offsets of the kept variables (+ end)
+  // sliced-ELL copies for the second-generation persistent solve kernel (pcg2.hpp): pattern built once, A's values refreshed
+  // with every assembly, T / T' filled once
+  SellBuild sA, sT, sTt;
+  bool sell_A = false, sell_T = false;
 };
 
 struct System {
@@ -410,6 +415,12 @@ struct System {
     PcgPlan *dev = nullptr;
   };
   std::map<int, PcgDev> pplans;
+  struct Pcg2Dev {
+    Pcg2Plan host;
+    Pcg2Plan *dev = nullptr;
+    size_t smem = 0;
+  };
+  std::map<int, Pcg2Dev> pplans2;
   double *pc_p2 = nullptr, *pcg_partials = nullptr, *pcg_out = nullptr;
   unsigned int *pcg_bar = nullptr;
 };
@@ -477,11 +488,13 @@ struct mgbx_handle {
   std::vector<Pending> ev_pending;
   cudaEvent_t ev_cur = nullptr;
   int pcg_grid = 0;
+  int pcg2_grid = 0;         // CTAs of the second-generation persistent kernel (0: not available)
   double dgemm_flops = 0.0;   // FP64 tensor-core flops issued so far (spectral path)
   double cur_rtol2 = 1e-22;
   int cur_window = 25;       // PCG stagnation window (iterations without a new best residual)
   int last_solve_status = 1;       // 1 converged / direct, 2 stagnated above the tolerance, 3 iteration limit, -1 breakdown
   double last_solve_rel = 0.0;     // final relative residual |r| / |b| of the last PCG solve (0 for a direct solve)
+  double last_solve_erel = 0.0;    // share of the direction's energy b.x = |x|_A^2 gained in the last four PCG iterations
   // multi-GPU
   int rank = 0, nranks = 1;
   void *comm = nullptr;
@@ -1001,6 +1014,21 @@ struct Engine {
     return C;
   }
   int pcg_persistent(System &S, int ktop, const double *b, double *x);
+  // ---- second-generation persistent kernel (pcg2.hpp)
+  std::vector<int> active_levels(const System &S, int ktop) const {
+    const int nlev = (int)S.lev.size();
+    const int kend = (S.cut >= 0) ? std::max(S.cut, ktop) : nlev - 1;
+    std::vector<int> act;
+    for (int k = ktop; k <= kend; ++k) {
+      if (k < kend && S.lev[k].T_identity) continue;   // same matrix as the next level
+      act.push_back(k);
+    }
+    return act;
+  }
+  SellBuild make_sell(const DevCsr &A, int64_t nthreads);
+  void sell_prepare(System &S, int ktop);
+  System::Pcg2Dev &pcg2_plan(System &S, int ktop);
+  int pcg_persistent2(System &S, int ktop, const double *b, double *x);
   int pcg(System &S, int ktop, const double *b, double *x);
   int solve_compact(System &S, int ktop, const double *b, double *x);
   int solve(Amg &A, System &S, int J, const double *g, double *dir);
@@ -1454,6 +1482,7 @@ void Engine::setup_hierarchy(Amg &A, System &S, int ktop) {
     if (!Lc.dense_inv) Lc.dense_inv = h->pool.alloc<double>((size_t)m * m);
     LAUNCH(KC_DENSE, k_coarse_inverse<<<1, 1024, coarse_inverse_smem(m), s>>>(Lc.A, Lc.dense_inv));
   }
+  if (h->cfg.persistent == 2 && h->pcg2_grid > 0) sell_prepare(S, ktop);
 }
 
 void Engine::dense_factor(System &S, SysLevel &Lv, bool want_inverse) {
@@ -1633,17 +1662,177 @@ int Engine::pcg_persistent(System &S, int ktop, const double *b, double *x) {
   pre_launch(KC_PCG);
   CK(cudaLaunchCooperativeKernel((const void *)k_pcg_persistent, dim3(h->pcg_grid), dim3(kPcgThreads), args, 0, s));
   post_launch(KC_PCG);
-  CK(cudaMemcpyAsync(h->hscal + 8, S.pcg_out, sizeof(double) * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(h->hscal + 8, S.pcg_out, sizeof(double) * 6, cudaMemcpyDeviceToHost, s));
   sync();
   const int it = (int)h->hscal[8];
   const double status = h->hscal[10];
   h->last_solve_status = (int)status;
   h->last_solve_rel = (h->hscal[11] > 0.0) ? std::sqrt(h->hscal[9] / h->hscal[11]) : 0.0;
+  h->last_solve_erel = (h->hscal[12] > 0.0) ? h->hscal[13] / h->hscal[12] : 0.0;
+  if (x != S.pc_x) copy(x, S.pc_x, m);
+  return status < 0 ? -std::max(it, 1) : it;
+}
+
+// sliced-ELL copy of a device CSR pattern (32 rows per slice, slices-per-CTA for the grid the kernel is launched with)
+SellBuild Engine::make_sell(const DevCsr &A, int64_t nthreads) {
+  SellBuild B;
+  if (A.rows >= INT32_MAX / 2) throw std::runtime_error("persistent solve kernel: a level matrix exceeds 32-bit indexing");
+  // lanes per row: widen while the level leaves at least half of the threads that share its phases idle and the rows
+  // still give every lane two entries (measured, tools/micro/bench_spmv_phase: one lane per row wins on the two finest
+  // levels of C2, four lanes on the 32 k-row level)
+  int lpr = 1;
+  const double avg = A.rows ? (double)A.nnz / (double)A.rows : 0.0;
+  while (lpr < 8 && A.rows * (int64_t)lpr * 2 <= nthreads && avg / lpr >= 2.0) lpr *= 2;
+  const int rps = 32 / lpr;
+  const int nsl = (int)((A.rows + rps - 1) / rps);
+  B.M.rows = (int)A.rows;
+  B.M.lpr = lpr;
+  B.M.nslices = nsl;
+  B.M.spc = (nsl + std::max(1, h->pcg2_grid) - 1) / std::max(1, h->pcg2_grid);
+  if (nsl == 0) return B;
+  int *width = tmp_alloc<int>(nsl, s);
+  CK(sell_slice_widths(A.rows, lpr, A.ptr, width, s));
+  std::vector<int> hw(nsl);
+  CK(cudaMemcpyAsync(hw.data(), width, sizeof(int) * nsl, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  tmp_free(width, s);
+  std::vector<int> soff(nsl + 1, 0);
+  int64_t tot = 0;
+  for (int q = 0; q < nsl; ++q) {
+    tot += 32 * (int64_t)hw[q];
+    if (tot > INT32_MAX) throw std::runtime_error("persistent solve kernel: sliced-ELL level matrix exceeds 32-bit indexing");
+    soff[q + 1] = (int)tot;
+  }
+  B.M.entries = (int)tot;
+  B.soff = h->pool.upload<int>(soff.data(), soff.size(), s);
+  B.idx = h->pool.alloc<int>((size_t)tot);
+  B.src = h->pool.alloc<int>((size_t)tot);
+  B.val = h->pool.alloc<double>((size_t)tot);
+  B.valf = h->pool.alloc<float>((size_t)tot);
+  CK(sell_fill_pattern(A.rows, lpr, A.ptr, A.idx, B.soff, B.idx, B.src, s));
+  h->launches += 2;
+  B.M.soff = B.soff;
+  B.M.idx = B.idx;
+  B.M.val = B.val;
+  B.M.valf = nullptr;
+  CK(cudaStreamSynchronize(s));   // soff (host vector) has been consumed
+  return B;
+}
+
+// Build (once) the sliced-ELL structures of the active levels below lev[ktop] and refresh the values of the level matrices.
+// Called from setup_hierarchy after every assembly, i.e. before every solve.
+void Engine::sell_prepare(System &S, int ktop) {
+  const std::vector<int> act = active_levels(S, ktop);
+  const int64_t grid_threads = (int64_t)h->pcg2_grid * kPcg2Threads;
+  for (size_t q = 0; q < act.size(); ++q) {
+    SysLevel &Lv = S.lev[act[q]];
+    // threads that share this level's phases: the whole grid, or CTA 0 alone for the tail (q > 0 and small)
+    const int64_t nthr = (q > 0 && Lv.m <= h->cfg.tail_max) ? kPcg2Threads : grid_threads;
+    if (!Lv.sell_A) {
+      Lv.sA = make_sell(Lv.A, nthr);
+      Lv.sell_A = true;
+    }
+    if (Lv.sA.M.entries) LAUNCH(KC_VEC, CK(sell_fill_values(Lv.sA.M.entries, Lv.sA.src, Lv.A.val, Lv.sA.val, Lv.sA.valf, s)));
+    if (q + 1 < act.size() && !Lv.sell_T) {
+      const int64_t nthr_c = (S.lev[act[q + 1]].m <= h->cfg.tail_max) ? kPcg2Threads : grid_threads;
+      Lv.sT = make_sell(Lv.T, nthr);
+      Lv.sTt = make_sell(Lv.Tt, nthr_c);
+      if (Lv.sT.M.entries) LAUNCH(KC_VEC, CK(sell_fill_values(Lv.sT.M.entries, Lv.sT.src, Lv.T.val, Lv.sT.val, Lv.sT.valf, s)));
+      if (Lv.sTt.M.entries) LAUNCH(KC_VEC, CK(sell_fill_values(Lv.sTt.M.entries, Lv.sTt.src, Lv.Tt.val, Lv.sTt.val, Lv.sTt.valf, s)));
+      Lv.sell_T = true;
+    }
+  }
+}
+
+System::Pcg2Dev &Engine::pcg2_plan(System &S, int ktop) {
+  auto it = S.pplans2.find(ktop);
+  if (it != S.pplans2.end()) return it->second;
+  System::Pcg2Dev &D = S.pplans2[ktop];
+  Pcg2Plan &P = D.host;
+  P = Pcg2Plan();
+  const std::vector<int> act = active_levels(S, ktop);
+  if ((int)act.size() > kPcg2MaxLevels) throw std::runtime_error("persistent solve kernel: too many levels");
+  P.nlev = (int)act.size();
+  P.bottom_dense = (S.cut >= 0 && act.back() == S.cut) ? 1 : 0;
+  P.nu = std::max(1, h->cfg.smoother_sweeps);
+  P.nu_bottom = 30;
+  P.smoother = h->cfg.smoother;
+  P.cheb_ratio = h->cfg.cheb_ratio > 1.0 ? h->cfg.cheb_ratio : 8.0;
+  const bool f32 = precond_fp32(S);
+  for (int q = 0; q < P.nlev; ++q) {
+    SysLevel &Lv = S.lev[act[q]];
+    Pcg2Level &pl = P.lev[q];
+    if (Lv.m > INT32_MAX / 2) throw std::runtime_error("persistent solve kernel: level exceeds 32-bit indexing");
+    pl.m = (int)Lv.m;
+    pl.A = Lv.sA.M;
+    pl.A.valf = Lv.sA.valf;       // narrowed below for the grid-wide levels
+    if (q + 1 < P.nlev) {
+      pl.T = Lv.sT.M;
+      pl.T.valf = Lv.sT.valf;
+      pl.Tt = Lv.sTt.M;
+      pl.Tt.valf = Lv.sTt.valf;
+    }
+    pl.idiag = Lv.diag;
+    pl.dinv = Lv.dinv;
+    pl.lam = Lv.lam;
+    pl.b = Lv.b;
+    pl.x = Lv.x;
+    pl.x2 = Lv.x2;
+    pl.r = Lv.r;
+  }
+  // the tail [nbig, nlev): levels with <= tail_max unknowns, as many as fit into CTA 0's shared memory
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  const size_t cap = pcg2_max_tail_bytes(dev);
+  P.nbig = 0;
+  for (int q = 0; q < P.nlev; ++q)
+    if (S.lev[act[q]].m > h->cfg.tail_max) P.nbig = q + 1;
+  P.nbig = std::max(P.nbig, 1);
+  while (P.nbig < P.nlev && (pcg2_tail_bytes(P) > cap || P.nlev - P.nbig > 12)) P.nbig++;
+  D.smem = (P.nbig < P.nlev) ? pcg2_tail_bytes(P) : 0;
+  P.tail_smem_bytes = (int)D.smem;
+  for (int q = 0; q < P.nbig; ++q) {   // grid-wide levels read FP32 values only when the FP32 preconditioner is on
+    if (!f32) P.lev[q].A.valf = P.lev[q].T.valf = P.lev[q].Tt.valf = nullptr;
+  }
+  P.dense_inv = P.bottom_dense ? S.lev[S.cut].dense_inv : nullptr;
+  P.r = S.pc_r;
+  P.p = S.pc_p;
+  P.p2 = S.pc_p2;
+  P.Ap = S.pc_Ap;
+  P.x = S.pc_x;
+  P.b = S.pc_b;
+  P.partials = S.pcg_partials;
+  P.bar = S.pcg_bar;
+  P.out = S.pcg_out;
+  D.dev = h->pool.upload<Pcg2Plan>(&P, 1, s);
+  CK(cudaStreamSynchronize(s));
+  if (h->cfg.verbose > 0)
+    fprintf(stderr, "[mgbx] persistent PCG (gen 2) plan: %d levels (%d grid-wide, %d in CTA 0 from %zu bytes of shared memory), dense bottom %d, grid %d x %d\n",
+            P.nlev, P.nbig, P.nlev - P.nbig, D.smem, P.bottom_dense, h->pcg2_grid, kPcg2Threads);
+  return D;
+}
+
+int Engine::pcg_persistent2(System &S, int ktop, const double *b, double *x) {
+  SysLevel &Lv = S.lev[ktop];
+  const int64_t m = Lv.m;
+  System::Pcg2Dev &D = pcg2_plan(S, ktop);
+  if (b != S.pc_b) copy(S.pc_b, b, m);
+  pre_launch(KC_PCG);
+  CK(pcg2_launch(D.dev, h->pcg2_grid, D.smem, h->cur_rtol2, h->cfg.pcg_maxit, h->cur_window, s));
+  post_launch(KC_PCG);
+  CK(cudaMemcpyAsync(h->hscal + 8, S.pcg_out, sizeof(double) * 6, cudaMemcpyDeviceToHost, s));
+  sync();
+  const int it = (int)h->hscal[8];
+  const double status = h->hscal[10];
+  h->last_solve_status = (int)status;
+  h->last_solve_rel = (h->hscal[11] > 0.0) ? std::sqrt(h->hscal[9] / h->hscal[11]) : 0.0;
+  h->last_solve_erel = (h->hscal[12] > 0.0) ? h->hscal[13] / h->hscal[12] : 0.0;
   if (x != S.pc_x) copy(x, S.pc_x, m);
   return status < 0 ? -std::max(it, 1) : it;
 }
 
 int Engine::pcg(System &S, int ktop, const double *b, double *x) {
+  if (h->cfg.persistent == 2 && h->pcg2_grid > 0) return pcg_persistent2(S, ktop, b, x);
   if (h->cfg.persistent) return pcg_persistent(S, ktop, b, x);
   SysLevel &Lv = S.lev[ktop];
   const int64_t m = Lv.m;
@@ -1660,10 +1849,12 @@ int Engine::pcg(System &S, int ktop, const double *b, double *x) {
   const double bb = h->hscal[10];
   h->last_solve_status = 1;
   h->last_solve_rel = 0.0;
+  h->last_solve_erel = 0.0;
   if (!(bb > 0.0) || !std::isfinite(bb)) {
     zero(x, m);
     return 0;
   }
+  double e_tot = 0.0, e_hist[4] = {0.0, 0.0, 0.0, 0.0};
   const double target = h->cur_rtol2 * bb;
   // the iteration body is captured once per (system, top level) and replayed as a CUDA graph
   cudaGraphExec_t gexec = nullptr;
@@ -1711,6 +1902,9 @@ int Engine::pcg(System &S, int ktop, const double *b, double *x) {
       break;
     }
     h->last_solve_rel = std::sqrt(rr / bb);
+    e_hist[it & 3] = e_tot;                                  // value four iterations ago is overwritten next time round
+    e_tot += h->hscal[8] * h->hscal[8] / h->hscal[9];        // alpha (r.z) = (r.z)^2 / p.Ap
+    h->last_solve_erel = e_tot > 0.0 ? (e_tot - e_hist[(it + 1) & 3]) / e_tot : 0.0;
     if (rr <= target) break;
     if (rr < best * 0.999) {
       best = rr;
@@ -1731,6 +1925,7 @@ int Engine::solve_compact(System &S, int ktop, const double *b, double *x) {
   if (use_direct(S, Lv)) {
     h->last_solve_status = 1;
     h->last_solve_rel = 0.0;
+    h->last_solve_erel = 0.0;
     const bool small = Lv.m <= kCoarseMaxDense;
     auto apply = [&](const double *rhs, double *out) {
       if (small) LAUNCH(KC_DENSE, k_dense_solve_small<<<1, 1024, dense_solve_small_smem((int)Lv.m), s>>>(Lv.A, rhs, out, nullptr));
@@ -1836,15 +2031,16 @@ Engine::NewtonOut Engine::newton(Amg &A, int J, double t, int maxit, int stop_ki
     const bool dir_finite = (h->hscal[6] == 0.0) && std::isfinite(h->hscal[5]) && std::isfinite(inc);
     out.inc = inc;
     if (h->cfg.verbose > 1)
-      fprintf(stderr, "[mgbx] newton J=%d m=%lld k=%d y=%.17g |g|=%.6g lam2=%.6g pcg=%d t=%g\n", J, (long long)m, k, y, gnorm, inc, pit, t);
+      fprintf(stderr, "[mgbx] newton J=%d m=%lld k=%d y=%.17g |g|=%.6g lam2=%.6g pcg=%d status=%d rel=%.3g erel=%.3g t=%g\n", J, (long long)m, k, y, gnorm, inc, pit,
+              h->last_solve_status, h->last_solve_rel, h->last_solve_erel, t);
     // An iterative solve that broke down or stopped far from the requested residual is a FAILED solve, as a failed
     // factorisation is for the reference's direct `H \\ g` (src/utils.jl:142-145): for a CG iterate g.x_k <= g.H^-1 g, so an
     // under-converged direction under-estimates the Newton decrement and could end the iteration early with a wrong z.
     // The Newton run is reported as not converged; mgb_core then shrinks kappa (or phase I grows the box).
-    if (h->last_solve_status < 0 || h->last_solve_rel > h->cfg.pcg_fail_rtol) {
+    if (h->last_solve_status < 0 || (h->last_solve_rel > h->cfg.pcg_fail_rtol && h->last_solve_erel > h->cfg.pcg_fail_etol)) {
       if (h->cfg.verbose > 0)
-        fprintf(stderr, "[mgbx] newton J=%d m=%lld k=%d: linear solve failed (status %d, |r|/|b| = %.3g after %d PCG iterations)\n", J, (long long)m, k,
-                h->last_solve_status, h->last_solve_rel, pit < 0 ? -pit : pit);
+        fprintf(stderr, "[mgbx] newton J=%d m=%lld k=%d: linear solve failed (status %d, |r|/|b| = %.3g, energy gained in the last 4 iterations %.3g, after %d PCG iterations)\n",
+                J, (long long)m, k, h->last_solve_status, h->last_solve_rel, h->last_solve_erel, pit < 0 ? -pit : pit);
       if (h->res) h->res->solve_failures++;
       break;
     }
@@ -2279,7 +2475,7 @@ void mgbx_default_config(mgbx_config *c) {
   c->verbose = 0;
   c->profile = 0;
   c->use_graphs = 1;
-  c->persistent = 1;
+  c->persistent = 2;
   c->tail_max = 1200;
   c->pcg_rtol_final = 1e-15;
   c->fused = 1;
@@ -2289,6 +2485,7 @@ void mgbx_default_config(mgbx_config *c) {
   c->pcg_lanes = 0;
   c->lambda_power = 0;
   c->pcg_fail_rtol = 1e-5;
+  c->pcg_fail_etol = 1e-8;
 }
 
 void mgbx_default_step_opts(mgbx_step_opts *o, int64_t n) {
@@ -2350,6 +2547,7 @@ int mgbx_create(const mgbx_problem *prob, const mgbx_config *cfg, mgbx_handle **
       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_persistent, kPcgThreads, 0));
       if (!coop || per_sm < 1) throw std::runtime_error("CUDA device cannot run the cooperative persistent solve kernel");
       h->pcg_grid = std::min(nsm, kPcgMaxGrid);   // one CTA per SM
+      h->pcg2_grid = pcg2_grid(dev);
       CK(cudaFuncSetAttribute(k_coarse_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coarse_inverse_smem(kCoarseMaxDense)));
       CK(cudaFuncSetAttribute(k_dense_solve_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dense_solve_small_smem(kCoarseMaxDense)));
       CK(cudaFuncSetAttribute(k_chol_diag_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCholDiagSmem));
@@ -2639,8 +2837,24 @@ int mgbx_solver_info(mgbx_handle *h, int which, mgbx_solver_info_t *out) {
     out->condensed = S->condensed ? 1 : 0;
     out->assembly_terms = S->top.nterms;
     out->hblk_entries = S->hblk_size;
+    auto it2 = S->pplans2.find(0);
+    if (it2 != S->pplans2.end()) {
+      const Pcg2Plan &P = it2->second.host;
+      out->nlev = P.nlev;
+      out->nbig = P.nbig;
+      out->bottom_dense = P.bottom_dense;
+      out->grid = h->pcg2_grid;
+      out->threads = kPcg2Threads;
+      const std::vector<int> act = Engine(h).active_levels(*S, 0);
+      for (int q = 0; q < P.nlev; ++q) {
+        const SysLevel &Lv = S->lev[act[q]];
+        out->m[q] = P.lev[q].m;
+        out->nnz[q] = Lv.A.nnz;
+        out->nnzT[q] = (q + 1 < P.nlev) ? Lv.T.nnz : 0;
+      }
+    }
     auto it = S->pplans.find(0);
-    if (it != S->pplans.end()) {
+    if (it2 == S->pplans2.end() && it != S->pplans.end()) {
       const PcgPlan &P = it->second.host;
       out->nlev = P.nlev;
       out->nbig = P.nbig;

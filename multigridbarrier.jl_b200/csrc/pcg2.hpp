@@ -1,0 +1,87 @@
+// pcg2.hpp -- interface of the second-generation persistent solve kernel (pcg2.cu, its own translation unit).
+//
+// Replaces, like k_pcg_persistent before it, the reference's `solve(Symmetric(H), g)` (src/utils.jl:142-145: CHOLMOD; cuDSS in
+// ext/MultiGridBarrierCUDAExt/cudss_solver.jl:264-381) by ONE cooperative launch that runs the whole V-cycle-preconditioned CG.
+// What changed against the first generation (solver_kernels.cuh):
+//   * every level matrix (A, T, T') is stored as sliced ELL, 32 rows per slice, column-major inside a slice: a warp owns a slice,
+//     lane = row, so index / value loads are coalesced and a row's loads are independent of each other (no row-pointer ->
+//     entry chain; the only dependent load left is the gather of the vector entry);
+//   * rows are OWNED: CTA c works on the same contiguous block of slices of a level in every phase, warps take the block's
+//     slices round-robin -- the mapping the multi-GPU row partition extends (a rank owns a block of CTAs' blocks);
+//   * the single-CTA tail levels keep their matrices in CTA 0's shared memory (copied once per launch);
+//   * distinct exit states (converged / stagnated / iteration limit / breakdown).
+// Row sums run over a row's entries in column order, as the CSR one-lane-per-row kernel did: results are deterministic.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mgbx {
+
+constexpr int kPcg2Threads = 1024;
+constexpr int kPcg2MaxGrid = 1024;
+constexpr int kPcg2MaxLevels = 32;
+
+// sliced-ELL matrix: slice s holds rows [rps s, rps s + rps), rps = 32 / lpr; lane l of the owning warp reads the entries
+// idx/val[soff[s] + 32 j + l], j < width(s).
+// Padding entries carry val = 0 and idx = the first column of their row (a valid gather for rectangular matrices too).
+// lpr lanes share a row (1, 2, 4 or 8; a slice then holds 32 / lpr rows): entry k of a row sits with lane (k mod lpr) of the
+// row's lane group, so that short levels still occupy the whole grid and a long row's dependent loads are split.
+struct SellMat {
+  int rows = 0, nslices = 0;
+  int lpr = 1;                 // lanes per row
+  int spc = 0;                 // slices per CTA (grid-wide levels): CTA c owns slices [c spc, (c+1) spc)
+  int entries = 0;             // padded entries (soff[nslices])
+  const int *soff = nullptr;   // nslices + 1
+  const int *idx = nullptr;
+  const double *val = nullptr;
+  const float *valf = nullptr; // FP32 copy of the values: used instead of val when set (preconditioner passes; always by the tail)
+};
+
+struct Pcg2Level {
+  int m = 0;
+  SellMat A, T, Tt;            // T: rows of this level <- next coarser active level; Tt: rows of the coarser level <- this level
+  const double *idiag = nullptr;   // 1 / a_ii (Chebyshev)
+  const double *dinv = nullptr;    // l1-Jacobi 1 / sum_j |a_ij|
+  const double *lam = nullptr;     // bound of lambda_max(D^-1 A) (device scalar, refreshed with the values)
+  double *b = nullptr, *x = nullptr, *x2 = nullptr, *r = nullptr;
+};
+
+struct Pcg2Plan {
+  int nlev = 0, nbig = 0;      // active levels: [0, nbig) by the whole grid, [nbig, nlev) by CTA 0 alone
+  int bottom_dense = 0;        // the last level is applied through dense_inv (m x m, row-major)
+  int nu = 2, nu_bottom = 30;
+  int smoother = 1;            // 1 Chebyshev(nu) on [lam/ratio, lam], 0 l1-Jacobi
+  double cheb_ratio = 8.0;
+  int tail_smem_bytes = 0;     // shared-memory bytes holding the tail levels' matrices (0: tail reads global memory)
+  Pcg2Level lev[kPcg2MaxLevels];
+  const double *dense_inv = nullptr;
+  double *r = nullptr, *p = nullptr, *p2 = nullptr, *Ap = nullptr, *x = nullptr;
+  const double *b = nullptr;
+  double *partials = nullptr;  // 3 x kPcg2MaxGrid
+  unsigned int *bar = nullptr;
+  double *out = nullptr;       // [0] iterations, [1] |r|^2, [2] status (1 converged, 2 stagnated above the tolerance, 3 iteration limit, -1 breakdown), [3] |b|^2,
+                               // [4] b.x = |x|_A^2, [5] the part of [4] gained in the last four iterations
+};
+
+// shared memory the tail needs: indices + FP32 values of A, T, Tt of the levels >= nbig, their diagonals and work vectors
+size_t pcg2_tail_bytes(const Pcg2Plan &P);
+// one-time attribute setup + occupancy check; returns the number of CTAs to launch (<= SM count), 0 if the device cannot run it
+int pcg2_grid(int device);
+size_t pcg2_max_tail_bytes(int device);   // dynamic shared memory available to the tail
+cudaError_t pcg2_launch(const Pcg2Plan *dev_plan, int grid, size_t smem_bytes, double rtol2, int maxit, int stall_window, cudaStream_t s);
+
+// ---- sliced-ELL construction from a device CSR (int64 row pointers, int32 columns), once per pattern
+struct SellBuild {
+  SellMat M;
+  int *soff = nullptr, *idx = nullptr, *src = nullptr;   // src: CSR position of every padded entry, -1 = padding
+  double *val = nullptr;
+  float *valf = nullptr;
+};
+// width[s] = longest row of slice s (device array of nslices ints)
+cudaError_t sell_slice_widths(int64_t rows, int lpr, const int64_t *ptr, int *width, cudaStream_t s);
+// fills idx / src from the CSR pattern (soff already on the device)
+cudaError_t sell_fill_pattern(int64_t rows, int lpr, const int64_t *ptr, const int32_t *csr_idx, const int *soff, int *idx, int *src, cudaStream_t s);
+// val[e] = src[e] >= 0 ? csr_val[src[e]] : 0  (and the FP32 copy if valf != nullptr); called whenever the matrix values change
+cudaError_t sell_fill_values(int entries, const int *src, const double *csr_val, double *val, float *valf, cudaStream_t s);
+
+}  // namespace mgbx

@@ -730,11 +730,14 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_persistent(const PcgPlan
   }
   const double bb = grid_sum(part, slot0, P.bar);
   int it = 0;
-  double rr = bb, status = 1.0;
+  double rr = bb, status = 1.0, e_tot = 0.0, e_last4 = 0.0;
   if (bb > 0.0 && isfinite(bb)) {
     const double target = rtol2 * bb;
     double rz_old = 1.0, best = bb;
     int since_best = 0;
+    // energy bookkeeping: for CG from x = 0, b.x_k = |x_k|_A^2 = sum_j alpha_j (r.z)_j grows monotonically to b.A^-1 b -- the
+    // Newton decrement the caller needs; e_m4 is its value four iterations ago
+    double e_m1 = 0.0, e_m2 = 0.0, e_m3 = 0.0, e_m4 = 0.0;
     const PLevel &top = P.lev[0];
     while (it < maxit) {
       // z = M^{-1} r, with r.z accumulated in the last smoothing sweep of the top level
@@ -786,6 +789,11 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_persistent(const PcgPlan
         break;
       }
       const double alpha = rz / pAp;
+      e_m4 = e_m3;
+      e_m3 = e_m2;
+      e_m2 = e_m1;
+      e_m1 = e_tot;
+      e_tot += alpha * rz;
       double prr = 0.0;
       for (int64_t i = tid; i < m; i += nthr) {
         P.x[i] += alpha * __ldcg(pv + i);
@@ -808,12 +816,15 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_persistent(const PcgPlan
       }
     }
     if (status == 1.0 && rr > target) status = 3.0;   // iteration limit
+    e_last4 = e_tot - e_m4;
   }
   if (tid == 0) {
     P.out[0] = (double)it;
     P.out[1] = rr;
     P.out[2] = status;
     P.out[3] = bb;
+    P.out[4] = e_tot;      // b.x = |x|_A^2 (energy of the computed direction)
+    P.out[5] = e_last4;    // the part of it gained in the last four iterations
   }
 }
 

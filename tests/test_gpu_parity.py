@@ -326,7 +326,7 @@ def test_persistent_pcg_matches_multilaunch_pcg(tail_max):
     s = 1e-3 * rng.normal(size=m)
     g = rng.normal(size=m)
     out = []
-    for persistent in (0, 1):
+    for persistent in (0, 1, 2):
         h = native.Handle(prob, dense_direct_max=0, coarse_max=40, persistent=persistent, tail_max=tail_max, smoother=0, pcg_rtol=1e-11)
         try:
             x, its = h.solve_newton_system(0, J, 2.0, s, g)
@@ -337,8 +337,40 @@ def test_persistent_pcg_matches_multilaunch_pcg(tail_max):
             out.append((x, its))
         finally:
             h.close()
-    assert abs(out[0][1] - out[1][1]) <= 1
-    assert rel(out[1][0], out[0][0]) < 1e-8
+    for x, its in out[1:]:
+        assert abs(out[0][1] - its) <= 1
+        assert rel(x, out[0][0]) < 1e-8
+
+
+@pytest.mark.parametrize("smoother,fp32", [(1, 0), (1, 1), (0, 0)])
+def test_second_generation_persistent_kernel_matches_first(smoother, fp32):
+    """csrc/pcg2.cu (sliced-ELL levels, row ownership, tail out of shared memory with FP32 matrix values) against the
+    first-generation CSR kernel: the same preconditioned CG, so the same iteration count (+-1) and the same solution to the
+    PCG tolerance, with the Chebyshev and the l1-Jacobi smoother, with FP64 and FP32 preconditioner matrices, on a 2-D and a
+    3-D hierarchy, with and without a tail."""
+    for prob, kw in ((P.assemble(H.amg(G.subdivide(G.fem2d_P1(), 7)), p=1.5), dict(tail_max=1200)),
+                     (P.assemble(H.amg(G.structured_box(3, 12, k=1)), p=1.0), dict(tail_max=0)),
+                     (P.assemble(H.amg(G.structured_box(3, 12, k=1)), p=1.0), dict(tail_max=300))):
+        M = prob.M[0]
+        J = len(M.R_fine) - 1
+        m = M.R_fine[J].shape[1]
+        rng = np.random.default_rng(11)
+        s = 1e-3 * rng.normal(size=m)
+        g = rng.normal(size=m)
+        out = []
+        for persistent in (1, 2):
+            h = native.Handle(prob, dense_direct_max=0, coarse_max=40, persistent=persistent, smoother=smoother, precond_fp32=fp32, pcg_rtol=1e-11, **kw)
+            try:
+                x, its = h.solve_newton_system(0, J, 2.0, s, g)
+                Hm = h.hessian(0, J, 2.0, s)
+                assert np.linalg.norm(Hm @ x - g) <= 1e-9 * np.linalg.norm(g)
+                x2, its2 = h.solve_newton_system(0, J, 2.0, s, g)
+                assert np.array_equal(x, x2) and its == its2          # deterministic
+                out.append((x, its))
+            finally:
+                h.close()
+        assert abs(out[0][1] - out[1][1]) <= 1, (out[0][1], out[1][1])
+        assert rel(out[1][0], out[0][0]) < 1e-8
 
 
 def test_persistent_pcg_lane_widths_agree():
@@ -353,7 +385,7 @@ def test_persistent_pcg_lane_widths_agree():
     g = rng.normal(size=m)
     out = []
     for lanes in (-1, 0, -2, 1, 2, 8, 16, 32):
-        h = native.Handle(prob, dense_direct_max=0, coarse_max=40, tail_max=300, pcg_lanes=lanes, pcg_rtol=1e-11)
+        h = native.Handle(prob, dense_direct_max=0, coarse_max=40, tail_max=300, pcg_lanes=lanes, pcg_rtol=1e-11, persistent=1)
         try:
             x, its = h.solve_newton_system(0, J, 2.0, s, g)
             Hm = h.hessian(0, J, 2.0, s)
