@@ -161,15 +161,21 @@ typedef struct {
                                 Gershgorin bound of lambda_max in the Chebyshev interval (the bound stays as an upper clamp).  Default 0
                                 (off): measured on CPU only so far (tools/smoother_lab.py: 14-38 % fewer PCG iterations on 3-D
                                 problems, none in 2-D); to be enabled once run on hardware */
-  double pcg_fail_rtol;      /* a PCG solve that breaks down, or ends (stagnation / pcg_maxit) with |r|/|b| above this AND with the
-                                direction's energy still growing (pcg_fail_etol), is a FAILED solve: the Newton run reports "not
-                                converged" (as a failed factorisation would in the reference, src/utils.jl:142-145) instead of
-                                continuing with an under-converged direction.  Default 1e-5: Newton counts are unchanged down to
-                                1e-7 and within +-1 at 1e-6 (tools/inexact_newton_lab.py) */
+  double pcg_fail_rtol;      /* a PCG solve that breaks down is a FAILED solve: the Newton run reports "not converged" (as a failed
+                                factorisation would in the reference, src/utils.jl:142-145).  A solve that ends (stagnation / pcg_maxit)
+                                with |r|/|b| above this AND with the direction's energy still growing (pcg_fail_etol) is INEXACT: its
+                                direction is used (inexact Newton under the line search) but its decrement -- which a CG iterate
+                                under-estimates -- may not end the Newton iteration; only the stagnation rule of stopping_exact may.
+                                Both are counted in mgbx_step_result.solve_failures.  Default 1e-5: Newton counts are unchanged down
+                                to 1e-7 and within +-1 at 1e-6 (tools/inexact_newton_lab.py) */
   double pcg_fail_etol;      /* for CG from x = 0, g.x_k = |x_k|_A^2 grows monotonically to the Newton decrement g.H^-1 g.  Late in
                                 the t-ramp (conditioning ~ t^2) the residual norm can stall above pcg_fail_rtol although that
                                 energy -- what the stop rule and the Armijo test consume -- has converged: a stagnated solve is
                                 accepted when its last four iterations added less than this share of the energy.  Default 1e-8 */
+  int32_t pcg_stall_window;  /* PCG stops when the residual has not improved by 0.1 % for this many iterations (default 25; the
+                                finalize pass uses 6) */
+  int32_t direct_fallback;   /* 1 (default): a PCG solve that broke down or stayed inexact is redone by the dense Cholesky when the
+                                system has <= 8192 unknowns */
 } mgbx_config;
 
 /* options of one mgb_step (src/mgb.jl:16-30; defaults src/mgb.jl:360-363) */
@@ -194,8 +200,9 @@ typedef struct {
   double inc;                     /* last Newton decrement squared */
   int32_t f01_evals, f2_evals, linear_solves, pcg_iters;
   double ms_f01, ms_f2, ms_solve; /* device time (CUDA events) spent per stage */
-  int32_t solve_failures;         /* Newton runs abandoned because the linear solve failed (see pcg_fail_rtol) */
+  int32_t solve_failures;         /* linear solves that broke down (Newton run abandoned) or stayed inexact (see pcg_fail_rtol) */
   int32_t its_finalize;           /* the part of its[L-1] spent in the finalize pass (the reference adds it into its[L], src/mgb.jl:76-80) */
+  int32_t direct_fallbacks;       /* PCG solves redone by the dense direct solver (cfg.direct_fallback) */
 } mgbx_step_result;
 
 typedef struct {

@@ -48,8 +48,8 @@ end
 mutable struct StepResult                      # mgbx_step_result
     converged::Int32; its::NTuple{32,Int32}; y::Float64; gnorm::Float64; inc::Float64
     f01_evals::Int32; f2_evals::Int32; linear_solves::Int32; pcg_iters::Int32
-    ms_f01::Float64; ms_f2::Float64; ms_solve::Float64; solve_failures::Int32; its_finalize::Int32
-    StepResult() = new(0, ntuple(_ -> Int32(0), 32), 0.0, 0.0, 0.0, 0, 0, 0, 0, 0.0, 0.0, 0.0, 0, 0)
+    ms_f01::Float64; ms_f2::Float64; ms_solve::Float64; solve_failures::Int32; its_finalize::Int32; direct_fallbacks::Int32
+    StepResult() = new(0, ntuple(_ -> Int32(0), 32), 0.0, 0.0, 0.0, 0, 0, 0, 0, 0.0, 0.0, 0.0, 0, 0, 0)
 end
 mutable struct ScalarsOut                      # mgbx_scalars_out
     c_dot_Dz::Float64; var_max::NTuple{12,Float64}; var_absmax::NTuple{12,Float64}; all_finite::Int32

@@ -499,6 +499,10 @@ struct mgbx_handle {
   int rank = 0, nranks = 1;
   void *comm = nullptr;
   int device = -1;           // CUDA device ordinal the handle lives on (made current at every ABI entry point)
+  // phase profile of the second-generation solve kernel (env MGBX_PCG_PROF=1): summed ns and counts per tag (level * 16 + kind)
+  std::vector<double> prof_ns;
+  std::vector<int64_t> prof_cnt;
+  std::vector<unsigned long long> prof_host;
 };
 
 namespace {
@@ -1804,6 +1808,7 @@ System::Pcg2Dev &Engine::pcg2_plan(System &S, int ktop) {
   P.partials = S.pcg_partials;
   P.bar = S.pcg_bar;
   P.out = S.pcg_out;
+  if (getenv("MGBX_PCG_PROF")) P.prof = h->pool.zeros<unsigned long long>(1 + 2 * (size_t)kPcg2ProfCap, s);
   D.dev = h->pool.upload<Pcg2Plan>(&P, 1, s);
   CK(cudaStreamSynchronize(s));
   if (h->cfg.verbose > 0)
@@ -1820,6 +1825,22 @@ int Engine::pcg_persistent2(System &S, int ktop, const double *b, double *x) {
   pre_launch(KC_PCG);
   CK(pcg2_launch(D.dev, h->pcg2_grid, D.smem, h->cur_rtol2, h->cfg.pcg_maxit, h->cur_window, s));
   post_launch(KC_PCG);
+  if (D.host.prof) {   // debugging aid: accumulate the per-phase durations of this launch
+    h->prof_host.resize(1 + 2 * (size_t)kPcg2ProfCap);
+    CK(cudaMemcpyAsync(h->prof_host.data(), D.host.prof, sizeof(unsigned long long) * h->prof_host.size(), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (h->prof_ns.empty()) {
+      h->prof_ns.assign(kPcg2MaxLevels * 16, 0.0);
+      h->prof_cnt.assign(kPcg2MaxLevels * 16, 0);
+    }
+    const size_t nrec = (size_t)h->prof_host[0];
+    for (size_t q = 1; q < nrec; ++q) {
+      const int tag = (int)h->prof_host[1 + 2 * q];
+      if (tag < 0 || tag >= kPcg2MaxLevels * 16) continue;
+      h->prof_ns[tag] += (double)(h->prof_host[2 + 2 * q] - h->prof_host[2 + 2 * (q - 1)]);
+      h->prof_cnt[tag]++;
+    }
+  }
   CK(cudaMemcpyAsync(h->hscal + 8, S.pcg_out, sizeof(double) * 6, cudaMemcpyDeviceToHost, s));
   sync();
   const int it = (int)h->hscal[8];
@@ -1938,7 +1959,30 @@ int Engine::solve_compact(System &S, int ktop, const double *b, double *x) {
     LAUNCH(KC_VEC, k_axpby<<<nblk(Lv.m), 256, 0, s>>>(Lv.m, 1.0, x, 1.0, Lv.x2, x));
     return 0;
   }
-  return pcg(S, ktop, b, x);
+  const int it = pcg(S, ktop, b, x);
+  // PCG first, direct second: a solve that broke down or stayed inexact is redone by the dense Cholesky when the system is
+  // small enough to hold as a dense matrix (the un-condensable families, the last steps of a parabolic ramp)
+  const bool bad = h->last_solve_status < 0 || (h->last_solve_rel > h->cfg.pcg_fail_rtol && h->last_solve_erel > h->cfg.pcg_fail_etol);
+  if (bad && h->cfg.direct_fallback && Lv.m <= kDenseMaxUnknowns) {
+    if (h->cfg.verbose > 0)
+      fprintf(stderr, "[mgbx] PCG on %lld unknowns ended with status %d, |r|/|b| = %.3g: falling back to the dense direct solve\n", (long long)Lv.m,
+              h->last_solve_status, h->last_solve_rel);
+    const bool small = Lv.m <= kCoarseMaxDense;
+    if (!small) dense_factor(S, Lv, false);
+    auto apply = [&](const double *rhs, double *out) {
+      if (small) LAUNCH(KC_DENSE, k_dense_solve_small<<<1, 1024, dense_solve_small_smem((int)Lv.m), s>>>(Lv.A, rhs, out, nullptr));
+      else dense_apply(Lv, rhs, out);
+    };
+    apply(b, x);
+    spmv(Lv.A, x, b, -1.0, Lv.r, Lv.spmv_group);
+    apply(Lv.r, Lv.x2);
+    LAUNCH(KC_VEC, k_axpby<<<nblk(Lv.m), 256, 0, s>>>(Lv.m, 1.0, x, 1.0, Lv.x2, x));
+    h->last_solve_status = 1;
+    h->last_solve_rel = 0.0;
+    h->last_solve_erel = 0.0;
+    if (h->res) h->res->direct_fallbacks++;
+  }
+  return it;
 }
 
 // dir = H_J^{-1} g  (full level-J vectors).  With a condensed system the node-local variables are
@@ -2008,7 +2052,7 @@ Engine::NewtonOut Engine::newton(Amg &A, int J, double t, int maxit, int stop_ki
   // attainable accuracy so that it stagnates where a direct solve would
   const double rt = (stop_kind == 0) ? std::min(h->cfg.pcg_rtol, h->cfg.pcg_rtol_final) : h->cfg.pcg_rtol;
   h->cur_rtol2 = rt * rt;
-  h->cur_window = (stop_kind == 0) ? 6 : 25;   // finalize: iterate to the attainable accuracy, detected quickly
+  h->cur_window = (stop_kind == 0) ? 6 : std::max(1, h->cfg.pcg_stall_window);   // finalize: iterate to the attainable accuracy, detected quickly
   zero(A.x, m);
   EvalOut e0 = eval_f01(A, J, t, A.z, A.x, A.g);
   if (!e0.finite) {
@@ -2037,12 +2081,21 @@ Engine::NewtonOut Engine::newton(Amg &A, int J, double t, int maxit, int stop_ki
     // factorisation is for the reference's direct `H \\ g` (src/utils.jl:142-145): for a CG iterate g.x_k <= g.H^-1 g, so an
     // under-converged direction under-estimates the Newton decrement and could end the iteration early with a wrong z.
     // The Newton run is reported as not converged; mgb_core then shrinks kappa (or phase I grows the box).
-    if (h->last_solve_status < 0 || (h->last_solve_rel > h->cfg.pcg_fail_rtol && h->last_solve_erel > h->cfg.pcg_fail_etol)) {
+    bool solve_inexact = false;
+    if (h->last_solve_status < 0) {   // breakdown (indefinite or non-finite): no direction at all
       if (h->cfg.verbose > 0)
-        fprintf(stderr, "[mgbx] newton J=%d m=%lld k=%d: linear solve failed (status %d, |r|/|b| = %.3g, energy gained in the last 4 iterations %.3g, after %d PCG iterations)\n",
-                J, (long long)m, k, h->last_solve_status, h->last_solve_rel, h->last_solve_erel, pit < 0 ? -pit : pit);
+        fprintf(stderr, "[mgbx] newton J=%d m=%lld k=%d: linear solve broke down after %d PCG iterations\n", J, (long long)m, k, pit < 0 ? -pit : pit);
       if (h->res) h->res->solve_failures++;
       break;
+    }
+    if (h->last_solve_rel > h->cfg.pcg_fail_rtol && h->last_solve_erel > h->cfg.pcg_fail_etol) {
+      // under-converged: the direction is still a descent direction and is used (inexact Newton, guarded by the line search),
+      // but its decrement is not trusted to end the iteration
+      solve_inexact = true;
+      if (h->res) h->res->solve_failures++;
+      if (h->cfg.verbose > 0)
+        fprintf(stderr, "[mgbx] newton J=%d m=%lld k=%d: inexact linear solve (status %d, |r|/|b| = %.3g, energy gained in the last 4 iterations %.3g, after %d PCG iterations)\n",
+                J, (long long)m, k, h->last_solve_status, h->last_solve_rel, h->last_solve_erel, pit < 0 ? -pit : pit);
     }
     if (!dir_finite) {
       if (h->cfg.verbose > 0)
@@ -2133,7 +2186,8 @@ Engine::NewtonOut Engine::newton(Amg &A, int J, double t, int maxit, int stop_ki
       }
       sstep *= o.ls_beta;
     }
-    if (stop_test(stop_kind, lambda_tol, theta, ymin, yn, gmin, gnn, std::sqrt(inc))) converged = true;
+    // an under-converged solve under-estimates the decrement (g.x_k <= g.H^-1 g): only the stagnation rule may stop then
+    if (stop_test(solve_inexact ? 0 : stop_kind, lambda_tol, theta, ymin, yn, gmin, gnn, std::sqrt(inc))) converged = true;
     if (have_trial) {
       std::swap(A.x, A.xbest);
       std::swap(A.g, A.gbest);
@@ -2486,6 +2540,8 @@ void mgbx_default_config(mgbx_config *c) {
   c->lambda_power = 0;
   c->pcg_fail_rtol = 1e-5;
   c->pcg_fail_etol = 1e-8;
+  c->pcg_stall_window = 25;
+  c->direct_fallback = 1;
 }
 
 void mgbx_default_step_opts(mgbx_step_opts *o, int64_t n) {
@@ -2592,6 +2648,16 @@ static int g_comm_users = 0;   // live handles holding g_comm: it is neither rep
 void mgbx_destroy(mgbx_handle *h) {
   if (!h) return;
   if (h->device >= 0) cudaSetDevice(h->device);
+  if (!h->prof_ns.empty()) {
+    static const char *kinds[16] = {"first2", "pre", "resid", "restrict", "tail", "prolong", "post", "dense", "rz_sum", "pcg_matvec", "pcg_update", "init", "", "", "", ""};
+    double tot = 0.0;
+    for (double v : h->prof_ns) tot += v;
+    fprintf(stderr, "[mgbx] phase profile of k_pcg2 (CTA 0's clock; each phase ends at its grid barrier), total %.3f ms\n", tot * 1e-6);
+    for (size_t tag = 0; tag < h->prof_ns.size(); ++tag)
+      if (h->prof_cnt[tag])
+        fprintf(stderr, "[mgbx]   level %2d %-10s  n=%8lld  avg %7.2f us  total %8.3f ms  %5.1f %%\n", (int)(tag / 16), kinds[tag % 16], (long long)h->prof_cnt[tag],
+                h->prof_ns[tag] * 1e-3 / h->prof_cnt[tag], h->prof_ns[tag] * 1e-6, 100.0 * h->prof_ns[tag] / tot);
+  }
   if (h->comm && h->comm == g_comm && g_comm_users > 0) --g_comm_users;
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (int w = 0; w < 2; ++w)

@@ -34,6 +34,23 @@ __device__ __forceinline__ void grid_barrier2(unsigned int *bar) {
   __syncthreads();
 }
 
+// Optional phase profile (Pcg2Plan::prof != nullptr; debugging aid, env MGBX_PCG_PROF): thread 0 of CTA 0 appends
+// (tag, globaltimer) after the barrier that ends a grid-wide phase; tag = level * 16 + kind.
+enum { PK_FIRST2 = 0, PK_PRE = 1, PK_RESID = 2, PK_RESTRICT = 3, PK_TAIL = 4, PK_PROLONG = 5, PK_POST = 6, PK_DENSE = 7, PK_RZSUM = 8, PK_MATVEC = 9,
+       PK_UPDATE = 10, PK_INIT = 11 };
+__device__ __forceinline__ void prof_mark(unsigned long long *prof, int tag) {
+  if (prof && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const unsigned long long n = prof[0];
+    if (n + 1 < (unsigned long long)kPcg2ProfCap) {
+      prof[1 + 2 * n] = (unsigned long long)tag;
+      prof[2 + 2 * n] = t;
+      prof[0] = n + 1;
+    }
+  }
+}
+
 // Loads.  GRID scope: matrix data is immutable while the kernel runs (read-only path), vectors were written by other CTAs in
 // the previous phase (read at L2).  CTA scope (tail): everything lives in shared memory or is private to CTA 0: plain loads.
 template <bool GRID>
@@ -270,6 +287,7 @@ struct VcArgs {
   int nlev, nbig, bottom_dense, nu, nu_bottom, smoother;
   double cheb_ratio;
   const double *dense_inv;
+  unsigned long long *prof;
 };
 
 // V-cycle over the active levels [k0, k1) in scope `sc`; btop: right-hand side of level k0; lev: the level table of this scope
@@ -290,6 +308,7 @@ __device__ double vcycle(const VcArgs &P, const Pcg2Level *lev, const Scope<GRID
     if (last && P.bottom_dense) {
       ph_dense<GRID>(sc, P.dense_inv, Lv.m, bk, Lv.x);
       sc.sync();
+      if (GRID) prof_mark(P.prof, k * 16 + PK_DENSE);
       continue;
     }
     const bool cheb = (P.smoother == 1) && !last;   // an iterated bottom level keeps l1-Jacobi
@@ -312,11 +331,13 @@ __device__ double vcycle(const VcArgs &P, const Pcg2Level *lev, const Scope<GRID
       }
     }
     sc.sync();
+    if (GRID) prof_mark(P.prof, k * 16 + PK_FIRST2);
     for (int it = 0; it < npre; ++it) {
       if (cheb) rho = C.step(rho, c_dd, c_dr);
       // l1-Jacobi: every sweep is a "first" step (x += dinv (b - A x))
       ph_step<GRID>(sc, Lv.A, idg, bk, cur, oth, Lv.r, !cheb, th_inv, c_dd, c_dr, nullptr);
       sc.sync();
+      if (GRID) prof_mark(P.prof, k * 16 + PK_PRE);
       double *t = cur;
       cur = oth;
       oth = t;
@@ -324,14 +345,17 @@ __device__ double vcycle(const VcArgs &P, const Pcg2Level *lev, const Scope<GRID
     if (!last) {
       ph_spmv<GRID>(sc, Lv.A, cur, bk, -1.0, Lv.r);
       sc.sync();
+      if (GRID) prof_mark(P.prof, k * 16 + PK_RESID);
       ph_spmv<GRID>(sc, Lv.Tt, Lv.r, nullptr, 1.0, lev[k + 1].b);
       sc.sync();
+      if (GRID) prof_mark(P.prof, k * 16 + PK_RESTRICT);
     }
   }
   // ---- coarser levels
   if (GRID && k1 < P.nlev) {
     tail();
     sc.sync();
+    prof_mark(P.prof, k1 * 16 + PK_TAIL);
   }
   // ---- up
   for (int k = k1 - 1; k >= k0; --k) {
@@ -346,6 +370,7 @@ __device__ double vcycle(const VcArgs &P, const Pcg2Level *lev, const Scope<GRID
     double *cur = cur_x2 ? Lv.x2 : Lv.x, *oth = cur_x2 ? Lv.x : Lv.x2;
     ph_spmv<GRID>(sc, Lv.T, lev[k + 1].x, cur, 1.0, cur);   // x += T xc (row-local)
     sc.sync();
+    if (GRID) prof_mark(P.prof, k * 16 + PK_PROLONG);
     const bool cheb = (P.smoother == 1);
     const double *idg = cheb ? Lv.idiag : Lv.dinv;
     const Cheb C(cheb ? *Lv.lam : 1.0, P.cheb_ratio);
@@ -355,7 +380,10 @@ __device__ double vcycle(const VcArgs &P, const Pcg2Level *lev, const Scope<GRID
       const bool fin = (it == npost - 1) && (k == k0) && (dot_top != nullptr);
       if (cheb && it > 0) rho = C.step(rho, c_dd, c_dr);
       part += ph_step<GRID>(sc, Lv.A, idg, bk, cur, oth, Lv.r, !cheb || it == 0, th_inv, c_dd, c_dr, fin ? dot_top : nullptr);
-      if (!fin) sc.sync();
+      if (!fin) {
+        sc.sync();
+        if (GRID) prof_mark(P.prof, k * 16 + PK_POST);
+      }
       double *t = cur;
       cur = oth;
       oth = t;
@@ -443,7 +471,8 @@ __global__ void __launch_bounds__(kPcg2Threads, 1) k_pcg2(const Pcg2Plan *plan_g
   const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
   const int m = P.lev[0].m;
   double *slot0 = P.partials, *slot1 = P.partials + kPcg2MaxGrid, *slot2 = P.partials + 2 * kPcg2MaxGrid;
-  const VcArgs VA{P.nlev, P.nbig, P.bottom_dense, P.nu, P.nu_bottom, P.smoother, P.cheb_ratio, P.dense_inv};
+  const VcArgs VA{P.nlev, P.nbig, P.bottom_dense, P.nu, P.nu_bottom, P.smoother, P.cheb_ratio, P.dense_inv, P.prof};
+  if (P.prof && tid == 0) P.prof[0] = 0;
 
   // the tail: CTA 0 alone.  With shared-memory vectors the entry right-hand side is copied in (it was written by the whole
   // grid) and the result copied out to the global vector the grid prolongates from.
@@ -475,6 +504,7 @@ __global__ void __launch_bounds__(kPcg2Threads, 1) k_pcg2(const Pcg2Plan *plan_g
     part += bi * bi;
   }
   const double bb = grid_sum2(part, slot0, P.bar);
+  prof_mark(P.prof, PK_INIT);
   int it = 0;
   double rr = bb, status = 1.0, e_tot = 0.0, e_last4 = 0.0;
   if (bb > 0.0 && isfinite(bb)) {
@@ -498,6 +528,7 @@ __global__ void __launch_bounds__(kPcg2Threads, 1) k_pcg2(const Pcg2Plan *plan_g
         for (int64_t i = tid; i < m; i += nthr) prz += P.r[i] * __ldcg(z + i);
       }
       const double rz = grid_sum2(prz, slot1, P.bar);
+      prof_mark(P.prof, PK_RZSUM);
       const double beta = rz / rz_old;
       rz_old = rz;
       // p2 = z + beta p;  Ap = A p2 (neighbour values formed on the fly);  p2.Ap
@@ -519,6 +550,7 @@ __global__ void __launch_bounds__(kPcg2Threads, 1) k_pcg2(const Pcg2Plan *plan_g
         }
       }
       const double pAp = grid_sum2(ppap, slot2, P.bar);
+      prof_mark(P.prof, PK_MATVEC);
       {
         double *t = pv;
         pv = pv2;
@@ -542,6 +574,7 @@ __global__ void __launch_bounds__(kPcg2Threads, 1) k_pcg2(const Pcg2Plan *plan_g
         prr += ri * ri;
       }
       rr = grid_sum2(prr, slot0, P.bar);
+      prof_mark(P.prof, PK_UPDATE);
       if (!isfinite(rr)) {
         status = -1.0;
         break;

@@ -20,6 +20,7 @@ namespace mgbx {
 constexpr int kPcg2Threads = 1024;
 constexpr int kPcg2MaxGrid = 1024;
 constexpr int kPcg2MaxLevels = 32;
+constexpr int kPcg2ProfCap = 1 << 16;   // phase-profile records per launch (debugging aid)
 
 // sliced-ELL matrix: slice s holds rows [rps s, rps s + rps), rps = 32 / lpr; lane l of the owning warp reads the entries
 // idx/val[soff[s] + 32 j + l], j < width(s).
@@ -59,6 +60,7 @@ struct Pcg2Plan {
   const double *b = nullptr;
   double *partials = nullptr;  // 3 x kPcg2MaxGrid
   unsigned int *bar = nullptr;
+  unsigned long long *prof = nullptr;   // optional phase profile: [0] count, then (tag, globaltimer ns) pairs; tag = level * 16 + kind
   double *out = nullptr;       // [0] iterations, [1] |r|^2, [2] status (1 converged, 2 stagnated above the tolerance, 3 iteration limit, -1 breakdown), [3] |b|^2,
                                // [4] b.x = |x|_A^2, [5] the part of [4] gained in the last four iterations
 };

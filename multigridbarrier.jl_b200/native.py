@@ -60,7 +60,7 @@ class Config(C.Structure):
                 ("persistent", C.c_int32), ("tail_max", C.c_int32), ("pcg_rtol_final", C.c_double),
                 ("fused", C.c_int32), ("smoother", C.c_int32), ("cheb_ratio", C.c_double),
                 ("precond_fp32", C.c_int32), ("pcg_lanes", C.c_int32), ("lambda_power", C.c_int32),
-                ("pcg_fail_rtol", C.c_double), ("pcg_fail_etol", C.c_double)]
+                ("pcg_fail_rtol", C.c_double), ("pcg_fail_etol", C.c_double), ("pcg_stall_window", C.c_int32), ("direct_fallback", C.c_int32)]
 
 
 class StepOpts(C.Structure):
@@ -75,7 +75,7 @@ class StepResult(C.Structure):
                 ("gnorm", C.c_double), ("inc", C.c_double), ("f01_evals", C.c_int32),
                 ("f2_evals", C.c_int32), ("linear_solves", C.c_int32), ("pcg_iters", C.c_int32),
                 ("ms_f01", C.c_double), ("ms_f2", C.c_double), ("ms_solve", C.c_double),
-                ("solve_failures", C.c_int32), ("its_finalize", C.c_int32)]
+                ("solve_failures", C.c_int32), ("its_finalize", C.c_int32), ("direct_fallbacks", C.c_int32)]
 
 
 class ScalarsOut(C.Structure):

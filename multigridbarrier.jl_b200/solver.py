@@ -94,6 +94,7 @@ def mgb_core(h: native.Handle, which, L, tol=math.sqrt(EPS), t=0.1, maxit=10000,
             stats["linear_solves"] += r.linear_solves
             stats["pcg_iters"] += r.pcg_iters
             stats["solve_failures"] = stats.get("solve_failures", 0) + r.solve_failures
+            stats["direct_fallbacks"] = stats.get("direct_fallbacks", 0) + r.direct_fallbacks
             stats["ms_f01"] += r.ms_f01
             stats["ms_f2"] += r.ms_f2
             stats["ms_solve"] += r.ms_solve
@@ -252,7 +253,7 @@ def mgb_solve(prob, barrier_nodes=None, config=None, log=None, handle=None, comm
     t0 = time.time()
     h = handle if handle is not None else native.Handle(prob, barrier_weights=bw, comm=comm, **(config or {}))
     t_create = time.time() - t0
-    stats = dict(f01_evals=0, f2_evals=0, linear_solves=0, pcg_iters=0, solve_failures=0, ms_f01=0.0, ms_f2=0.0, ms_solve=0.0)
+    stats = dict(f01_evals=0, f2_evals=0, linear_solves=0, pcg_iters=0, solve_failures=0, direct_fallbacks=0, ms_f01=0.0, ms_f2=0.0, ms_solve=0.0)
     try:
         l0 = h.launch_count()
         sol = mgb_driver(h, prob.M, log=_log, stats=stats, **kw)

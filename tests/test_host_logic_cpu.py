@@ -54,7 +54,7 @@ class OracleHandle:
         fin = O.stopping_exact(o.finalize_theta) if o.finalize else None
         self.steps += 1
         r = types.SimpleNamespace(its=[0] * 32, f01_evals=0, f2_evals=0, linear_solves=0, pcg_iters=0, ms_f01=0.0, ms_f2=0.0, ms_solve=0.0,
-                                  converged=0, solve_failures=0, its_finalize=0)
+                                  converged=0, solve_failures=0, its_finalize=0, direct_fallbacks=0)
         try:
             SOL = O.mgb_step(Q, M, self.z[which], t * cost, o.maxit, o.max_newton, ls, sc, fin, initial_step=bool(o.initial_step),
                              barrier_weights=bw)
