@@ -129,7 +129,8 @@ typedef struct {
   int32_t dense_direct_max;  /* Newton systems with <= this many unknowns: dense Cholesky (default 2048) */
   int32_t coarse_max;        /* V-cycle is cut at the first level with <= this many unknowns (default 128 = the maximum) */
   int32_t pcg_maxit;         /* default 400 */
-  double pcg_rtol;           /* relative residual, default 1e-9 (Newton counts and the t-schedule match the direct-solve oracle, tests) */
+  double pcg_rtol;           /* relative residual, default 1e-7: Newton counts, the t-schedule and z are unchanged from 1e-9 down to 1e-6 on
+                                the bench workload (profiles/r02a_rtol_sweep.jsonl), the oracle lab says the same (tools/inexact_newton_lab.py) */
   int32_t smoother_sweeps;   /* pre = post smoothing sweeps (Chebyshev degree), default 2 */
   int32_t condense;          /* 1 (default): eliminate node-local :full variables exactly before PCG */
   int32_t device;            /* CUDA device ordinal, -1 = current */
@@ -157,10 +158,10 @@ typedef struct {
                                 -2: the same over {1, 2, 4, 8, 16, 32}; -1: by average row length only; 1 / 2 / 4 / 8 / 16 / 32
                                 forces that width on every level.  (Tuning hook: environment variable MGBX_TUNE_LANES =
                                 comma-separated widths per plan level, the last entry being the coarsest level, overrides modes 0 and -2.) */
-  int32_t lambda_power;      /* > 0: that many power iterations on D^-1 A per level and Newton system (warm-started) replace the
-                                Gershgorin bound of lambda_max in the Chebyshev interval (the bound stays as an upper clamp).  Default 0
-                                (off): measured on CPU only so far (tools/smoother_lab.py: 14-38 % fewer PCG iterations on 3-D
-                                problems, none in 2-D); to be enabled once run on hardware */
+  int32_t lambda_power;      /* -1 (default): automatic -- 6 when the top matrix averages more than 16 entries per row (3-D meshes), else 0;
+                                > 0: that many power iterations on D^-1 A per level and Newton system (warm-started) replace the
+                                Gershgorin bound of lambda_max in the Chebyshev interval (the bound stays as an upper clamp).  Measured on
+                                hardware (fem3d 32^3, profiles/r02c_stagnation_3d.jsonl): 42 % fewer PCG iterations; none in 2-D */
   double pcg_fail_rtol;      /* a PCG solve that breaks down is a FAILED solve: the Newton run reports "not converged" (as a failed
                                 factorisation would in the reference, src/utils.jl:142-145).  A solve that ends (stagnation / pcg_maxit)
                                 with |r|/|b| above this AND with the direction's energy still growing (pcg_fail_etol) is INEXACT: its
@@ -172,10 +173,14 @@ typedef struct {
                                 the t-ramp (conditioning ~ t^2) the residual norm can stall above pcg_fail_rtol although that
                                 energy -- what the stop rule and the Armijo test consume -- has converged: a stagnated solve is
                                 accepted when its last four iterations added less than this share of the energy.  Default 1e-8 */
-  int32_t pcg_stall_window;  /* PCG stops when the residual has not improved by 0.1 % for this many iterations (default 25; the
-                                finalize pass uses 6) */
+  int32_t pcg_stall_window;  /* PCG stops when the residual has not improved by 0.1 % for this many iterations (default 100: late in a 3-D
+                                ramp the residual plateaus for dozens of iterations before it drops -- with 25 the solves of fem3d 32^3 stopped
+                                at |r|/|b| ~ 1e-3; the finalize pass uses 6) */
   int32_t direct_fallback;   /* 1 (default): a PCG solve that broke down or stayed inexact is redone by the dense Cholesky when the
                                 system has <= 8192 unknowns */
+  int32_t elem_bulk;         /* 1 (default): the fused element kernel stages each tile's operator slabs and node columns with
+                                cp.async.bulk (one instruction per slab / block column, completion on an mbarrier) instead of one
+                                8-byte cp.async per double; 0: the per-double path */
 } mgbx_config;
 
 /* options of one mgb_step (src/mgb.jl:16-30; defaults src/mgb.jl:360-363) */
@@ -268,6 +273,9 @@ int mgbx_solve_newton_system(mgbx_handle *h, int which, int level, double t, con
 
 /* number of kernels launched through this handle so far (bench.py's gpu_launches) */
 int64_t mgbx_launch_count(const mgbx_handle *h);
+
+/* device memory held by the handle, by category (text, one line per category) and in total */
+int mgbx_memory_report(mgbx_handle *h, char *buf, int64_t buflen, int64_t *total_bytes);
 
 /* shape of the fine-level linear system and of the persistent solve kernel's plan (for roofline arithmetic);
  * zero-filled until the first fine-level Newton system has been solved */

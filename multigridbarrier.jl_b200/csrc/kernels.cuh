@@ -947,6 +947,8 @@ __device__ __forceinline__ unsigned int fdiv(unsigned int t, const FastDiv &f) {
 struct PlapParams {
   int64_t n, N;
   int p, epb, p1, ES;
+  int bulk;                    // 0: per-double cp.async staging; 1: one bulk copy per operator slab (p1 == p, ES == p*p);
+                               // 2: one bulk copy per block column (p even, p1 and ES even).  Ragged tiles use the per-double path.
   FastDiv dp, dpp;
   const double *ops[3];
   const double *zu, *zs;       // broken state of u and s (n each)
@@ -980,13 +982,42 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// ---- bulk asynchronous copies (cp.async.bulk, the 1-D form of TMA: SASS UBLKCP) completing on an mbarrier -------------------
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned int)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned int bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned int)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned int parity) {
+  const unsigned int a = (unsigned int)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(a),
+      "r"(parity)
+      : "memory");
+}
+// bytes: multiple of 16; smem and gmem 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void *smem, const void *gmem, unsigned int bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"((unsigned int)__cvta_generic_to_shared(smem)),
+               "l"(gmem), "r"(bytes), "r"((unsigned int)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // Tiles are software-pipelined: while tile k is evaluated, the operator blocks and node inputs of tile k+1 stream into the
 // other shared-memory buffer with cp.async (LDGSTS), so the evaluation never waits on HBM latency after the first tile.
 // COND: the slack is condensed node-locally (fine-level systems); !COND: nothing is eliminated and the four block pairs
 // (u,u), (u,s), (s,u), (s,s) are written (the coarse-level systems of the mgb_step recovery path).
 template <int MODE, int DIM, bool COND>
 __global__ void __launch_bounds__(256, 3) k_elem_plap(PlapParams P) {
-  extern __shared__ double esm[];
+  extern __shared__ __align__(16) double esm[];
   constexpr int NH = (DIM * (DIM + 1)) / 2;
   constexpr int NEX = NH > DIM ? NH : DIM;
   constexpr int NF = DIM + 2;
@@ -1000,6 +1031,17 @@ __global__ void __launch_bounds__(256, 3) k_elem_plap(PlapParams P) {
   const int op4[4] = {0, 0, 0, 1};
   const int64_t ntiles = (P.N + epb - 1) / epb;
   const double al = 2.0 / P.pexp;
+  // completion barriers of the two input buffers (bulk staging); a tile arms its buffer's barrier with the bytes it will receive
+  __shared__ __align__(8) unsigned long long mbar[2];
+  unsigned int mphase = 0u;   // bit b: parity of buffer b's next completion
+  if (P.bulk) {
+    if (tid == 0) {
+      mbar_init(&mbar[0], 1);
+      mbar_init(&mbar[1], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  }
   // buffer layout: ops [a][el][c][r] padded | us | ss | ws | bws | fs[NF]
   auto issue = [&](int64_t tile, int b) {
     double *buf = esm + (size_t)b * bufsz;
@@ -1007,6 +1049,48 @@ __global__ void __launch_bounds__(256, 3) k_elem_plap(PlapParams P) {
     const int ne = (int)min((int64_t)epb, P.N - e0);
     const int T = ne * p;
     const int64_t node0 = e0 * p;
+    if (P.bulk) {
+      // whole slabs move with one instruction each (UBLKCP); a ragged last tile (odd sizes break the 16-byte rule) falls through
+      // to the per-double path below and arms the barrier with zero bytes
+      const bool regular = ((ne & 1) == 0 || (p & 1) == 0) && ((T & 1) == 0);
+      if (regular) {
+        double *nd = buf + (size_t)DIM * epb * ES;
+        const int narr = 3 + (P.bw ? 1 : 0) + NF;
+        const unsigned int opbytes = (unsigned int)(ne * pp * 8), ndbytes = (unsigned int)(T * 8);
+        if (tid == 0) {
+          fence_proxy_async_smem();
+          mbar_expect_tx(&mbar[b], DIM * opbytes + narr * ndbytes);
+        }
+        __syncwarp();
+        if (P.bulk == 1) {
+          if (tid < DIM) bulk_g2s(buf + (size_t)tid * epb * ES, P.ops[tid] + e0 * (int64_t)pp, opbytes, &mbar[b]);
+        } else {
+          for (int t = tid; t < DIM * ne * p; t += 256) {   // one block column (p doubles) per copy into the padded layout
+            const int a = t / (ne * p), rem = t - a * ne * p;
+            const int el = (int)fdiv((unsigned int)rem, P.dp), c = rem - el * p;
+            bulk_g2s(buf + (size_t)a * epb * ES + el * ES + c * p1, P.ops[a] + (e0 + el) * (int64_t)pp + c * p, (unsigned int)(p * 8), &mbar[b]);
+          }
+        }
+        if (tid >= 32 && tid < 32 + narr) {
+          const int k = tid - 32;
+          const double *src;
+          double *dst;
+          if (k == 0) { src = P.zu; dst = nd; }
+          else if (k == 1) { src = P.zs; dst = nd + TM; }
+          else if (k == 2) { src = P.w; dst = nd + 2 * TM; }
+          else if (P.bw && k == 3) { src = P.bw; dst = nd + 3 * TM; }
+          else {
+            const int j = k - 3 - (P.bw ? 1 : 0);
+            src = P.f + (int64_t)j * P.n;
+            dst = nd + (4 + j) * TM;
+          }
+          bulk_g2s(dst, src + node0, ndbytes, &mbar[b]);
+        }
+        cp_async_commit();   // (empty group: keeps the wait_group bookkeeping of the ragged path uniform)
+        return;
+      }
+      if (tid == 0) mbar_expect_tx(&mbar[b], 0);
+    }
 #pragma unroll
     for (int a = 0; a < DIM; ++a) {
       const double *src = P.ops[a] + e0 * (int64_t)pp;
@@ -1038,6 +1122,10 @@ __global__ void __launch_bounds__(256, 3) k_elem_plap(PlapParams P) {
       cp_async_wait<1>();
     } else {
       cp_async_wait<0>();
+    }
+    if (P.bulk) {
+      mbar_wait(&mbar[b], (mphase >> b) & 1u);
+      mphase ^= 1u << b;
     }
     __syncthreads();
     const double *ops_s = esm + (size_t)b * bufsz;

@@ -138,6 +138,8 @@ NcclApi &nccl_api() {
 struct Pool {
   std::vector<void *> ptrs;
   size_t bytes = 0;
+  const char *cat = "problem";                 // category the next allocations are booked under (mgbx_memory_report)
+  std::map<std::string, size_t> by_cat;
   cudaStream_t stream = nullptr;   // set at create: allocations are stream-ordered (cudaMallocAsync), cheap and reusable
   template <class T>
   T *alloc(size_t n) {
@@ -147,6 +149,7 @@ struct Pool {
     if (e != cudaSuccess) throw std::runtime_error(std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
     ptrs.push_back(p);
     bytes += n * sizeof(T);
+    by_cat[cat] += n * sizeof(T);
     return (T *)p;
   }
   template <class T>
@@ -894,10 +897,26 @@ struct Engine {
     Q.p = A.p;
     Q.p1 = A.p | 1;
     Q.ES = (A.p * Q.p1) | 1;
+    // bulk staging (cfg.elem_bulk): operator slabs and node columns arrive by cp.async.bulk instead of one 8-byte cp.async per
+    // double.  Odd p: the padded layout already equals the contiguous one (p1 == p, ES == p*p) -> one copy per operator slab;
+    // even p: columns are padded to p + 2 (16-byte aligned, conflict-free transposed reads) -> one copy per block column.
+    Q.bulk = 0;
+    if (h->cfg.elem_bulk) {
+      if (A.p & 1) {
+        if (Q.p1 == A.p && Q.ES == A.p * A.p) Q.bulk = 1;
+      } else {
+        Q.p1 = A.p + 2;
+        Q.ES = A.p * Q.p1;
+        if (Q.ES % 16 == 0) Q.ES += 8;
+        Q.bulk = 2;
+      }
+    }
     int epb = std::max(1, 256 / A.p);
     const size_t cap = 216 * 1024, want = 72 * 1024;   // aim at 3 resident CTAs per SM (double-buffered tiles)
     while (epb > 1 && elem_plap_smem(dim, epb, Q.ES, A.p, cond) > want && epb * A.p > 128) epb = (epb + 1) / 2;
     while (epb > 1 && elem_plap_smem(dim, epb, Q.ES, A.p, cond) > cap) epb = (epb + 1) / 2;
+    if (Q.bulk && (epb & 1) && epb > 1) --epb;         // even tiles keep every slab a multiple of 16 bytes and 16-byte aligned
+    if (Q.bulk && (epb & 1) && (A.p & 1)) Q.bulk = 0;  // a one-element tile of an odd element cannot be bulk-copied
     smem = elem_plap_smem(dim, epb, Q.ES, A.p, cond);
     if (smem > cap) return false;
     Q.epb = epb;
@@ -916,6 +935,18 @@ struct Engine {
     Q.partials = h->partials;
     Q.ticket = h->ticket;
     Q.red_out = dist() ? h->dscal + 40 : h->dscal;
+    if (Q.bulk) {   // bulk copies need 16-byte aligned sources: every base pointer, and the column stride n of f / the state blocks
+      auto al16 = [](const void *q) { return q == nullptr || ((uintptr_t)q & 15) == 0; };
+      bool ok = al16(Q.zu) && al16(Q.zs) && al16(Q.w) && al16(Q.bw) && al16(Q.f) && (A.n % 2 == 0);
+      for (int a = 0; a < dim; ++a) ok = ok && al16(Q.ops[a]);
+      if (!ok) {   // fall back to the per-double staging with its own padding
+        Q.bulk = 0;
+        Q.p1 = A.p | 1;
+        Q.ES = (A.p * Q.p1) | 1;
+        smem = elem_plap_smem(dim, epb, Q.ES, A.p, cond);
+        if (smem > cap) return false;
+      }
+    }
     const int64_t ntiles = (A.N + epb - 1) / epb;
     grid = (unsigned int)std::max<int64_t>(1, std::min<int64_t>(ntiles, kRedBlocks));
     return true;
@@ -991,6 +1022,15 @@ struct Engine {
   bool precond_fp32(const System &S) const {
     return h->cfg.precond_fp32 == 1 || (h->cfg.precond_fp32 == 2 && !S.lev.empty() && S.lev[0].A.nnz >= 8000000);
   }
+  // power iterations per level and assembly for lambda_max(D^-1 A): cfg.lambda_power, or automatic (-1): 6 when the top
+  // matrix has long rows (3-D stencils: the Gershgorin bound overestimates 1.3-2.5x there and misplaces the Chebyshev
+  // interval -- measured on fem3d 32^3: 14 194 -> 8 294 PCG iterations per solve), none on 2-D meshes (bound within 4 %)
+  int lambda_power_its(const System &S) const {
+    if (h->cfg.lambda_power >= 0) return h->cfg.lambda_power;
+    if (S.lev.empty() || S.lev[0].A.rows == 0) return 0;
+    return ((double)S.lev[0].A.nnz / (double)S.lev[0].A.rows > 16.0) ? 6 : 0;
+  }
+  bool gen2_power(const System &S) const { return h->cfg.persistent == 2 && h->pcg2_grid > 0 && (int64_t)S.lev.size() * h->pcg2_grid <= 3 * (int64_t)kPcg2MaxGrid; }
   bool use_direct(const System &S, const SysLevel &Lv) const {
     return S.dense || Lv.m <= h->cfg.dense_direct_max;   // dense (spectral) systems have no hierarchy: always direct
   }
@@ -1067,6 +1107,7 @@ constexpr int kDenseMaxUnknowns = 8192;   // blocked Cholesky: the triangular so
 std::unique_ptr<System> build_system(mgbx_handle *h, Amg &A, bool condensed, int ltop) {
   auto S = std::make_unique<System>();
   Pool &pool = h->pool;
+  pool.cat = "system: patterns, gather plans, level vectors";
   cudaStream_t s = h->stream;
   const int L = ltop + 1;            // levels 0..ltop take part
   S->condensed = condensed;
@@ -1264,7 +1305,9 @@ std::unique_ptr<System> build_system(mgbx_handle *h, Amg &A, bool condensed, int
     einct.free_all();
     if (rtmp.d.ptr) rtmp.free_all();
   }
+  pool.cat = "system: element block Hessians";
   S->Hblk = pool.alloc<double>(S->hblk_size);
+  pool.cat = "system: Galerkin patterns and term lists";
   if (vb) fprintf(stderr, "[mgbx]   gather plan (%lld padded terms) %.3fs\n", (long long)S->top.nterms, tm.lap());
   // hierarchy patterns (device symbolic products) and Galerkin gather plans
   for (int k = 0; k < nlev; ++k) {
@@ -1474,7 +1517,7 @@ void Engine::setup_hierarchy(Amg &A, System &S, int ktop) {
     SysLevel &Lv = S.lev[k];
     CK(cudaMemsetAsync(Lv.lam, 0, sizeof(double), s));
     LAUNCH(KC_VEC, k_l1diag<<<nblk(Lv.m), 256, 0, s>>>(Lv.A, Lv.dinv, Lv.diag, (unsigned long long *)Lv.lam));
-    if (h->cfg.lambda_power > 0 && Lv.m > 1) lambda_power(Lv, h->cfg.lambda_power);
+    if (lambda_power_its(S) > 0 && Lv.m > 1 && !gen2_power(S)) lambda_power(Lv, lambda_power_its(S));
     if (precond_fp32(S)) {
       if (!Lv.val32) Lv.val32 = h->pool.alloc<float>(Lv.A.nnz);
       LAUNCH(KC_VEC, k_f64_to_f32<<<nblk(Lv.A.nnz), 256, 0, s>>>(Lv.A.nnz, Lv.A.val, Lv.val32));
@@ -1486,7 +1529,14 @@ void Engine::setup_hierarchy(Amg &A, System &S, int ktop) {
     if (!Lc.dense_inv) Lc.dense_inv = h->pool.alloc<double>((size_t)m * m);
     LAUNCH(KC_DENSE, k_coarse_inverse<<<1, 1024, coarse_inverse_smem(m), s>>>(Lc.A, Lc.dense_inv));
   }
-  if (h->cfg.persistent == 2 && h->pcg2_grid > 0) sell_prepare(S, ktop);
+  if (h->cfg.persistent == 2 && h->pcg2_grid > 0) {
+    sell_prepare(S, ktop);
+    if (lambda_power_its(S) > 0 && gen2_power(S)) {   // all levels' power iterations in one cooperative launch
+      System::Pcg2Dev &D = pcg2_plan(S, ktop);
+      if ((int64_t)D.host.nlev * h->pcg2_grid > 3 * (int64_t)kPcg2MaxGrid) throw std::runtime_error("internal: too many levels for the power-iteration kernel");
+      LAUNCH(KC_VEC, CK(pcg2_lambda_power(D.dev, h->pcg2_grid, lambda_power_its(S), 1.2, s)));
+    }
+  }
 }
 
 void Engine::dense_factor(System &S, SysLevel &Lv, bool want_inverse) {
@@ -1680,6 +1730,7 @@ int Engine::pcg_persistent(System &S, int ktop, const double *b, double *x) {
 // sliced-ELL copy of a device CSR pattern (32 rows per slice, slices-per-CTA for the grid the kernel is launched with)
 SellBuild Engine::make_sell(const DevCsr &A, int64_t nthreads) {
   SellBuild B;
+  h->pool.cat = "solve kernel: sliced-ELL level matrices";
   if (A.rows >= INT32_MAX / 2) throw std::runtime_error("persistent solve kernel: a level matrix exceeds 32-bit indexing");
   // lanes per row: widen while the level leaves at least half of the threads that share its phases idle and the rows
   // still give every lane two entries (measured, tools/micro/bench_spmv_phase: one lane per row wins on the two finest
@@ -1783,6 +1834,12 @@ System::Pcg2Dev &Engine::pcg2_plan(System &S, int ktop) {
     pl.x = Lv.x;
     pl.x2 = Lv.x2;
     pl.r = Lv.r;
+    if (!Lv.pw) {   // power-iteration vector (warm-started across Newton iterations)
+      Lv.pw = h->pool.alloc<double>(Lv.m);
+      Lv.pw_nrm = h->pool.zeros<double>(1, s);
+      LAUNCH(KC_VEC, k_pw_init<<<nblk(Lv.m), 256, 0, s>>>(Lv.m, Lv.pw));
+    }
+    pl.pw = Lv.pw;
   }
   // the tail [nbig, nlev): levels with <= tail_max unknowns, as many as fit into CTA 0's shared memory
   int dev = 0;
@@ -2085,6 +2142,13 @@ Engine::NewtonOut Engine::newton(Amg &A, int J, double t, int maxit, int stop_ki
     if (h->last_solve_status < 0) {   // breakdown (indefinite or non-finite): no direction at all
       if (h->cfg.verbose > 0)
         fprintf(stderr, "[mgbx] newton J=%d m=%lld k=%d: linear solve broke down after %d PCG iterations\n", J, (long long)m, k, pit < 0 ? -pit : pit);
+      if (h->res) h->res->solve_failures++;
+      break;
+    }
+    if (h->last_solve_rel > 0.5 && h->last_solve_erel > h->cfg.pcg_fail_etol) {   // no better than the zero vector: a failed solve
+      if (h->cfg.verbose > 0)
+        fprintf(stderr, "[mgbx] newton J=%d m=%lld k=%d: linear solve failed (status %d, |r|/|b| = %.3g after %d PCG iterations)\n", J, (long long)m, k,
+                h->last_solve_status, h->last_solve_rel, pit < 0 ? -pit : pit);
       if (h->res) h->res->solve_failures++;
       break;
     }
@@ -2522,7 +2586,7 @@ void mgbx_default_config(mgbx_config *c) {
   c->dense_direct_max = 2048;
   c->coarse_max = 128;
   c->pcg_maxit = 400;
-  c->pcg_rtol = 1e-9;
+  c->pcg_rtol = 1e-7;
   c->smoother_sweeps = 2;
   c->condense = 1;
   c->device = -1;
@@ -2537,11 +2601,12 @@ void mgbx_default_config(mgbx_config *c) {
   c->cheb_ratio = 8.0;
   c->precond_fp32 = 2;
   c->pcg_lanes = 0;
-  c->lambda_power = 0;
+  c->lambda_power = -1;
   c->pcg_fail_rtol = 1e-5;
   c->pcg_fail_etol = 1e-8;
-  c->pcg_stall_window = 25;
+  c->pcg_stall_window = 100;
   c->direct_fallback = 1;
+  c->elem_bulk = 1;
 }
 
 void mgbx_default_step_opts(mgbx_step_opts *o, int64_t n) {
@@ -2891,6 +2956,23 @@ int mgbx_set_grids(mgbx_handle *h, const double *f_grid, const double *g_grid) {
 }
 
 int64_t mgbx_launch_count(const mgbx_handle *h) { return h ? h->launches : 0; }
+
+int mgbx_memory_report(mgbx_handle *h, char *buf, int64_t buflen, int64_t *total_bytes) {
+  if (!h) return MGBX_ERR_ARG;
+  std::string out;
+  for (auto &kv : h->pool.by_cat) {
+    char line[256];
+    snprintf(line, sizeof(line), "%-52s %10.1f MB\n", kv.first.c_str(), kv.second / 1e6);
+    out += line;
+  }
+  if (total_bytes) *total_bytes = (int64_t)h->pool.bytes;
+  if (buf && buflen > 0) {
+    const size_t nc = std::min<size_t>(out.size(), (size_t)buflen - 1);
+    memcpy(buf, out.data(), nc);
+    buf[nc] = 0;
+  }
+  return MGBX_OK;
+}
 
 int mgbx_solver_info(mgbx_handle *h, int which, mgbx_solver_info_t *out) {
   if (!h || !out || which < 0 || which > 1) return MGBX_ERR_ARG;

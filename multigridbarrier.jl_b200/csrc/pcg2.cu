@@ -161,8 +161,10 @@ __device__ __forceinline__ double sell_row_any(const SellMat &A, int s, int lane
 }
 
 // y = alpha * M x + (y0 ? y0 : 0)      (y may alias y0; y must not alias x)
+// ys != nullptr: also ys = y .* yscale (the pre-scaled right-hand side the next level's first smoothing pass gathers)
 template <bool GRID>
-__device__ void ph_spmv(const Scope<GRID> &sc, const SellMat &M, const double *x, const double *y0, double alpha, double *y) {
+__device__ void ph_spmv(const Scope<GRID> &sc, const SellMat &M, const double *x, const double *y0, double alpha, double *y, double *ys = nullptr,
+                        const double *yscale = nullptr) {
   int s0, s1;
   sc.range(M, s0, s1);
   const GatherX<GRID> g{x};
@@ -170,7 +172,11 @@ __device__ void ph_spmv(const Scope<GRID> &sc, const SellMat &M, const double *x
     bool lead;
     const int row = sell_rowof(M, s, sc.lane, lead);
     const double acc = sell_row_any<GRID>(M, s, sc.lane, g);
-    if (lead) y[row] = alpha * acc + (y0 ? Ld<GRID>::v(y0 + row) : 0.0);
+    if (lead) {
+      const double v = alpha * acc + (y0 ? Ld<GRID>::v(y0 + row) : 0.0);
+      y[row] = v;
+      if (ys) ys[row] = v * Ld<GRID>::m(yscale + row);
+    }
   }
 }
 
@@ -196,12 +202,13 @@ struct Cheb {
 };
 
 // steps 0 and 1 from x = 0 in one pass: d0 = th_inv D^-1 b; r1 = b - A d0; d1 = c_dd d0 + c_dr D^-1 r1; x = d0 + d1
+// bs = b .* idiag is written by whoever produced b (restriction, PCG update), so that the row sums gather ONE vector
 template <bool GRID>
-__device__ void ph_first2(const Scope<GRID> &sc, const SellMat &A, const double *idiag, const double *b, double *xnew, double *d, double th_inv,
-                          double c_dd, double c_dr) {
+__device__ void ph_first2(const Scope<GRID> &sc, const SellMat &A, const double *idiag, const double *b, const double *bs, double *xnew, double *d,
+                          double th_inv, double c_dd, double c_dr) {
   int s0, s1;
   sc.range(A, s0, s1);
-  const GatherScaled<GRID> g{b, idiag};
+  const GatherX<GRID> g{bs};
   for (int s = s0 + sc.warp; s < s1; s += sc.nwarps) {
     bool lead;
     const int row = sell_rowof(A, s, sc.lane, lead);
@@ -296,6 +303,28 @@ struct VcArgs {
 // makes the last sweep land in x, so no pointer is ever swapped and every CTA agrees on where results live.
 // dot_top != nullptr: returns this thread's share of sum dot_top[i] x[i] on level k0, and the barrier after the last sweep is
 // left to the caller's grid_sum.
+// Where level k's down-sweep starts and which diagonal it scales with: `cur` receives the first smoothing pass, `oth` is free
+// until the next sweep -- it holds bs = b .* idg for that pass.  The producer of b (restriction / PCG update) and the consumer
+// (ph_first2) must agree, hence one function.
+struct SmoothBufs {
+  double *cur, *oth;
+  const double *idg;
+  bool two;   // the level starts with the fused two-step pass (ph_first2), i.e. it reads bs
+};
+__device__ __forceinline__ SmoothBufs smooth_bufs(const VcArgs &P, const Pcg2Level &Lv, int k) {
+  const bool last = (k == P.nlev - 1);
+  const bool cheb = (P.smoother == 1) && !last;
+  const int want = last ? P.nu_bottom : P.nu;
+  const int done = (want >= 2) ? 2 : 1;
+  const int npre = want - done, npost = last ? 0 : P.nu;
+  SmoothBufs B;
+  B.cur = ((npre + npost) & 1) ? Lv.x2 : Lv.x;
+  B.oth = ((npre + npost) & 1) ? Lv.x : Lv.x2;
+  B.idg = cheb ? Lv.idiag : Lv.dinv;
+  B.two = (done == 2) && !(last && P.bottom_dense);
+  return B;
+}
+
 template <bool GRID, class Tail>
 __device__ double vcycle(const VcArgs &P, const Pcg2Level *lev, const Scope<GRID> &sc, int k0, int k1, const double *btop, const double *dot_top,
                          const Tail &tail) {
@@ -322,7 +351,7 @@ __device__ double vcycle(const VcArgs &P, const Pcg2Level *lev, const Scope<GRID
     const double th_inv = cheb ? C.th_inv : 1.0;
     if (done == 2) {
       if (cheb) rho = C.step(rho, c_dd, c_dr);
-      ph_first2<GRID>(sc, Lv.A, idg, bk, cur, Lv.r, th_inv, c_dd, c_dr);
+      ph_first2<GRID>(sc, Lv.A, idg, bk, oth, cur, Lv.r, th_inv, c_dd, c_dr);   // oth holds b .* idg (smooth_bufs)
     } else {
       for (int i = sc.tid(); i < Lv.m; i += sc.nthr()) {
         const double d0 = th_inv * Ld<GRID>::v(bk + i) * Ld<GRID>::m(idg + i);
@@ -346,7 +375,10 @@ __device__ double vcycle(const VcArgs &P, const Pcg2Level *lev, const Scope<GRID
       ph_spmv<GRID>(sc, Lv.A, cur, bk, -1.0, Lv.r);
       sc.sync();
       if (GRID) prof_mark(P.prof, k * 16 + PK_RESID);
-      ph_spmv<GRID>(sc, Lv.Tt, Lv.r, nullptr, 1.0, lev[k + 1].b);
+      {
+        const SmoothBufs nb = smooth_bufs(P, lev[k + 1], k + 1);
+        ph_spmv<GRID>(sc, Lv.Tt, Lv.r, nullptr, 1.0, lev[k + 1].b, nb.two ? nb.oth : nullptr, nb.idg);
+      }
       sc.sync();
       if (GRID) prof_mark(P.prof, k * 16 + PK_RESTRICT);
     }
@@ -481,9 +513,16 @@ __global__ void __launch_bounds__(kPcg2Threads, 1) k_pcg2(const Pcg2Plan *plan_g
     const Scope<false> cta{0, 1, warp, nwarps, lane, nullptr};
     const int nb = P.nbig;
     const Pcg2Level *tl = TL - nb;   // indexed by level
-    if (tail_smem) {
+    {
+      // the entry right-hand side was written by the whole grid: copy it into CTA 0's vector (shared memory) together with its
+      // pre-scaled copy for the first smoothing pass
+      const SmoothBufs sb = smooth_bufs(VA, TL[0], nb);
       const double *gb = P.lev[nb].b;
-      for (int i = threadIdx.x; i < TL[0].m; i += blockDim.x) TL[0].b[i] = __ldcg(gb + i);
+      for (int i = threadIdx.x; i < TL[0].m; i += blockDim.x) {
+        const double v = __ldcg(gb + i);
+        if (tail_smem) TL[0].b[i] = v;
+        if (sb.two) sb.oth[i] = v * sb.idg[i];
+      }
       __syncthreads();
     }
     vcycle<false>(VA, tl, cta, nb, P.nlev, TL[0].b, nullptr, NoTail());
@@ -495,12 +534,14 @@ __global__ void __launch_bounds__(kPcg2Threads, 1) k_pcg2(const Pcg2Plan *plan_g
 
   // the p / p2 ping-pong lives in registers
   double *pv = P.p, *pv2 = P.p2;
+  const SmoothBufs top_sb = smooth_bufs(VA, P.lev[0], 0);   // r .* idiag for the top level's first smoothing pass goes to top_sb.oth
   double part = 0.0;
   for (int64_t i = tid; i < m; i += nthr) {
     const double bi = P.b[i];
     P.x[i] = 0.0;
     pv[i] = 0.0;
     P.r[i] = bi;
+    if (top_sb.two) top_sb.oth[i] = bi * __ldg(top_sb.idg + i);
     part += bi * bi;
   }
   const double bb = grid_sum2(part, slot0, P.bar);
@@ -571,6 +612,7 @@ __global__ void __launch_bounds__(kPcg2Threads, 1) k_pcg2(const Pcg2Plan *plan_g
         P.x[i] += alpha * __ldcg(pv + i);
         const double ri = P.r[i] - alpha * __ldcg(P.Ap + i);
         P.r[i] = ri;
+        if (top_sb.two) top_sb.oth[i] = ri * __ldg(top_sb.idg + i);
         prr += ri * ri;
       }
       rr = grid_sum2(prr, slot0, P.bar);
@@ -601,6 +643,63 @@ __global__ void __launch_bounds__(kPcg2Threads, 1) k_pcg2(const Pcg2Plan *plan_g
     P.out[3] = bb;
     P.out[4] = e_tot;      // b.x = |x|_A^2 (energy of the computed direction)
     P.out[5] = e_last4;    // the part of it gained in the last four iterations
+  }
+}
+
+// ---- lambda_max(D^-1 A) by power iteration, all levels of a plan in ONE cooperative launch ---------------------------------
+// The levels are independent, so one phase serves them all: y = D^-1 A v (+ this CTA's share of |y|^2 per level), grid barrier,
+// every CTA adds the partials in the same order, v = y / |y|, grid barrier.  The vector v (Pcg2Level::pw) persists between
+// launches (warm start across Newton iterations).  lam <- min(lam, safety |D^-1 A v|): the Gershgorin bound k_l1diag left in
+// lam stays an upper clamp.
+__global__ void __launch_bounds__(kPcg2Threads, 1) k_lambda_power(const Pcg2Plan *plan_g, int iters, double safety) {
+  __shared__ Pcg2Plan P;
+  {
+    const uint64_t *src = reinterpret_cast<const uint64_t *>(plan_g);
+    uint64_t *dst = reinterpret_cast<uint64_t *>(&P);
+    for (int i = threadIdx.x; i < (int)(sizeof(Pcg2Plan) / sizeof(uint64_t)); i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const Scope<true> sc{(int)blockIdx.x, (int)gridDim.x, warp, nwarps, lane, P.bar};
+  const int nl = P.nlev - (P.bottom_dense ? 1 : 0);   // a dense bottom level has no smoother
+  for (int it = 0; it < iters; ++it) {
+    for (int q = 0; q < nl; ++q) {
+      const Pcg2Level &Lv = P.lev[q];
+      SellMat A = Lv.A;
+      A.valf = nullptr;
+      // every level is shared by the whole grid here, whatever the solve kernel does with it
+      const int spc = (A.nslices + (int)gridDim.x - 1) / (int)gridDim.x;
+      const int s0 = (int)blockIdx.x * spc, s1 = min(A.nslices, s0 + spc);
+      const GatherX<true> g{Lv.pw};
+      double part = 0.0;
+      for (int s = s0 + warp; s < s1; s += nwarps) {
+        bool lead;
+        const int row = sell_rowof(A, s, lane, lead);
+        const double acc = sell_row<true, false>(A, s, lane, g);
+        if (lead) {
+          const double y = acc * __ldg(Lv.idiag + row);
+          Lv.r[row] = y;
+          part += y * y;
+        }
+      }
+      const double bs = block_sum_bcast2(part);
+      if (threadIdx.x == 0) P.partials[(size_t)q * gridDim.x + blockIdx.x] = bs;
+    }
+    grid_barrier2(P.bar);
+    for (int q = 0; q < nl; ++q) {
+      const Pcg2Level &Lv = P.lev[q];
+      double v = 0.0;
+      for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) v += __ldcg(P.partials + (size_t)q * gridDim.x + b);
+      const double nrm = sqrt(block_sum_bcast2(v));
+      const double inv = nrm > 0.0 ? 1.0 / nrm : 0.0;
+      for (int i = (int)(blockIdx.x * blockDim.x + threadIdx.x); i < Lv.m; i += (int)(gridDim.x * blockDim.x)) Lv.pw[i] = __ldcg(Lv.r + i) * inv;
+      if (it == iters - 1 && blockIdx.x == 0 && threadIdx.x == 0 && nrm > 0.0 && isfinite(nrm)) {
+        double *lam = const_cast<double *>(Lv.lam);
+        const double est = safety * nrm;
+        if (est < *lam) *lam = est;
+      }
+    }
+    grid_barrier2(P.bar);
   }
 }
 
@@ -702,6 +801,11 @@ size_t pcg2_max_tail_bytes(int device) {
 cudaError_t pcg2_launch(const Pcg2Plan *dev_plan, int grid, size_t smem_bytes, double rtol2, int maxit, int stall_window, cudaStream_t s) {
   void *args[] = {(void *)&dev_plan, (void *)&rtol2, (void *)&maxit, (void *)&stall_window};
   return cudaLaunchCooperativeKernel((const void *)k_pcg2, dim3(grid), dim3(kPcg2Threads), args, smem_bytes, s);
+}
+
+cudaError_t pcg2_lambda_power(const Pcg2Plan *dev_plan, int grid, int iters, double safety, cudaStream_t s) {
+  void *args[] = {(void *)&dev_plan, (void *)&iters, (void *)&safety};
+  return cudaLaunchCooperativeKernel((const void *)k_lambda_power, dim3(grid), dim3(kPcg2Threads), args, 0, s);
 }
 
 cudaError_t sell_slice_widths(int64_t rows, int lpr, const int64_t *ptr, int *width, cudaStream_t s) {

@@ -45,6 +45,7 @@ struct Pcg2Level {
   const double *dinv = nullptr;    // l1-Jacobi 1 / sum_j |a_ij|
   const double *lam = nullptr;     // bound of lambda_max(D^-1 A) (device scalar, refreshed with the values)
   double *b = nullptr, *x = nullptr, *x2 = nullptr, *r = nullptr;
+  double *pw = nullptr;            // power-iteration vector for lambda_max(D^-1 A) (pcg2_lambda_power), kept between launches
 };
 
 struct Pcg2Plan {
@@ -70,6 +71,9 @@ size_t pcg2_tail_bytes(const Pcg2Plan &P);
 // one-time attribute setup + occupancy check; returns the number of CTAs to launch (<= SM count), 0 if the device cannot run it
 int pcg2_grid(int device);
 size_t pcg2_max_tail_bytes(int device);   // dynamic shared memory available to the tail
+// `iters` power iterations on D^-1 A for every level of the plan in one cooperative launch; lam <- min(lam, safety |D^-1 A v|)
+// (needs nlev * grid <= 3 * kPcg2MaxGrid partial slots and Pcg2Level::pw initialised to a non-zero vector)
+cudaError_t pcg2_lambda_power(const Pcg2Plan *dev_plan, int grid, int iters, double safety, cudaStream_t s);
 cudaError_t pcg2_launch(const Pcg2Plan *dev_plan, int grid, size_t smem_bytes, double rtol2, int maxit, int stall_window, cudaStream_t s);
 
 // ---- sliced-ELL construction from a device CSR (int64 row pointers, int32 columns), once per pattern

@@ -60,7 +60,7 @@ class Config(C.Structure):
                 ("persistent", C.c_int32), ("tail_max", C.c_int32), ("pcg_rtol_final", C.c_double),
                 ("fused", C.c_int32), ("smoother", C.c_int32), ("cheb_ratio", C.c_double),
                 ("precond_fp32", C.c_int32), ("pcg_lanes", C.c_int32), ("lambda_power", C.c_int32),
-                ("pcg_fail_rtol", C.c_double), ("pcg_fail_etol", C.c_double), ("pcg_stall_window", C.c_int32), ("direct_fallback", C.c_int32)]
+                ("pcg_fail_rtol", C.c_double), ("pcg_fail_etol", C.c_double), ("pcg_stall_window", C.c_int32), ("direct_fallback", C.c_int32), ("elem_bulk", C.c_int32)]
 
 
 class StepOpts(C.Structure):
@@ -97,7 +97,7 @@ EXPORTS = [
     "mgbx_phase1_init", "mgbx_attach_feasibility", "mgbx_set_feasibility_box", "mgbx_reset_feasibility_state", "mgbx_handoff",
     "mgbx_matched_t", "mgbx_get_z", "mgbx_get_z_unfinalized", "mgbx_set_z", "mgbx_set_grids", "mgbx_level_size",
     "mgbx_barrier_eval", "mgbx_hessian_pattern", "mgbx_hessian_values", "mgbx_solve_newton_system",
-    "mgbx_plan_pattern", "mgbx_recover_transfer", "mgbx_launch_count", "mgbx_kernel_stats", "mgbx_set_profile", "mgbx_solver_info",
+    "mgbx_plan_pattern", "mgbx_recover_transfer", "mgbx_launch_count", "mgbx_memory_report", "mgbx_kernel_stats", "mgbx_set_profile", "mgbx_solver_info",
 ]
 
 _lib = None
@@ -153,6 +153,7 @@ def lib():
     L.mgbx_plan_pattern.argtypes = [C.POINTER(Csr), C.c_int64, C.c_int32, C.c_int32, C.c_int32, c_i32p,
                                     c_i64p, c_i64p, c_i64p]
     L.mgbx_recover_transfer.argtypes = [C.POINTER(Csr), C.POINTER(Csr), c_i64p, c_i64p, c_i64p, c_f64p]
+    L.mgbx_memory_report.argtypes = [H, C.c_char_p, C.c_int64, c_i64p]
     L.mgbx_launch_count.argtypes = [H]
     L.mgbx_launch_count.restype = C.c_int64
     L.mgbx_kernel_stats.argtypes = [H, C.c_int, c_i32p, C.POINTER(C.c_char_p), c_i64p, c_f64p]
@@ -402,6 +403,13 @@ class Handle:
         keep = _Keep()
         self._check(lib().mgbx_set_grids(self._h, keep.colmajor(f_grid) if f_grid is not None else None,
                                          keep.colmajor(g_grid) if g_grid is not None else None))
+
+    def memory_report(self):
+        """(text, total bytes): device memory held by the handle, by category."""
+        buf = C.create_string_buffer(8192)
+        tot = C.c_int64()
+        self._check(lib().mgbx_memory_report(self._h, buf, 8192, C.byref(tot)))
+        return buf.value.decode(), tot.value
 
     def launch_count(self):
         return int(lib().mgbx_launch_count(self._h))

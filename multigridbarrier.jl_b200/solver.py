@@ -258,6 +258,7 @@ def mgb_solve(prob, barrier_nodes=None, config=None, log=None, handle=None, comm
         l0 = h.launch_count()
         sol = mgb_driver(h, prob.M, log=_log, stats=stats, **kw)
         stats["gpu_launches"] = h.launch_count() - l0
+        stats["device_memory_report"], stats["device_bytes"] = h.memory_report()
     finally:
         if own:
             h.close()

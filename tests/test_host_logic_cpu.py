@@ -109,6 +109,9 @@ class OracleHandle:
     def get_z(self, which=native.MAIN):
         return self.z[which].copy()
 
+    def memory_report(self):
+        return "", 0
+
     def get_z_unfinalized(self, which=native.MAIN):
         return self.zunfin[which].copy()
 
