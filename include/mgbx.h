@@ -181,6 +181,10 @@ typedef struct {
   int32_t elem_bulk;         /* 1 (default): the fused element kernel stages each tile's operator slabs and node columns with
                                 cp.async.bulk (one instruction per slab / block column, completion on an mbarrier) instead of one
                                 8-byte cp.async per double; 0: the per-double path */
+  int32_t shard_solve;       /* multi-GPU: 1 (default) the leading V-cycle levels with >= shard_min_rows unknowns are ROW-SHARDED over the
+                                ranks inside the persistent solve kernel (peer stores over NVLink into CUDA-IPC-mapped exchange arenas,
+                                cross-GPU flag barrier, csrc/pcg2.hpp); 0: every rank runs the whole solve (replicated) */
+  int32_t shard_min_rows;    /* default 100000 */
 } mgbx_config;
 
 /* options of one mgb_step (src/mgb.jl:16-30; defaults src/mgb.jl:360-363) */

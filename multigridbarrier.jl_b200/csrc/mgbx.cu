@@ -422,6 +422,10 @@ struct System {
     Pcg2Plan host;
     Pcg2Plan *dev = nullptr;
     size_t smem = 0;
+    // multi-GPU row-sharded solve: this rank's exchange arena (cudaMalloc, exported by CUDA IPC) and the peers' mappings
+    char *arena = nullptr;
+    size_t arena_bytes = 0;
+    void *peer[kPcg2MaxRanks] = {nullptr};
   };
   std::map<int, Pcg2Dev> pplans2;
   double *pc_p2 = nullptr, *pcg_partials = nullptr, *pcg_out = nullptr;
@@ -1072,6 +1076,7 @@ struct Engine {
   SellBuild make_sell(const DevCsr &A, int64_t nthreads);
   void sell_prepare(System &S, int ktop);
   System::Pcg2Dev &pcg2_plan(System &S, int ktop);
+  void pcg2_setup_dist(System::Pcg2Dev &D, int nshard);
   int pcg_persistent2(System &S, int ktop, const double *b, double *x);
   int pcg(System &S, int ktop, const double *b, double *x);
   int solve_compact(System &S, int ktop, const double *b, double *x);
@@ -1866,6 +1871,15 @@ System::Pcg2Dev &Engine::pcg2_plan(System &S, int ktop) {
   P.bar = S.pcg_bar;
   P.out = S.pcg_out;
   if (getenv("MGBX_PCG_PROF")) P.prof = h->pool.zeros<unsigned long long>(1 + 2 * (size_t)kPcg2ProfCap, s);
+  if (dist() && h->cfg.shard_solve && P.nlev >= 2) {
+    // multi-GPU: the leading levels with at least shard_min_rows unknowns are row-sharded over the ranks (pcg2.hpp)
+    int nshard = 0;
+    for (int q = 0; q < P.nbig && q < P.nlev - 1; ++q) {
+      if (P.lev[q].m < h->cfg.shard_min_rows) break;
+      nshard = q + 1;
+    }
+    if (nshard > 0) pcg2_setup_dist(D, nshard);
+  }
   D.dev = h->pool.upload<Pcg2Plan>(&P, 1, s);
   CK(cudaStreamSynchronize(s));
   if (h->cfg.verbose > 0)
@@ -1874,13 +1888,84 @@ System::Pcg2Dev &Engine::pcg2_plan(System &S, int ktop) {
   return D;
 }
 
+// Exchange arena of one sharded solve plan: every vector a peer writes into (the work vectors of the sharded levels, p, x, the
+// partial-sum slots, the barrier flags) is carved out of ONE cudaMalloc block with the same layout on every rank; the blocks
+// are exported with CUDA IPC, the handles all-gathered with NCCL, and each rank maps its peers' blocks.
+void Engine::pcg2_setup_dist(System::Pcg2Dev &D, int nshard) {
+  Pcg2Plan &P = D.host;
+  const int nr = h->nranks;
+  if (nr > kPcg2MaxRanks) throw std::runtime_error("row-sharded solve: more than 8 ranks");
+  if ((int64_t)nr * h->pcg2_grid > kPcg2MaxGrid) throw std::runtime_error("row-sharded solve: too many CTAs for the partial-sum slots");
+  size_t bytes = 0;
+  auto take = [&](size_t n) {
+    const size_t off = bytes;
+    bytes += (n + 255) & ~(size_t)255;
+    return off;
+  };
+  const size_t o_flags = take(sizeof(unsigned long long) * kPcg2MaxRanks), o_arr = take(sizeof(unsigned int)), o_rel = take(sizeof(unsigned long long));
+  const size_t o_part = take(sizeof(double) * 3 * (size_t)kPcg2MaxGrid);
+  const size_t m0 = (size_t)P.lev[0].m;
+  const size_t o_p = take(8 * m0), o_p2 = take(8 * m0), o_x = take(8 * m0);
+  std::vector<size_t> o_lev(4 * (size_t)nshard);
+  for (int q = 0; q < nshard; ++q)
+    for (int v = 0; v < 4; ++v) o_lev[4 * q + v] = take(8 * (size_t)P.lev[q].m);
+  CK(cudaMalloc((void **)&D.arena, bytes));
+  D.arena_bytes = bytes;
+  CK(cudaMemsetAsync(D.arena, 0, bytes, s));
+  // export / all-gather / import
+  cudaIpcMemHandle_t mine;
+  CK(cudaIpcGetMemHandle(&mine, D.arena));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  char *dsend = tmp_alloc<char>(64, s), *dall = tmp_alloc<char>(64 * (size_t)nr, s);
+  CK(cudaMemcpyAsync(dsend, &mine, 64, cudaMemcpyHostToDevice, s));
+  NCK(nccl_api().AllGather(dsend, dall, 8, kNcclInt64, h->comm, s));
+  std::vector<cudaIpcMemHandle_t> all(nr);
+  CK(cudaMemcpyAsync(all.data(), dall, 64 * (size_t)nr, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  tmp_free(dsend, s);
+  tmp_free(dall, s);
+  P.dist = Pcg2Dist();
+  P.dist.nranks = nr;
+  P.dist.rank = h->rank;
+  P.dist.nshard = nshard;
+  for (int q = 0; q < nr; ++q) {
+    if (q == h->rank) {
+      P.dist.peer_off[q] = 0;
+      continue;
+    }
+    CK(cudaIpcOpenMemHandle(&D.peer[q], all[q], cudaIpcMemLazyEnablePeerAccess));
+    P.dist.peer_off[q] = (long long)((char *)D.peer[q] - D.arena);
+  }
+  P.dist.flags = (unsigned long long *)(D.arena + o_flags);
+  P.dist.xarrive = (unsigned int *)(D.arena + o_arr);
+  P.dist.xrelease = (unsigned long long *)(D.arena + o_rel);
+  P.partials = (double *)(D.arena + o_part);
+  P.p = (double *)(D.arena + o_p);
+  P.p2 = (double *)(D.arena + o_p2);
+  P.x = (double *)(D.arena + o_x);
+  const int64_t gcta = (int64_t)nr * h->pcg2_grid;
+  auto respc = [&](SellMat &M) { M.spc = (int)((M.nslices + gcta - 1) / gcta); };
+  for (int q = 0; q < nshard; ++q) {
+    Pcg2Level &pl = P.lev[q];
+    pl.x = (double *)(D.arena + o_lev[4 * q + 0]);
+    pl.x2 = (double *)(D.arena + o_lev[4 * q + 1]);
+    pl.r = (double *)(D.arena + o_lev[4 * q + 2]);
+    pl.b = (double *)(D.arena + o_lev[4 * q + 3]);
+    respc(pl.A);              // rows of level q: owned by the CTAs of all ranks together
+    respc(pl.T);
+    if (q > 0) respc(P.lev[q - 1].Tt);
+  }
+  if (h->cfg.verbose > 0)
+    fprintf(stderr, "[mgbx] rank %d: row-sharded solve over %d ranks, %d of %d levels sharded, exchange arena %.1f MB\n", h->rank, nr, nshard, P.nlev, bytes / 1e6);
+}
+
 int Engine::pcg_persistent2(System &S, int ktop, const double *b, double *x) {
   SysLevel &Lv = S.lev[ktop];
   const int64_t m = Lv.m;
   System::Pcg2Dev &D = pcg2_plan(S, ktop);
   if (b != S.pc_b) copy(S.pc_b, b, m);
   pre_launch(KC_PCG);
-  CK(pcg2_launch(D.dev, h->pcg2_grid, D.smem, h->cur_rtol2, h->cfg.pcg_maxit, h->cur_window, s));
+  CK(pcg2_launch(D.dev, h->pcg2_grid, D.smem, h->cur_rtol2, h->cfg.pcg_maxit, h->cur_window, D.host.dist.nshard > 0, s));
   post_launch(KC_PCG);
   if (D.host.prof) {   // debugging aid: accumulate the per-phase durations of this launch
     h->prof_host.resize(1 + 2 * (size_t)kPcg2ProfCap);
@@ -1905,7 +1990,8 @@ int Engine::pcg_persistent2(System &S, int ktop, const double *b, double *x) {
   h->last_solve_status = (int)status;
   h->last_solve_rel = (h->hscal[11] > 0.0) ? std::sqrt(h->hscal[9] / h->hscal[11]) : 0.0;
   h->last_solve_erel = (h->hscal[12] > 0.0) ? h->hscal[13] / h->hscal[12] : 0.0;
-  if (x != S.pc_x) copy(x, S.pc_x, m);
+  if (status == -3.0) throw std::runtime_error("row-sharded solve: a peer rank never arrived at a cross-GPU barrier (ranks out of step?)");
+  if (x != D.host.x) copy(x, D.host.x, m);
   return status < 0 ? -std::max(it, 1) : it;
 }
 
@@ -2607,6 +2693,8 @@ void mgbx_default_config(mgbx_config *c) {
   c->pcg_stall_window = 100;
   c->direct_fallback = 1;
   c->elem_bulk = 1;
+  c->shard_solve = 1;
+  c->shard_min_rows = 100000;
 }
 
 void mgbx_default_step_opts(mgbx_step_opts *o, int64_t n) {
@@ -2729,6 +2817,14 @@ void mgbx_destroy(mgbx_handle *h) {
     for (System *S : {h->amg[w].sys_cond.get(), h->amg[w].sys_coarse.get(), h->amg[w].sys_hook.get()})
       if (S)
         for (auto &kv : S->graphs) cudaGraphExecDestroy(kv.second);
+  for (int w = 0; w < 2; ++w)
+    for (System *S : {h->amg[w].sys_cond.get(), h->amg[w].sys_coarse.get(), h->amg[w].sys_hook.get()})
+      if (S)
+        for (auto &kv : S->pplans2) {
+          for (void *q : kv.second.peer)
+            if (q) cudaIpcCloseMemHandle(q);
+          if (kv.second.arena) cudaFree(kv.second.arena);
+        }
   h->pool.release();
   if (h->hscal) cudaFreeHost(h->hscal);
   if (h->ev0) cudaEventDestroy(h->ev0);

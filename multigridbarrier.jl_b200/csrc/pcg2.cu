@@ -61,13 +61,93 @@ struct Ld {
   static __device__ __forceinline__ double v(const double *p) { return GRID ? __ldcg(p) : *p; }
 };
 
+// ---- multi-GPU (row-sharded levels): peer stores and the cross-GPU barrier ------------------------------------------------
+// Every rank runs the same kernel on the same (replicated) matrices.  The rows of a sharded level are owned by the CTAs of all
+// ranks together; what a CTA computes for its rows is stored locally AND into every peer's copy of the vector (NVLink stores
+// into the peers' exchange arenas, mapped by CUDA IPC; the arenas have identical layouts, so a peer address is the local one
+// plus a per-rank byte offset).  A cross-GPU barrier ends such a phase: every thread fences its stores system-wide, the CTAs
+// arrive on a local counter, CTA 0 publishes the epoch to every peer's flag word and waits for theirs, then releases its grid.
+struct XRt {                          // per-launch runtime state of the cross barrier, in shared memory (thread 0 only)
+  unsigned long long epoch;           // barriers passed so far (continues across launches: the counters are monotonic)
+  int aborted;
+};
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ void xbarrier(const Pcg2Dist &D, XRt *rt) {
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0 && !rt->aborted) {
+    const unsigned long long e = ++rt->epoch;
+    const unsigned long long t0 = gtime();
+    const unsigned long long limit = 4000000000ull;   // 4 s: a peer that never arrives must not hang the GPU
+    if (blockIdx.x != 0) {
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(D.xarrive) : "memory");
+      unsigned long long cur;
+      do {
+        asm volatile("ld.acquire.gpu.u64 %0, [%1];" : "=l"(cur) : "l"(D.xrelease) : "memory");
+        if (cur == ~0ull || gtime() - t0 > limit) {
+          rt->aborted = 1;
+          break;
+        }
+      } while (cur < e);
+    } else {
+      const unsigned int want = (unsigned int)((gridDim.x - 1) * e);   // monotonic arrival counter (wraps with the epoch)
+      unsigned int got;
+      bool ok = true;
+      do {
+        asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(got) : "l"(D.xarrive) : "memory");
+        if (gtime() - t0 > limit) ok = false;
+      } while (ok && (int)(got - want) < 0);
+      for (int q = 0; ok && q < D.nranks; ++q) {
+        if (q == D.rank) continue;
+        unsigned long long *pf = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(D.flags + D.rank) + D.peer_off[q]);
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(pf), "l"(e) : "memory");
+      }
+      for (int q = 0; ok && q < D.nranks; ++q) {
+        if (q == D.rank) continue;
+        unsigned long long cur;
+        do {
+          asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(cur) : "l"(D.flags + q) : "memory");
+          if (gtime() - t0 > limit) ok = false;
+        } while (ok && cur < e);
+      }
+      if (!ok) rt->aborted = 1;
+      const unsigned long long rel = ok ? e : ~0ull;   // ~0: tells the other CTAs to give up
+      asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(D.xrelease), "l"(rel) : "memory");
+    }
+  }
+  __syncthreads();
+}
+
+// where a phase stores a vector entry: locally, or locally and into every peer's copy
+template <bool DIST>
+struct Out {
+  int npeer;
+  long long off[kPcg2MaxRanks - 1];
+  __device__ __forceinline__ void st(double *p, int i, double v) const {
+    p[i] = v;
+    if (DIST) {
+      for (int q = 0; q < npeer; ++q) *reinterpret_cast<double *>(reinterpret_cast<char *>(p + i) + off[q]) = v;
+    }
+  }
+};
+
 template <bool GRID>
 struct Scope {
   int cta, ncta, warp, nwarps, lane;
   unsigned int *bar;
+  const Pcg2Dist *dist;   // != nullptr: this scope spans the CTAs of all ranks (cta = rank * CTAs per rank + local CTA) and
+  XRt *xrt;               // its phases end with the cross-GPU barrier
   __device__ __forceinline__ void sync() const {
-    if (GRID) grid_barrier2(bar);
-    else __syncthreads();
+    if (GRID) {
+      if (dist) xbarrier(*dist, xrt);
+      else grid_barrier2(bar);
+    } else {
+      __syncthreads();
+    }
   }
   // slices of M this CTA owns
   __device__ __forceinline__ void range(const SellMat &M, int &s0, int &s1) const {
@@ -162,9 +242,9 @@ __device__ __forceinline__ double sell_row_any(const SellMat &A, int s, int lane
 
 // y = alpha * M x + (y0 ? y0 : 0)      (y may alias y0; y must not alias x)
 // ys != nullptr: also ys = y .* yscale (the pre-scaled right-hand side the next level's first smoothing pass gathers)
-template <bool GRID>
-__device__ void ph_spmv(const Scope<GRID> &sc, const SellMat &M, const double *x, const double *y0, double alpha, double *y, double *ys = nullptr,
-                        const double *yscale = nullptr) {
+template <bool GRID, bool DIST>
+__device__ void ph_spmv(const Scope<GRID> &sc, const Out<DIST> &o, const SellMat &M, const double *x, const double *y0, double alpha, double *y,
+                        double *ys = nullptr, const double *yscale = nullptr) {
   int s0, s1;
   sc.range(M, s0, s1);
   const GatherX<GRID> g{x};
@@ -174,8 +254,8 @@ __device__ void ph_spmv(const Scope<GRID> &sc, const SellMat &M, const double *x
     const double acc = sell_row_any<GRID>(M, s, sc.lane, g);
     if (lead) {
       const double v = alpha * acc + (y0 ? Ld<GRID>::v(y0 + row) : 0.0);
-      y[row] = v;
-      if (ys) ys[row] = v * Ld<GRID>::m(yscale + row);
+      o.st(y, row, v);
+      if (ys) o.st(ys, row, v * Ld<GRID>::m(yscale + row));
     }
   }
 }
@@ -203,8 +283,8 @@ struct Cheb {
 
 // steps 0 and 1 from x = 0 in one pass: d0 = th_inv D^-1 b; r1 = b - A d0; d1 = c_dd d0 + c_dr D^-1 r1; x = d0 + d1
 // bs = b .* idiag is written by whoever produced b (restriction, PCG update), so that the row sums gather ONE vector
-template <bool GRID>
-__device__ void ph_first2(const Scope<GRID> &sc, const SellMat &A, const double *idiag, const double *b, const double *bs, double *xnew, double *d,
+template <bool GRID, bool DIST>
+__device__ void ph_first2(const Scope<GRID> &sc, const Out<DIST> &o, const SellMat &A, const double *idiag, const double *b, const double *bs, double *xnew, double *d,
                           double th_inv, double c_dd, double c_dr) {
   int s0, s1;
   sc.range(A, s0, s1);
@@ -217,16 +297,16 @@ __device__ void ph_first2(const Scope<GRID> &sc, const SellMat &A, const double 
       const double di = Ld<GRID>::m(idiag + row), bi = Ld<GRID>::v(b + row);
       const double d0 = th_inv * bi * di;
       const double d1 = c_dd * d0 + c_dr * (bi - th_inv * acc) * di;
-      xnew[row] = d0 + d1;
-      d[row] = d1;
+      o.st(xnew, row, d0 + d1);
+      d[row] = d1;   // the recurrence vector is only ever read by its owner
     }
   }
 }
 
 // one step on an existing iterate: r = b - A x; d = (first ? th_inv D^-1 r : c_dd d + c_dr D^-1 r); xnew = x + d;
 // returns this thread's share of sum_i dotw[i] xnew[i] (0 if dotw == nullptr)
-template <bool GRID>
-__device__ double ph_step(const Scope<GRID> &sc, const SellMat &A, const double *idiag, const double *b, const double *x, double *xnew, double *d,
+template <bool GRID, bool DIST>
+__device__ double ph_step(const Scope<GRID> &sc, const Out<DIST> &o, const SellMat &A, const double *idiag, const double *b, const double *x, double *xnew, double *d,
                           bool first, double th_inv, double c_dd, double c_dr, const double *dotw) {
   int s0, s1;
   sc.range(A, s0, s1);
@@ -241,7 +321,7 @@ __device__ double ph_step(const Scope<GRID> &sc, const SellMat &A, const double 
       const double dn = first ? th_inv * rr : c_dd * d[row] + c_dr * rr;
       const double v = Ld<GRID>::v(x + row) + dn;
       d[row] = dn;
-      xnew[row] = v;
+      o.st(xnew, row, v);
       if (dotw) part += Ld<GRID>::v(dotw + row) * v;
     }
   }
@@ -325,13 +405,19 @@ __device__ __forceinline__ SmoothBufs smooth_bufs(const VcArgs &P, const Pcg2Lev
   return B;
 }
 
-template <bool GRID, class Tail>
-__device__ double vcycle(const VcArgs &P, const Pcg2Level *lev, const Scope<GRID> &sc, int k0, int k1, const double *btop, const double *dot_top,
-                         const Tail &tail) {
+// DIST: levels [0, nshard) are row-sharded over the ranks: their phases run in scope `scx` (all ranks' CTAs), store through
+// `ox` (local + peers) and end with the cross-GPU barrier; the other levels are replicated (scope `sc`, local stores `ol`).
+// A phase is classified by the level whose rows it WRITES.
+template <bool GRID, bool DIST, class Tail>
+__device__ double vcycle(const VcArgs &P, const Pcg2Level *lev, const Scope<GRID> &sc, const Scope<GRID> &scx, const Out<DIST> &ol, const Out<DIST> &ox,
+                         int nshard, int k0, int k1, const double *btop, const double *dot_top, const Tail &tail) {
   double part = 0.0;
   // ---- down
   for (int k = k0; k < k1; ++k) {
     const Pcg2Level &Lv = lev[k];
+    const bool sh = DIST && k < nshard, shc = DIST && (k + 1) < nshard;   // this level / the next coarser one sharded
+    const Scope<GRID> &S = sh ? scx : sc;
+    const Out<DIST> &O = sh ? ox : ol;
     const double *bk = (k == k0) ? btop : Lv.b;
     const bool last = (k == P.nlev - 1);
     if (last && P.bottom_dense) {
@@ -351,35 +437,36 @@ __device__ double vcycle(const VcArgs &P, const Pcg2Level *lev, const Scope<GRID
     const double th_inv = cheb ? C.th_inv : 1.0;
     if (done == 2) {
       if (cheb) rho = C.step(rho, c_dd, c_dr);
-      ph_first2<GRID>(sc, Lv.A, idg, bk, oth, cur, Lv.r, th_inv, c_dd, c_dr);   // oth holds b .* idg (smooth_bufs)
+      ph_first2<GRID, DIST>(S, O, Lv.A, idg, bk, oth, cur, Lv.r, th_inv, c_dd, c_dr);   // oth holds b .* idg (smooth_bufs)
     } else {
-      for (int i = sc.tid(); i < Lv.m; i += sc.nthr()) {
+      for (int i = S.tid(); i < Lv.m; i += S.nthr()) {
         const double d0 = th_inv * Ld<GRID>::v(bk + i) * Ld<GRID>::m(idg + i);
-        cur[i] = d0;
-        Lv.r[i] = d0;
+        O.st(cur, i, d0);
+        O.st(Lv.r, i, d0);
       }
     }
-    sc.sync();
+    S.sync();
     if (GRID) prof_mark(P.prof, k * 16 + PK_FIRST2);
     for (int it = 0; it < npre; ++it) {
       if (cheb) rho = C.step(rho, c_dd, c_dr);
       // l1-Jacobi: every sweep is a "first" step (x += dinv (b - A x))
-      ph_step<GRID>(sc, Lv.A, idg, bk, cur, oth, Lv.r, !cheb, th_inv, c_dd, c_dr, nullptr);
-      sc.sync();
+      ph_step<GRID, DIST>(S, O, Lv.A, idg, bk, cur, oth, Lv.r, !cheb, th_inv, c_dd, c_dr, nullptr);
+      S.sync();
       if (GRID) prof_mark(P.prof, k * 16 + PK_PRE);
       double *t = cur;
       cur = oth;
       oth = t;
     }
     if (!last) {
-      ph_spmv<GRID>(sc, Lv.A, cur, bk, -1.0, Lv.r);
-      sc.sync();
+      ph_spmv<GRID, DIST>(S, O, Lv.A, cur, bk, -1.0, Lv.r);
+      S.sync();
       if (GRID) prof_mark(P.prof, k * 16 + PK_RESID);
       {
         const SmoothBufs nb = smooth_bufs(P, lev[k + 1], k + 1);
-        ph_spmv<GRID>(sc, Lv.Tt, Lv.r, nullptr, 1.0, lev[k + 1].b, nb.two ? nb.oth : nullptr, nb.idg);
+        const Scope<GRID> &Sc = shc ? scx : sc;   // the restriction writes rows of level k + 1
+        ph_spmv<GRID, DIST>(Sc, shc ? ox : ol, Lv.Tt, Lv.r, nullptr, 1.0, lev[k + 1].b, nb.two ? nb.oth : nullptr, nb.idg);
+        Sc.sync();
       }
-      sc.sync();
       if (GRID) prof_mark(P.prof, k * 16 + PK_RESTRICT);
     }
   }
@@ -393,6 +480,9 @@ __device__ double vcycle(const VcArgs &P, const Pcg2Level *lev, const Scope<GRID
   for (int k = k1 - 1; k >= k0; --k) {
     if (k == P.nlev - 1) continue;   // bottom level: nothing coarser
     const Pcg2Level &Lv = lev[k];
+    const bool sh = DIST && k < nshard;
+    const Scope<GRID> &S = sh ? scx : sc;
+    const Out<DIST> &O = sh ? ox : ol;
     const double *bk = (k == k0) ? btop : Lv.b;
     const int want = P.nu;
     const int done = (want >= 2) ? 2 : 1;
@@ -400,8 +490,8 @@ __device__ double vcycle(const VcArgs &P, const Pcg2Level *lev, const Scope<GRID
     const bool start_x2 = ((npre + npost) & 1) != 0;
     const bool cur_x2 = start_x2 != ((npre & 1) != 0);
     double *cur = cur_x2 ? Lv.x2 : Lv.x, *oth = cur_x2 ? Lv.x : Lv.x2;
-    ph_spmv<GRID>(sc, Lv.T, lev[k + 1].x, cur, 1.0, cur);   // x += T xc (row-local)
-    sc.sync();
+    ph_spmv<GRID, DIST>(S, O, Lv.T, lev[k + 1].x, cur, 1.0, cur);   // x += T xc (row-local)
+    S.sync();
     if (GRID) prof_mark(P.prof, k * 16 + PK_PROLONG);
     const bool cheb = (P.smoother == 1);
     const double *idg = cheb ? Lv.idiag : Lv.dinv;
@@ -411,9 +501,9 @@ __device__ double vcycle(const VcArgs &P, const Pcg2Level *lev, const Scope<GRID
     for (int it = 0; it < npost; ++it) {
       const bool fin = (it == npost - 1) && (k == k0) && (dot_top != nullptr);
       if (cheb && it > 0) rho = C.step(rho, c_dd, c_dr);
-      part += ph_step<GRID>(sc, Lv.A, idg, bk, cur, oth, Lv.r, !cheb || it == 0, th_inv, c_dd, c_dr, fin ? dot_top : nullptr);
+      part += ph_step<GRID, DIST>(S, O, Lv.A, idg, bk, cur, oth, Lv.r, !cheb || it == 0, th_inv, c_dd, c_dr, fin ? dot_top : nullptr);
       if (!fin) {
-        sc.sync();
+        S.sync();
         if (GRID) prof_mark(P.prof, k * 16 + PK_POST);
       }
       double *t = cur;
@@ -452,10 +542,12 @@ __device__ __forceinline__ void sell_to_smem(unsigned char *&cur, SellMat &M) {
   M.val = nullptr;
 }
 
+template <bool DIST>
 __global__ void __launch_bounds__(kPcg2Threads, 1) k_pcg2(const Pcg2Plan *plan_g, double rtol2, int maxit, int stall_window) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ Pcg2Plan P;
   __shared__ double s_e[5];
+  __shared__ XRt s_xrt;
   __shared__ Pcg2Level TL[kTailMaxLevels];   // CTA 0: tail levels with shared-memory matrices and vectors, index k - nbig
   {
     const uint64_t *src = reinterpret_cast<const uint64_t *>(plan_g);
@@ -498,11 +590,50 @@ __global__ void __launch_bounds__(kPcg2Threads, 1) k_pcg2(const Pcg2Plan *plan_g
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const Scope<true> sc{(int)blockIdx.x, (int)gridDim.x, warp, nwarps, lane, P.bar};
+  const Scope<true> sc{(int)blockIdx.x, (int)gridDim.x, warp, nwarps, lane, P.bar, nullptr, nullptr};
+  // multi-GPU: the scope of the sharded levels spans the CTAs of all ranks
+  const int nshard = DIST ? P.dist.nshard : 0;
+  const Scope<true> scx{DIST ? P.dist.rank * (int)gridDim.x + (int)blockIdx.x : (int)blockIdx.x, DIST ? P.dist.nranks * (int)gridDim.x : (int)gridDim.x,
+                        warp, nwarps, lane, P.bar, DIST ? &P.dist : nullptr, DIST ? &s_xrt : nullptr};
+  Out<DIST> ol, ox;
+  ol.npeer = 0;
+  ox.npeer = 0;
+  if (DIST) {
+    for (int q = 0; q < P.dist.nranks; ++q)
+      if (q != P.dist.rank) ox.off[ox.npeer++] = P.dist.peer_off[q];
+    if (threadIdx.x == 0) {
+      unsigned long long e0;
+      asm volatile("ld.acquire.gpu.u64 %0, [%1];" : "=l"(e0) : "l"(P.dist.xrelease) : "memory");
+      s_xrt.epoch = e0;   // stable: the previous launch has completed on every CTA
+      s_xrt.aborted = 0;
+    }
+    __syncthreads();
+  }
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
   const int m = P.lev[0].m;
   double *slot0 = P.partials, *slot1 = P.partials + kPcg2MaxGrid, *slot2 = P.partials + 2 * kPcg2MaxGrid;
+  // rows of the top level this CTA owns (DIST: the update of x and r is row-owned, like every phase of a sharded level)
+  const bool top_sh = DIST && nshard > 0;
+  int own0 = 0, own1 = 0;
+  if (top_sh) {
+    int s0, s1;
+    scx.range(P.lev[0].A, s0, s1);
+    const int rps = 32 / P.lev[0].A.lpr;
+    own0 = min(m, s0 * rps);
+    own1 = min(m, max(s0, s1) * rps);
+  }
+  // sum over the whole (multi-GPU) grid: every CTA deposits its partial in every rank's slot array, one cross barrier, then
+  // every CTA of every rank adds all partials in the same order
+  auto xsum = [&](double part, double *slot) -> double {
+    if (!top_sh) return grid_sum2(part, slot, P.bar);
+    const double bs = block_sum_bcast2(part);
+    if (threadIdx.x == 0) ox.st(slot, scx.cta, bs);
+    scx.sync();
+    double v = 0.0;
+    for (int b = threadIdx.x; b < scx.ncta; b += blockDim.x) v += __ldcg(slot + b);
+    return block_sum_bcast2(v);
+  };
   const VcArgs VA{P.nlev, P.nbig, P.bottom_dense, P.nu, P.nu_bottom, P.smoother, P.cheb_ratio, P.dense_inv, P.prof};
   if (P.prof && tid == 0) P.prof[0] = 0;
 
@@ -510,7 +641,7 @@ __global__ void __launch_bounds__(kPcg2Threads, 1) k_pcg2(const Pcg2Plan *plan_g
   // grid) and the result copied out to the global vector the grid prolongates from.
   auto tail = [&]() {
     if (blockIdx.x != 0) return;
-    const Scope<false> cta{0, 1, warp, nwarps, lane, nullptr};
+    const Scope<false> cta{0, 1, warp, nwarps, lane, nullptr, nullptr, nullptr};
     const int nb = P.nbig;
     const Pcg2Level *tl = TL - nb;   // indexed by level
     {
@@ -525,7 +656,8 @@ __global__ void __launch_bounds__(kPcg2Threads, 1) k_pcg2(const Pcg2Plan *plan_g
       }
       __syncthreads();
     }
-    vcycle<false>(VA, tl, cta, nb, P.nlev, TL[0].b, nullptr, NoTail());
+    const Out<false> lo{0, {}};
+    vcycle<false, false>(VA, tl, cta, cta, lo, lo, 0, nb, P.nlev, TL[0].b, nullptr, NoTail());
     if (tail_smem) {
       double *gx = P.lev[nb].x;
       for (int i = threadIdx.x; i < TL[0].m; i += blockDim.x) gx[i] = TL[0].x[i];
@@ -562,13 +694,13 @@ __global__ void __launch_bounds__(kPcg2Threads, 1) k_pcg2(const Pcg2Plan *plan_g
     while (it < maxit) {
       // z = M^{-1} r, with r.z accumulated in the last smoothing sweep of the top level
       const bool single = (P.nlev == 1);
-      double prz = vcycle<true>(VA, P.lev, sc, 0, P.nbig, P.r, single ? nullptr : P.r, tail);
+      double prz = vcycle<true, DIST>(VA, P.lev, sc, scx, ol, ox, nshard, 0, P.nbig, P.r, single ? nullptr : P.r, tail);
       const double *z = top.x;
       if (single) {   // one-level "hierarchy": no up-sweep ran, take the dot here
         prz = 0.0;
         for (int64_t i = tid; i < m; i += nthr) prz += P.r[i] * __ldcg(z + i);
       }
-      const double rz = grid_sum2(prz, slot1, P.bar);
+      const double rz = xsum(prz, slot1);
       prof_mark(P.prof, PK_RZSUM);
       const double beta = rz / rz_old;
       rz_old = rz;
@@ -576,7 +708,7 @@ __global__ void __launch_bounds__(kPcg2Threads, 1) k_pcg2(const Pcg2Plan *plan_g
       double ppap = 0.0;
       {
         int s0, s1;
-        sc.range(Atop, s0, s1);
+        (top_sh ? scx : sc).range(Atop, s0, s1);
         const GatherAxpy<true> g{z, pv, beta};
         for (int s = s0 + warp; s < s1; s += nwarps) {
           bool lead;
@@ -584,13 +716,14 @@ __global__ void __launch_bounds__(kPcg2Threads, 1) k_pcg2(const Pcg2Plan *plan_g
           const double acc = sell_row<true, false>(Atop, s, lane, g);
           if (lead) {
             const double pn = __ldcg(z + row) + beta * __ldcg(pv + row);
-            pv2[row] = pn;
+            if (top_sh) ox.st(pv2, row, pn);   // the next iteration's mat-vec gathers p from every rank's rows
+            else pv2[row] = pn;
             P.Ap[row] = acc;
             ppap += pn * acc;
           }
         }
       }
-      const double pAp = grid_sum2(ppap, slot2, P.bar);
+      const double pAp = xsum(ppap, slot2);
       prof_mark(P.prof, PK_MATVEC);
       {
         double *t = pv;
@@ -608,14 +741,24 @@ __global__ void __launch_bounds__(kPcg2Threads, 1) k_pcg2(const Pcg2Plan *plan_g
         s_e[4] += alpha * rz;
       }
       double prr = 0.0;
-      for (int64_t i = tid; i < m; i += nthr) {
-        P.x[i] += alpha * __ldcg(pv + i);
-        const double ri = P.r[i] - alpha * __ldcg(P.Ap + i);
-        P.r[i] = ri;
-        if (top_sb.two) top_sb.oth[i] = ri * __ldg(top_sb.idg + i);
-        prr += ri * ri;
+      if (top_sh) {
+        for (int i = own0 + (int)threadIdx.x; i < own1; i += (int)blockDim.x) {
+          P.x[i] += alpha * __ldcg(pv + i);
+          const double ri = P.r[i] - alpha * __ldcg(P.Ap + i);
+          P.r[i] = ri;
+          if (top_sb.two) ox.st(top_sb.oth, i, ri * __ldg(top_sb.idg + i));
+          prr += ri * ri;
+        }
+      } else {
+        for (int64_t i = tid; i < m; i += nthr) {
+          P.x[i] += alpha * __ldcg(pv + i);
+          const double ri = P.r[i] - alpha * __ldcg(P.Ap + i);
+          P.r[i] = ri;
+          if (top_sb.two) top_sb.oth[i] = ri * __ldg(top_sb.idg + i);
+          prr += ri * ri;
+        }
       }
-      rr = grid_sum2(prr, slot0, P.bar);
+      rr = xsum(prr, slot0);
       prof_mark(P.prof, PK_UPDATE);
       if (!isfinite(rr)) {
         status = -1.0;
@@ -635,6 +778,11 @@ __global__ void __launch_bounds__(kPcg2Threads, 1) k_pcg2(const Pcg2Plan *plan_g
       e_tot = s_e[4];
       e_last4 = s_e[4] - (it >= 4 ? s_e[it & 3] : 0.0);   // slot (it & 3) holds the total before iteration it - 3
     }
+  }
+  if (top_sh) {   // every rank needs the whole direction: owners publish their rows of x
+    for (int i = own0 + (int)threadIdx.x; i < own1; i += (int)blockDim.x) ox.st(P.x, i, P.x[i]);
+    scx.sync();
+    if (s_xrt.aborted) status = -3.0;   // a peer never arrived at a cross-GPU barrier
   }
   if (tid == 0) {
     P.out[0] = (double)it;
@@ -780,10 +928,13 @@ int pcg2_grid(int device) {
   cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   if (!coop) return 0;
   cudaFuncAttributes fa;
-  if (cudaFuncGetAttributes(&fa, k_pcg2) != cudaSuccess) return 0;
+  if (cudaFuncGetAttributes(&fa, k_pcg2<true>) != cudaSuccess) return 0;   // the larger of the two instantiations
   const int dyn = optin - (int)fa.sharedSizeBytes - 1024;
-  if (dyn > 0) cudaFuncSetAttribute(k_pcg2, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg2, kPcg2Threads, dyn > 0 ? dyn : 0) != cudaSuccess || per_sm < 1) return 0;
+  if (dyn > 0) {
+    cudaFuncSetAttribute(k_pcg2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+    cudaFuncSetAttribute(k_pcg2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+  }
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg2<true>, kPcg2Threads, dyn > 0 ? dyn : 0) != cudaSuccess || per_sm < 1) return 0;
   g_pcg2_grid[device] = nsm < kPcg2MaxGrid ? nsm : kPcg2MaxGrid;
   return g_pcg2_grid[device];
 }
@@ -793,14 +944,15 @@ size_t pcg2_max_tail_bytes(int device) {
   int optin = 0;
   cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   cudaFuncAttributes fa;
-  if (cudaFuncGetAttributes(&fa, k_pcg2) != cudaSuccess) return 0;
+  if (cudaFuncGetAttributes(&fa, k_pcg2<true>) != cudaSuccess) return 0;
   const int dyn = optin - (int)fa.sharedSizeBytes - 1024;
   return dyn > 0 ? (size_t)dyn : 0;
 }
 
-cudaError_t pcg2_launch(const Pcg2Plan *dev_plan, int grid, size_t smem_bytes, double rtol2, int maxit, int stall_window, cudaStream_t s) {
+cudaError_t pcg2_launch(const Pcg2Plan *dev_plan, int grid, size_t smem_bytes, double rtol2, int maxit, int stall_window, bool dist, cudaStream_t s) {
   void *args[] = {(void *)&dev_plan, (void *)&rtol2, (void *)&maxit, (void *)&stall_window};
-  return cudaLaunchCooperativeKernel((const void *)k_pcg2, dim3(grid), dim3(kPcg2Threads), args, smem_bytes, s);
+  const void *fn = dist ? (const void *)k_pcg2<true> : (const void *)k_pcg2<false>;
+  return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kPcg2Threads), args, smem_bytes, s);
 }
 
 cudaError_t pcg2_lambda_power(const Pcg2Plan *dev_plan, int grid, int iters, double safety, cudaStream_t s) {

@@ -18,7 +18,8 @@
 namespace mgbx {
 
 constexpr int kPcg2Threads = 1024;
-constexpr int kPcg2MaxGrid = 1024;
+constexpr int kPcg2MaxGrid = 2048;        // partial-sum slots per reduction (CTAs of all ranks of a multi-GPU solve)
+constexpr int kPcg2MaxRanks = 8;
 constexpr int kPcg2MaxLevels = 32;
 constexpr int kPcg2ProfCap = 1 << 16;   // phase-profile records per launch (debugging aid)
 
@@ -48,6 +49,17 @@ struct Pcg2Level {
   double *pw = nullptr;            // power-iteration vector for lambda_max(D^-1 A) (pcg2_lambda_power), kept between launches
 };
 
+// Multi-GPU solve (one process per GPU): levels [0, nshard) are row-sharded over the ranks.  Everything a peer writes lives in
+// this rank's exchange arena (one cudaMalloc block, identical layout on every rank, mapped into the peers by CUDA IPC):
+// peer_off[q] = (rank q's arena base) - (this rank's arena base) in this process's address space.
+struct Pcg2Dist {
+  int nranks = 1, rank = 0, nshard = 0;
+  long long peer_off[kPcg2MaxRanks] = {0};
+  unsigned long long *flags = nullptr;     // [nranks] epochs published by the peers' CTA 0 (in the arena)
+  unsigned int *xarrive = nullptr;         // local arrival counter of the cross barrier (monotonic)
+  unsigned long long *xrelease = nullptr;  // local release epoch (~0: abort)
+};
+
 struct Pcg2Plan {
   int nlev = 0, nbig = 0;      // active levels: [0, nbig) by the whole grid, [nbig, nlev) by CTA 0 alone
   int bottom_dense = 0;        // the last level is applied through dense_inv (m x m, row-major)
@@ -61,8 +73,10 @@ struct Pcg2Plan {
   const double *b = nullptr;
   double *partials = nullptr;  // 3 x kPcg2MaxGrid
   unsigned int *bar = nullptr;
+  Pcg2Dist dist;
   unsigned long long *prof = nullptr;   // optional phase profile: [0] count, then (tag, globaltimer ns) pairs; tag = level * 16 + kind
-  double *out = nullptr;       // [0] iterations, [1] |r|^2, [2] status (1 converged, 2 stagnated above the tolerance, 3 iteration limit, -1 breakdown), [3] |b|^2,
+  double *out = nullptr;       // [0] iterations, [1] |r|^2, [2] status (1 converged, 2 stagnated above the tolerance, 3 iteration limit, -1 breakdown,
+                               // -3 a peer never arrived at a cross-GPU barrier), [3] |b|^2,
                                // [4] b.x = |x|_A^2, [5] the part of [4] gained in the last four iterations
 };
 
@@ -74,7 +88,7 @@ size_t pcg2_max_tail_bytes(int device);   // dynamic shared memory available to 
 // `iters` power iterations on D^-1 A for every level of the plan in one cooperative launch; lam <- min(lam, safety |D^-1 A v|)
 // (needs nlev * grid <= 3 * kPcg2MaxGrid partial slots and Pcg2Level::pw initialised to a non-zero vector)
 cudaError_t pcg2_lambda_power(const Pcg2Plan *dev_plan, int grid, int iters, double safety, cudaStream_t s);
-cudaError_t pcg2_launch(const Pcg2Plan *dev_plan, int grid, size_t smem_bytes, double rtol2, int maxit, int stall_window, cudaStream_t s);
+cudaError_t pcg2_launch(const Pcg2Plan *dev_plan, int grid, size_t smem_bytes, double rtol2, int maxit, int stall_window, bool dist, cudaStream_t s);
 
 // ---- sliced-ELL construction from a device CSR (int64 row pointers, int32 columns), once per pattern
 struct SellBuild {
