@@ -173,6 +173,66 @@ def reference_arm(args, rank, world):
     }))
 
 
+def fem3d_record(args, cfg, rank, world, local_rank, sharded, new_comm, barrier, tmax_over_ranks):
+    """Sub-record on config C4's family: mgb_solve(assemble(amg(fem3d k=1 on c^3 hexahedra)); p=1; t=t0), ONE resident solve after one
+    warm-up solve, elements partitioned over the ranks for N > 1 (strong scaling, like the headline record).  Parity for N > 1:
+    rank 0 then solves the whole problem alone on its GPU and the objective / |z| are compared."""
+    import torch
+    from mgbx import geometry as G, hierarchy as H, native, problem as P, solver
+    c = args.fem3d_c
+    t0 = time.time()
+    prob = P.assemble(H.amg(G.structured_box(3, c, k=1)), p=1.0)
+    host_build_s = time.time() - t0
+    n = prob.geometry.n
+    bw = solver.barrier_weights(prob.M[0].w)
+    if sharded:
+        from mgbx import partition
+        lprob = partition.shard_problem(prob, rank, world)
+        lbw = partition.shard_barrier_weights(bw, *lprob.node_range)
+    else:
+        lprob, lbw = prob, bw
+    h = native.Handle(lprob, barrier_weights=lbw, device=local_rank, comm=new_comm(), **cfg)
+    try:
+        for rep in range(2):
+            h.set_grids(None, lprob.g)
+            barrier()
+            t1 = time.time()
+            sol = solver.mgb_solve(lprob, handle=h, t=args.fem3d_t)
+            barrier()
+            dt = time.time() - t1
+        info = h.solver_info()
+    finally:
+        h.close()
+    dt = tmax_over_ranks(dt)
+    S, st = sol["SOL_main"], sol["stats"]
+    its = int(S["its"].sum())
+    z2 = float(np.sum(sol["z"] ** 2))
+    if sharded:
+        t = torch.tensor([z2], dtype=torch.float64, device="cuda")
+        torch.distributed.all_reduce(t)
+        z2 = float(t.cpu()[0])
+    rec = {"workload": "mgb_solve(assemble(amg(fem3d(k=1) on %d^3 hexahedra)); p=1.0; t=%g): n=%d broken nodes, fine unknowns %d"
+                       % (c, args.fem3d_t, n, prob.M[0].R_fine[-1].shape[1]),
+           "time_to_solution_s": dt, "value": n * its / dt, "unit": UNIT, "newton_steps": its, "barrier_steps": int(S["its"].shape[1]),
+           "pcg_iters": int(st["pcg_iters"]), "solve_failures": int(st["solve_failures"]),
+           "stage_ms": {k: st[k] for k in ("ms_f01", "ms_f2", "ms_solve")}, "objective": float(S["c_dot_Dz"][-1]), "znorm": float(np.sqrt(z2)),
+           "host_build_s": host_build_s, "levels": info.get("m"), "row_sharded_levels": info.get("nshard", 0)}
+    if sharded:
+        if rank == 0:
+            ref = solver.mgb_solve(prob, config=dict(device=local_rank, **cfg), t=args.fem3d_t)
+            R = ref["SOL_main"]
+            zr = float(np.linalg.norm(ref["z"]))
+            rec["parity_vs_single_gpu"] = {
+                "objective_rel_diff": float(abs(rec["objective"] - R["c_dot_Dz"][-1]) / abs(R["c_dot_Dz"][-1])),
+                "znorm_rel_diff": float(abs(rec["znorm"] - zr) / zr), "newton_steps_single": int(R["its"].sum()),
+                "barrier_steps_single": int(R["its"].shape[1]), "pcg_iters_single": int(ref["stats"]["pcg_iters"]),
+                "single_gpu_e2e_s": float(ref["stats"]["create_s"] + sum(ref["stats"][k] for k in ("ms_f01", "ms_f2", "ms_solve")) * 1e-3)}
+            pv = rec["parity_vs_single_gpu"]
+            pv["pass"] = bool(pv["objective_rel_diff"] < 1e-8 and pv["znorm_rel_diff"] < 1e-6)
+        barrier()
+    return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -187,6 +247,8 @@ def main():
     ap.add_argument("--no-same-config", action="store_true")
     ap.add_argument("--replicas", action="store_true", help="N > 1: N independent solves instead of one element-partitioned solve")
     ap.add_argument("--no-profile-pass", action="store_true")
+    ap.add_argument("--fem3d-c", type=int, default=64, help="fem3d sub-record: k=1 hexahedra per edge (64: n = 2 097 152); 0 = skip")
+    ap.add_argument("--fem3d-t", type=float, default=0.01, help="initial t of the fem3d sub-record (DESIGN.md: t = 0.1 stalls in the reference algorithm itself on >= 32^3)")
     ap.add_argument("--config", action="append", default=[], help="mgbx_config override key=value (repeatable)")
     args = ap.parse_args()
 
@@ -391,10 +453,39 @@ def main():
                                 "value": ps.geometry.n * its_s / dts, "e2e_s": dte, "e2e_value": ps.geometry.n * int(se["SOL_main"]["its"].sum()) / dte,
                                 "parity": parity_record(ss, Ls, args.p)}
 
+    def tmax_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.cpu()[0])
+
+    # N > 1: the partitioned solve against the single-GPU solve of the same problem (rank 0 solves it alone)
+    vs_single = None
+    if sharded:
+        zz = reduce_sum(np.array([float(np.sum(sol["z"] ** 2))]))
+        if rank == 0:
+            ref1 = solver.mgb_solve(prob, config=dict(device=local_rank, **cfg))
+            R1 = ref1["SOL_main"]
+            zr = float(np.linalg.norm(ref1["z"]))
+            vs_single = {"objective_rel_diff": float(abs(sol["SOL_main"]["c_dot_Dz"][-1] - R1["c_dot_Dz"][-1]) / abs(R1["c_dot_Dz"][-1])),
+                         "znorm_rel_diff": float(abs(np.sqrt(zz[0]) - zr) / zr), "newton_steps_single": int(R1["its"].sum()),
+                         "same_t_schedule": bool(R1["ts"].shape == sol["SOL_main"]["ts"].shape and np.allclose(R1["ts"], sol["SOL_main"]["ts"], rtol=1e-12))}
+            vs_single["pass"] = bool(vs_single["objective_rel_diff"] < 1e-8 and vs_single["znorm_rel_diff"] < 1e-6)
+        barrier()
+    parity["vs_single_gpu"] = vs_single
+
+    fem3d = None
+    if args.fem3d_c > 0:
+        try:
+            fem3d = fem3d_record(args, cfg, rank, world, local_rank, sharded, new_comm, barrier, tmax_over_ranks)
+        except Exception as e:     # the sub-record must never take the headline line down with it
+            fem3d = {"error": repr(e)[:300]}
+
     tmax = torch.tensor([dev_s, wall, float(np.mean(e2e_times))], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     dev_s, wall, e2e_s = [float(x) for x in tmax.cpu()]
+    nshard = int(info.get("nshard", 0)) if (roof is not None) else 0
     units = 1 if sharded else world       # sharded: ONE solve split over the ranks; replicas: one solve per rank
     value = units * n * its_total * args.steps / dev_s
     e2e_value = units * n * its_e / e2e_s
@@ -407,7 +498,9 @@ def main():
                    "newton_steps_per_solve": its_total, "time_to_solution_s": dev_s / args.steps,
                    "parallelism": ("1 GPU" if world == 1 else
                                    ("element partition over %d GPUs: barrier / gradient / Hessian kernels sharded by element block, NCCL all-reduce "
-                                    "of R'g, Hessian values and scalars, replicated deterministic multigrid-PCG (strong scaling: ONE solve)" % world)
+                                    "of R'g, Hessian values and scalars; multigrid-PCG solve %s (strong scaling: ONE solve)"
+                                    % (world, ("row-sharded over the ranks inside the persistent kernel on its %d leading level(s) (peer stores over NVLink into "
+                                               "CUDA-IPC exchange arenas, cross-GPU flag barrier), replicated below" % nshard) if nshard else "replicated on every rank"))
                                    if sharded else "replicas: %d independent solves, no data-path collective" % world),
                    "l2_policy": "working set (>= 600 MB of grids, operators and CSR values) exceeds the 126 MB L2; no flush needed",
                    "wall_s_timed_region": wall, "mgbx_config_overrides": cfg},
@@ -428,6 +521,8 @@ def main():
         out["kernel_classes"] = {k: {"launches": v[0], "ms": round(v[1], 3)} for k, v in kstats.items()}
     if same:
         out["same_config"] = same
+    if fem3d:
+        out["fem3d"] = fem3d
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, dt, its, nn, obj = oracle_solve(args.cpu_L, args.p)
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": cpu_sample_text(args.cpu_L, nn, args.p, its, dt),

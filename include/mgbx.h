@@ -290,6 +290,7 @@ typedef struct {
   int64_t hblk_entries;       /* pairs * N * p * p */
   int64_t galerkin_terms;     /* padded terms of all Galerkin product gathers */
   double dgemm_flops;         /* FP64 tensor-core (DMMA) flops issued through this handle so far (spectral path) */
+  int32_t nshard, nranks;     /* multi-GPU: leading V-cycle levels that are row-sharded over the ranks (0: replicated solve), ranks */
 } mgbx_solver_info_t;
 int mgbx_solver_info(mgbx_handle *h, int which, mgbx_solver_info_t *out);
 

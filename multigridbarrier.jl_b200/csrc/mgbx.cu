@@ -1236,7 +1236,7 @@ std::unique_ptr<System> build_system(mgbx_handle *h, Amg &A, bool condensed, int
     S->pc_Ap = pool.alloc<double>(m);
     S->pc_x = pool.alloc<double>(m);
     S->pc_b = pool.alloc<double>(m);
-    S->pcg_partials = pool.zeros<double>(3 * (size_t)kPcgMaxGrid, s);
+    S->pcg_partials = pool.zeros<double>(3 * (size_t)std::max(kPcgMaxGrid, kPcg2MaxGrid), s);
     S->pcg_out = pool.zeros<double>(8, s);
     S->pcg_bar = pool.zeros<unsigned int>(4, s);
     CK(cudaStreamSynchronize(s));
@@ -1368,7 +1368,7 @@ std::unique_ptr<System> build_system(mgbx_handle *h, Amg &A, bool condensed, int
   S->pc_Ap = pool.alloc<double>(mx);
   S->pc_x = pool.alloc<double>(mx);
   S->pc_b = pool.alloc<double>(mx);
-  S->pcg_partials = pool.zeros<double>(3 * (size_t)kPcgMaxGrid, s);
+  S->pcg_partials = pool.zeros<double>(3 * (size_t)std::max(kPcgMaxGrid, kPcg2MaxGrid), s);
   S->pcg_out = pool.zeros<double>(8, s);
   S->pcg_bar = pool.zeros<unsigned int>(4, s);
   CK(cudaStreamSynchronize(s));
@@ -3089,6 +3089,8 @@ int mgbx_solver_info(mgbx_handle *h, int which, mgbx_solver_info_t *out) {
       out->bottom_dense = P.bottom_dense;
       out->grid = h->pcg2_grid;
       out->threads = kPcg2Threads;
+      out->nshard = P.dist.nshard;
+      out->nranks = P.dist.nranks;
       const std::vector<int> act = Engine(h).active_levels(*S, 0);
       for (int q = 0; q < P.nlev; ++q) {
         const SysLevel &Lv = S->lev[act[q]];

@@ -677,6 +677,9 @@ __global__ void __launch_bounds__(kPcg2Threads, 1) k_pcg2(const Pcg2Plan *plan_g
     part += bi * bi;
   }
   const double bb = grid_sum2(part, slot0, P.bar);
+  // multi-GPU: no peer store before every rank is inside this launch (a peer may still be running the kernels in front of
+  // it -- the power iteration uses the level vectors of the exchange arena as scratch)
+  if (top_sh) scx.sync();
   prof_mark(P.prof, PK_INIT);
   int it = 0;
   double rr = bb, status = 1.0, e_tot = 0.0, e_last4 = 0.0;

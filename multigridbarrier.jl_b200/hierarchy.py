@@ -330,6 +330,9 @@ def _compose(geometry, subspaces, refine) -> MultiGrid:
             Rl = [sp.csr_matrix(M) for M in Rl]
         R[X] = Rl
         T[X] = [_transfer(sX[l + 1], rX[l], sX[l]) for l in range(L - 1)]
+        for M in R[X] + T[X]:          # canonical CSR once, here: every consumer (block joins for the two AMGs) wants sorted rows
+            if sp.issparse(M) and not M.has_canonical_format:
+                M.sum_duplicates()
     return MultiGrid(geometry, R, T)
 
 
@@ -560,7 +563,25 @@ def _blockdiag(mats):
     if _is_dense(mats[0]):
         import scipy.linalg as sl
         return sl.block_diag(*mats)
-    return sp.block_diag(mats, format="csr")
+    # direct CSR concatenation (what sp.block_diag(mats, format="csr") returns, without its COO round trip and sort:
+    # 3.6 of the 17 s of host set-up on a 40^3 hexahedral mesh)
+    indptr, indices, data = [np.zeros(1, np.int64)], [], []
+    rows = cols = nnz = 0
+    for M in mats:
+        M = sp.csr_matrix(M)
+        if not M.has_canonical_format:
+            M = M.copy()
+            M.sum_duplicates()
+        indptr.append(M.indptr[1:].astype(np.int64) + nnz)
+        indices.append(M.indices.astype(np.int64) + cols)
+        data.append(np.asarray(M.data, dtype=float))
+        rows += M.shape[0]
+        cols += M.shape[1]
+        nnz += M.nnz
+    idt = np.int32 if max(rows, cols, nnz) < 2 ** 31 - 1 else np.int64
+    out = sp.csr_matrix((np.concatenate(data), np.concatenate(indices).astype(idt), np.concatenate(indptr).astype(idt)), shape=(rows, cols))
+    out.has_canonical_format = True
+    return out
 
 
 def amg_helper(mg: MultiGrid, state_variables, D) -> AMG:

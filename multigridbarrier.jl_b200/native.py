@@ -88,7 +88,8 @@ class SolverInfo(C.Structure):
     _fields_ = [("condensed", C.c_int32), ("nlev", C.c_int32), ("nbig", C.c_int32), ("bottom_dense", C.c_int32),
                 ("grid", C.c_int32), ("threads", C.c_int32), ("m", C.c_int64 * MAX_LEVELS),
                 ("nnz", C.c_int64 * MAX_LEVELS), ("nnzT", C.c_int64 * MAX_LEVELS), ("assembly_terms", C.c_int64),
-                ("hblk_entries", C.c_int64), ("galerkin_terms", C.c_int64), ("dgemm_flops", C.c_double)]
+                ("hblk_entries", C.c_int64), ("galerkin_terms", C.c_int64), ("dgemm_flops", C.c_double),
+                ("nshard", C.c_int32), ("nranks", C.c_int32)]
 
 
 EXPORTS = [
@@ -422,7 +423,7 @@ class Handle:
         return dict(condensed=bool(out.condensed), nlev=L, nbig=out.nbig, bottom_dense=bool(out.bottom_dense),
                     grid=out.grid, threads=out.threads, m=list(out.m[:L]), nnz=list(out.nnz[:L]), nnzT=list(out.nnzT[:L]),
                     assembly_terms=out.assembly_terms, hblk_entries=out.hblk_entries, galerkin_terms=out.galerkin_terms,
-                    dgemm_flops=out.dgemm_flops)
+                    dgemm_flops=out.dgemm_flops, nshard=out.nshard, nranks=out.nranks)
 
     def set_profile(self, on):
         self._check(lib().mgbx_set_profile(self._h, int(on)))

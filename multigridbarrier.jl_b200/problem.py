@@ -204,6 +204,26 @@ def default_g(dim):
     return lambda x: np.array([float(np.dot(x, x)), 100.0])
 
 
+def default_f_grid(dim, x):
+    """map_rows(default_f(dim), x) without the per-node Python call."""
+    out = np.zeros((x.shape[0], dim + 2))
+    out[:, 0] = 0.5
+    out[:, dim + 1] = 1.0
+    return out
+
+
+def default_g_grid(dim, x):
+    """map_rows(default_g(dim), x) without the per-node Python call; the sum of squares is formed left to right exactly as
+    the reference writes it (x[1]^2+x[2]^2+x[3]^2, src/mgb.jl:592-593)."""
+    n = x.shape[0]
+    if dim == 1:
+        return np.stack([x[:, 0].astype(float), np.full(n, 2.0)], axis=1)
+    s = x[:, 0] * x[:, 0]
+    for d in range(1, dim):
+        s = s + x[:, d] * x[:, d]
+    return np.stack([s, np.full(n, 100.0)], axis=1)
+
+
 def default_D(dim):
     return [("u", "id")] + [("u", n) for n in ("dx", "dy", "dz")[:dim]] + [("s", "id")]
 
@@ -240,9 +260,9 @@ def assemble(mg: MultiGrid, dim=None, state_variables=None, D=None, x=None, p=1.
     if x is None:
         x = geom.xflat()
     if g_grid is None:
-        g_grid = map_rows(default_g(dim) if g is None else g, x)
+        g_grid = default_g_grid(dim, x) if g is None else map_rows(g, x)
     if f_grid is None:
-        f_grid = map_rows(default_f(dim) if f is None else f, x)
+        f_grid = default_f_grid(dim, x) if f is None else map_rows(f, x)
     if Q is None:
         Q = convex_Euclidian_power(mg, idx=default_idx(dim), p_grid=np.full(x.shape[0], float(p)))
     if M is None:

@@ -80,6 +80,11 @@ def case_fem3d(c, t, p=1.0, maxit=10000, stride=1):
     return lambda: _solve_case(lambda: P.assemble(H.amg(G.structured_box(3, c, k=1)), p=p), stride=stride, **kw)
 
 
+def case_fem3d_k(k, L, t=0.1, stride=1):
+    """fem3d(k=k) refined L times (src/TensorFEM.jl: the reference's default fem3d is k = 3): Q_k hexahedra, (k+1)^3 nodes each."""
+    return lambda: _solve_case(lambda: P.assemble(H.amg(G.subdivide(G.fem3d(k=k), L)), p=1.0), stride=stride, t=t)
+
+
 def case_spectral2d(n1):
     return lambda: _solve_case(lambda: P.assemble(H.amg(G.spectral2d(n=n1)), p=1.0))
 
@@ -119,6 +124,13 @@ CASES = {
     "fem3d_k1_c24_t0.1": ("mgb_solve(assemble(amg(fem3d(k=1, K=24^3 box)); p=1.0); t=0.1)", case_fem3d(24, 0.1)),
     "fem3d_k1_c24_t0.01": ("mgb_solve(assemble(amg(fem3d(k=1, K=24^3 box)); p=1.0); t=0.01)", case_fem3d(24, 0.01)),
     "fem3d_k1_c32_t0.01": ("mgb_solve(assemble(amg(fem3d(k=1, K=32^3 box)); p=1.0); t=0.01)", case_fem3d(32, 0.01, stride=4)),
+    # config C4 variants (ii)/(iii): Q_2 and Q_3 hexahedra
+    "fem3d_k2_L3_t0.1": ("mgb_solve(assemble(amg(subdivide(fem3d(k=2),3)); p=1.0); t=0.1)", case_fem3d_k(2, 3)),
+    "fem3d_k2_L4_t0.1": ("mgb_solve(assemble(amg(subdivide(fem3d(k=2),4)); p=1.0); t=0.1)", case_fem3d_k(2, 4)),
+    "fem3d_k2_L5_t0.1": ("mgb_solve(assemble(amg(subdivide(fem3d(k=2),5)); p=1.0); t=0.1)", case_fem3d_k(2, 5)),
+    "fem3d_k3_L2_t0.1": ("mgb_solve(assemble(amg(subdivide(fem3d(k=3),2)); p=1.0); t=0.1)", case_fem3d_k(3, 2)),
+    "fem3d_k3_L3_t0.1": ("mgb_solve(assemble(amg(subdivide(fem3d(k=3),3)); p=1.0); t=0.1)", case_fem3d_k(3, 3)),
+    "fem3d_k3_L4_t0.1": ("mgb_solve(assemble(amg(subdivide(fem3d(k=3),4)); p=1.0); t=0.1)", case_fem3d_k(3, 4)),
     # config C3 family
     "spectral2d_n32_p1": ("mgb_solve(assemble(amg(spectral2d(n=32)); p=1.0))", case_spectral2d(32)),
     # config C5 family
