@@ -19,7 +19,7 @@
  *   mgbx_get_z_unfinalized  <- SOL.z_unfinalized                      src/mgb.jl:76-80
  *   mgbx_destroy       <- mgb_cleanup                                 src/mgb.jl:840
  *   mgbx_barrier_eval, mgbx_hessian_pattern, mgbx_hessian_values, mgbx_solve_newton_system,
- *   mgbx_plan_pattern, mgbx_recover_transfer  <- fine-grained parity hooks for barrier(Q).f0/f1/f2 (src/convex.jl:155-202),
+ *   mgbx_plan_pattern, mgbx_recover_transfer, mgbx_shard_row_range  <- fine-grained parity hooks for barrier(Q).f0/f1/f2 (src/convex.jl:155-202),
  *                         _make_block_assembly_plan (src/BlockMatrices.jl:322-491) and solve (src/utils.jl:142-145)
  *
  * Conventions
@@ -308,6 +308,13 @@ int mgbx_plan_pattern(const mgbx_csr *R, int64_t N, int32_t p, int32_t nu, int32
  * mgbx_amg.T == NULL.  val / rowptr / colind may be NULL to query nnz (rowptr holds R_next->cols + 1 entries). */
 int mgbx_recover_transfer(const mgbx_csr *R_next, const mgbx_csr *R_cur, int64_t *nnz, int64_t *rowptr, int64_t *colind,
                           double *val);
+
+/* host-only (no GPU needed): rows [row_begin, row_end) of a V-cycle level that `rank` owns in the row-sharded multi-GPU solve
+ * (cfg.shard_solve; csrc/pcg2.hpp pcg2_rank_rows -- the same arithmetic the persistent kernel's plan uses): the level's sliced-ELL
+ * slices (32 / lanes_per_row rows each) are dealt in contiguous runs to the nranks * ctas_per_rank CTAs of all ranks.  The
+ * reference has no multi-GPU code (src/mgb.jl:392-403 only points at an MPI package); the partition follows the north-star. */
+int mgbx_shard_row_range(int64_t rows, int32_t lanes_per_row, int32_t ctas_per_rank, int32_t nranks, int32_t rank, int64_t *row_begin,
+                         int64_t *row_end);
 
 #ifdef __cplusplus
 }

@@ -1748,7 +1748,7 @@ SellBuild Engine::make_sell(const DevCsr &A, int64_t nthreads) {
   B.M.rows = (int)A.rows;
   B.M.lpr = lpr;
   B.M.nslices = nsl;
-  B.M.spc = (nsl + std::max(1, h->pcg2_grid) - 1) / std::max(1, h->pcg2_grid);
+  B.M.spc = pcg2_slices_per_cta(nsl, std::max(1, h->pcg2_grid));
   if (nsl == 0) return B;
   int *width = tmp_alloc<int>(nsl, s);
   CK(sell_slice_widths(A.rows, lpr, A.ptr, width, s));
@@ -1944,7 +1944,7 @@ void Engine::pcg2_setup_dist(System::Pcg2Dev &D, int nshard) {
   P.p2 = (double *)(D.arena + o_p2);
   P.x = (double *)(D.arena + o_x);
   const int64_t gcta = (int64_t)nr * h->pcg2_grid;
-  auto respc = [&](SellMat &M) { M.spc = (int)((M.nslices + gcta - 1) / gcta); };
+  auto respc = [&](SellMat &M) { M.spc = pcg2_slices_per_cta(M.nslices, gcta); };
   for (int q = 0; q < nshard; ++q) {
     Pcg2Level &pl = P.lev[q];
     pl.x = (double *)(D.arena + o_lev[4 * q + 0]);
@@ -3289,6 +3289,14 @@ int mgbx_recover_transfer(const mgbx_csr *R_next, const mgbx_csr *R_cur, int64_t
     if (val) std::copy(T.val.begin(), T.val.end(), val);
     return MGBX_OK;
   });
+}
+
+int mgbx_shard_row_range(int64_t rows, int32_t lanes_per_row, int32_t ctas_per_rank, int32_t nranks, int32_t rank, int64_t *row_begin,
+                         int64_t *row_end) {
+  if (!row_begin || !row_end || rows < 0 || ctas_per_rank < 1 || nranks < 1 || rank < 0 || rank >= nranks) return MGBX_ERR_ARG;
+  if (lanes_per_row != 1 && lanes_per_row != 2 && lanes_per_row != 4 && lanes_per_row != 8 && lanes_per_row != 16 && lanes_per_row != 32) return MGBX_ERR_ARG;
+  pcg2_rank_rows(rows, lanes_per_row, ctas_per_rank, nranks, rank, *row_begin, *row_end);
+  return MGBX_OK;
 }
 
 }  // extern "C"

@@ -28,6 +28,18 @@ constexpr int kPcg2ProfCap = 1 << 16;   // phase-profile records per launch (deb
 // Padding entries carry val = 0 and idx = the first column of their row (a valid gather for rectangular matrices too).
 // lpr lanes share a row (1, 2, 4 or 8; a slice then holds 32 / lpr rows): entry k of a row sits with lane (k mod lpr) of the
 // row's lane group, so that short levels still occupy the whole grid and a long row's dependent loads are split.
+// slices of a level each CTA owns when `ncta` CTAs (of one GPU, or of all ranks of a row-sharded level) share it
+inline int pcg2_slices_per_cta(int64_t nslices, int64_t ncta) { return (int)((nslices + ncta - 1) / (ncta > 0 ? ncta : 1)); }
+// rows [r0, r1) of a level with `rows` rows and `lpr` lanes per row that rank `rank` of `nranks` owns in a row-sharded solve
+// with `grid` CTAs per rank (CTA c of rank r is CTA r * grid + c of the joint grid)
+inline void pcg2_rank_rows(int64_t rows, int lpr, int grid, int nranks, int rank, int64_t &r0, int64_t &r1) {
+  const int64_t rps = 32 / lpr, nsl = (rows + rps - 1) / rps;
+  const int64_t spc = pcg2_slices_per_cta(nsl, (int64_t)grid * nranks);
+  const int64_t s0 = (int64_t)rank * grid * spc, s1 = (int64_t)(rank + 1) * grid * spc;
+  r0 = s0 * rps < rows ? s0 * rps : rows;
+  r1 = s1 * rps < rows ? s1 * rps : rows;
+}
+
 struct SellMat {
   int rows = 0, nslices = 0;
   int lpr = 1;                 // lanes per row

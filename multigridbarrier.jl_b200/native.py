@@ -99,7 +99,7 @@ EXPORTS = [
     "mgbx_phase1_init", "mgbx_attach_feasibility", "mgbx_set_feasibility_box", "mgbx_reset_feasibility_state", "mgbx_handoff",
     "mgbx_matched_t", "mgbx_get_z", "mgbx_get_z_unfinalized", "mgbx_set_z", "mgbx_set_grids", "mgbx_level_size",
     "mgbx_barrier_eval", "mgbx_hessian_pattern", "mgbx_hessian_values", "mgbx_solve_newton_system",
-    "mgbx_plan_pattern", "mgbx_recover_transfer", "mgbx_launch_count", "mgbx_memory_report", "mgbx_kernel_stats", "mgbx_set_profile", "mgbx_solver_info",
+    "mgbx_plan_pattern", "mgbx_recover_transfer", "mgbx_shard_row_range", "mgbx_launch_count", "mgbx_memory_report", "mgbx_kernel_stats", "mgbx_set_profile", "mgbx_solver_info",
 ]
 
 _lib = None
@@ -154,6 +154,7 @@ def lib():
     L.mgbx_solve_newton_system.argtypes = [H, C.c_int, C.c_int, C.c_double, c_f64p, c_f64p, c_f64p, c_i32p]
     L.mgbx_plan_pattern.argtypes = [C.POINTER(Csr), C.c_int64, C.c_int32, C.c_int32, C.c_int32, c_i32p,
                                     c_i64p, c_i64p, c_i64p]
+    L.mgbx_shard_row_range.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_i64p, c_i64p]
     L.mgbx_recover_transfer.argtypes = [C.POINTER(Csr), C.POINTER(Csr), c_i64p, c_i64p, c_i64p, c_f64p]
     L.mgbx_memory_report.argtypes = [H, C.c_char_p, C.c_int64, c_i64p]
     L.mgbx_launch_count.argtypes = [H]
@@ -499,6 +500,15 @@ def plan_pattern(R, N, p, nu, D_var):
     if rc != OK:
         raise MgbxError(rc, (lib().mgbx_last_error(None) or b"").decode())
     return ptr, ind
+
+
+def shard_row_range(rows, lanes_per_row, ctas_per_rank, nranks, rank):
+    """Host-only: rows [r0, r1) of a level that `rank` owns in the row-sharded multi-GPU solve (csrc/pcg2.hpp)."""
+    r0, r1 = C.c_int64(), C.c_int64()
+    rc = lib().mgbx_shard_row_range(int(rows), int(lanes_per_row), int(ctas_per_rank), int(nranks), int(rank), C.byref(r0), C.byref(r1))
+    if rc != OK:
+        raise MgbxError(rc, "bad argument")
+    return r0.value, r1.value
 
 
 def recover_transfer(R_next, R_cur):

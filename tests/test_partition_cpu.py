@@ -146,3 +146,79 @@ def test_gloo_world2_partial_sums_match_single_rank():
     out = mgr.dict()
     mp.spawn(_rank_main, args=(world, port, out), nprocs=world, join=True)
     assert dict(out) == {0: True, 1: True}
+
+
+# ---- row-sharded solve (cfg.shard_solve): row ownership and the push-to-peers exchange, on the CPU -----------------------
+
+@pytest.mark.parametrize("rows,lpr,grid,nranks", [(261121, 1, 148, 2), (261121, 4, 148, 8), (130561, 4, 148, 4), (970299, 4, 148, 8),
+                                                  (5, 1, 148, 2), (0, 1, 148, 2), (4737, 8, 3, 3), (100000, 32, 148, 8)])
+def test_shard_row_ranges_partition_the_level(rows, lpr, grid, nranks):
+    """mgbx_shard_row_range (host-only, csrc/pcg2.hpp pcg2_rank_rows): the ranks' row ranges are contiguous, ordered, disjoint and
+    cover the level; every range starts on a slice boundary (32 / lpr rows), as the kernel's slice ownership requires."""
+    from mgbx import native
+    rps = 32 // lpr
+    prev = 0
+    for r in range(nranks):
+        r0, r1 = native.shard_row_range(rows, lpr, grid, nranks, r)
+        assert r0 == prev and r0 <= r1 <= rows
+        assert r0 % rps == 0 or r0 == rows
+        prev = r1
+    assert prev == rows
+    with pytest.raises(native.MgbxError):
+        native.shard_row_range(rows, 3, grid, nranks, 0)
+
+
+def _rank_rowshard(rank, world, port, out):
+    """One rank of the CPU emulation of a row-sharded smoothing phase + fixed-order reduction (csrc/pcg2.cu, DIST = true)."""
+    import torch
+    import torch.distributed as dist
+    from mgbx import native
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(5)          # identical (replicated) matrix and vectors on every rank
+        m, grid, lpr = 4737, 6, 4
+        A = sp.random(m, m, density=0.004, random_state=7, format="csr") + sp.identity(m, format="csr") * 4.0
+        x, b = rng.normal(size=m), rng.normal(size=m)
+        idg = 1.0 / A.diagonal()
+        r0, r1 = native.shard_row_range(m, lpr, grid, world, rank)
+        # the phase: this rank computes ITS rows of xnew = x + idg (b - A x) and "stores them into every peer's copy"
+        mine = x[r0:r1] + idg[r0:r1] * (b[r0:r1] - A[r0:r1] @ x)
+        parts = [None] * world
+        dist.all_gather_object(parts, (r0, r1, mine))
+        xnew = np.empty(m)
+        for (a0, a1, v) in parts:
+            xnew[a0:a1] = v
+        ref = x + idg * (b - A @ x)
+        ok = np.array_equal(xnew, ref) or np.allclose(xnew, ref, rtol=0, atol=1e-15)
+        # the reduction: one partial per CTA of the joint grid, deposited in every rank's slot array, summed in CTA order
+        rps = 32 // lpr
+        nsl = (m + rps - 1) // rps
+        spc = -(-nsl // (grid * world))
+        slots = np.zeros(grid * world)
+        for c in range(grid):
+            g = rank * grid + c
+            c0, c1 = min(m, g * spc * rps), min(m, (g + 1) * spc * rps)
+            slots[g] = float(np.dot(b[c0:c1], xnew[c0:c1]))
+        t = torch.from_numpy(slots)
+        dist.all_reduce(t)                       # every slot is written by exactly one rank: the sum IS the exchange
+        total = 0.0
+        for v in t.numpy():
+            total += float(v)                    # same order on every rank -> bitwise identical control flow
+        allt = [None] * world
+        dist.all_gather_object(allt, total)
+        ok = ok and all(v == allt[0] for v in allt) and abs(total - float(b @ ref)) <= 1e-10 * abs(float(b @ ref))
+        out[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_row_sharded_phase_matches_single_rank():
+    import torch.multiprocessing as mp
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_rank_rowshard, args=(world, port, out), nprocs=world, join=True)
+    assert dict(out) == {0: True, 1: True}
