@@ -185,6 +185,12 @@ typedef struct {
                                 ranks inside the persistent solve kernel (peer stores over NVLink into CUDA-IPC-mapped exchange arenas,
                                 cross-GPU flag barrier, csrc/pcg2.hpp); 0: every rank runs the whole solve (replicated) */
   int32_t shard_min_rows;    /* default 100000 */
+  int32_t spectral_kron;     /* 1 (default): dense (spectral) discretisations whose operators and prolongations are Kronecker products
+                                (spectral2d: :dx = kron(DX, I), R = kron(R1, R1), src/spectral2d.jl:22-35) assemble R'HR sum-factorised
+                                (one small DMMA GEMM per block of variables instead of full n x n x n products); 0: unstructured GEMMs */
+  int32_t uncondensed_pcg;   /* 0 (default): a fine-level Newton system that keeps a slack variable which cannot be eliminated node-locally
+                                (a slack in :broken_P1, test/test_pure_p2.jl) and has more unknowns than the dense direct solver takes
+                                (8192) is refused with MGBX_ERR_UNSUPPORTED; 1: run the V-cycle PCG on it anyway (slow to fail) */
 } mgbx_config;
 
 /* options of one mgb_step (src/mgb.jl:16-30; defaults src/mgb.jl:360-363) */

@@ -64,6 +64,9 @@ enum { STAGE_F01 = -1, STAGE_F2 = -2, STAGE_SOLVE = -3 };
 
 namespace {
 
+struct UnsupportedError : std::runtime_error {
+  explicit UnsupportedError(const std::string &m) : std::runtime_error(m) {}
+};
 struct ArgError : std::runtime_error {
   using std::runtime_error::runtime_error;
 };
@@ -408,6 +411,20 @@ struct System {
   bool dense = false;
   std::vector<double *> Rt;          // per kept variable: transposed dense prolongation block (m_q x n)
   double *Hd = nullptr, *Wt = nullptr;
+  // sum-factorised assembly (tensor-product spectral discretisations, dense_kernels.cuh): one entry per block of kept variables
+  struct KronPair {
+    int c1a = 0, c2a = 0, c1b = 0, c2b = 0, ncombo = 0;
+    int64_t offa = 0, offb = 0;
+    const double *AA = nullptr;            // (c1a c1b) x (ncombo n1), constant
+    const double *Qj[kKronMaxCombos], *Qk[kKronMaxCombos];
+    int hidx[kKronMaxCombos];              // packed-symmetric index of the node sample h_jk
+  };
+  bool kron = false;
+  // fine-level system with a slack-like variable (only :id rows) that could NOT be eliminated node-locally (e.g. a slack in
+  // :broken_P1): its 1/slack^2 entries stay in the matrix, which the V-cycle PCG cannot solve reliably late in the t-ramp
+  bool uncondensed_slack = false;
+  std::vector<KronPair> kp;
+  double *Wcat = nullptr;
   // PCG work at the largest size
   double *pc_r = nullptr, *pc_z = nullptr, *pc_p = nullptr, *pc_Ap = nullptr, *pc_x = nullptr, *pc_b = nullptr;
   std::map<int, cudaGraphExec_t> graphs;        // captured PCG iteration per top level (non-persistent path)
@@ -438,6 +455,10 @@ struct Amg {
   int D_var[MGBX_MAX_ND], D_op[MGBX_MAX_ND];
   double *w = nullptr, *f = nullptr, *bw = nullptr, *z = nullptr, *zsave = nullptr, *zinit = nullptr, *zunfin = nullptr;
   const double *ops[MGBX_MAX_OPS];
+  // tensor-product structure of a dense discretisation (spectral2d): ops[o] = kron(kronA[o], kronB[o]), n1 x n1 row-major host
+  // factors; kron_n1 == 0: none
+  int kron_n1 = 0;
+  std::vector<std::vector<double>> kronA, kronB;
   HostCsr hRL;
   std::vector<HostCsr> hT;
   DevCsr RL, RLt;
@@ -1109,6 +1130,42 @@ struct Engine {
 inline bool dense_mode(const Amg &A) { return A.N == 1 && A.p > 64; }
 constexpr int kDenseMaxUnknowns = 8192;   // blocked Cholesky: the triangular solve keeps the right-hand side in shared memory (64 KB)
 
+// M = kron(A, B) with A r1 x c1 and B r2 x c2 (row-major outputs)?  M(r, c) is any accessor.  The factors are fixed up to a
+// scalar by taking B as the block through the entry of largest magnitude; the product is verified entry by entry.
+template <class F>
+bool kron_factor(F M, int r1, int r2, int c1, int c2, std::vector<double> &A, std::vector<double> &B) {
+  const int64_t rows = (int64_t)r1 * r2, cols = (int64_t)c1 * c2;
+  double best = 0.0;
+  int64_t pr = 0, pc = 0;
+  for (int64_t r = 0; r < rows; ++r)
+    for (int64_t c = 0; c < cols; ++c) {
+      const double v = std::fabs(M(r, c));
+      if (v > best) {
+        best = v;
+        pr = r;
+        pc = c;
+      }
+    }
+  if (!(best > 0.0) || !std::isfinite(best)) return false;
+  const int a0 = (int)(pr / r2), b0 = (int)(pr % r2), g0 = (int)(pc / c2), d0 = (int)(pc % c2);
+  A.assign((size_t)r1 * c1, 0.0);
+  B.assign((size_t)r2 * c2, 0.0);
+  for (int b = 0; b < r2; ++b)
+    for (int d = 0; d < c2; ++d) B[(size_t)b * c2 + d] = M((int64_t)a0 * r2 + b, (int64_t)g0 * c2 + d);
+  const double piv = B[(size_t)b0 * c2 + d0];
+  for (int a = 0; a < r1; ++a)
+    for (int g = 0; g < c1; ++g) A[(size_t)a * c1 + g] = M((int64_t)a * r2 + b0, (int64_t)g * c2 + d0) / piv;
+  const double tol = 1e-12 * best;
+  for (int64_t r = 0; r < rows; ++r)
+    for (int64_t c = 0; c < cols; ++c)
+      if (std::fabs(M(r, c) - A[(size_t)(r / r2) * c1 + (c / c2)] * B[(size_t)(r % r2) * c2 + (c % c2)]) > tol) return false;
+  return true;
+}
+inline int isqrt_exact(int64_t v) {
+  const int r = (int)std::llround(std::sqrt((double)v));
+  return ((int64_t)r * r == v) ? r : 0;
+}
+
 std::unique_ptr<System> build_system(mgbx_handle *h, Amg &A, bool condensed, int ltop) {
   auto S = std::make_unique<System>();
   Pool &pool = h->pool;
@@ -1157,6 +1214,16 @@ std::unique_ptr<System> build_system(mgbx_handle *h, Amg &A, bool condensed, int
   }
   for (int v = 0; v < A.nu; ++v) (is_elim[v] ? S->elim : S->kept).push_back(v);
   S->nE = (int)S->elim.size();
+  if (condensed)
+    for (int v = 0; v < A.nu; ++v) {
+      bool idonly = true, any = false;
+      for (int j = 0; j < A.nD; ++j)
+        if (A.D_var[j] == v) {
+          any = true;
+          if (A.D_op[j] >= 0) idonly = false;
+        }
+      if (any && idonly && !is_elim[v] && A.nu > 1) S->uncondensed_slack = true;
+    }
   // row classification
   S->nK = 0;
   for (int j = 0; j < A.nD; ++j) {
@@ -1229,6 +1296,102 @@ std::unique_ptr<System> build_system(mgbx_handle *h, Amg &A, bool condensed, int
     S->Hd = pool.alloc<double>((size_t)A.n * A.n);
     S->Wt = pool.alloc<double>((size_t)mvmax * A.n);
     S->cut = -1;
+    // ---- sum-factorised assembly when every operator and every prolongation block is a Kronecker product
+    if (h->cfg.spectral_kron && A.kron_n1 > 0 && S->nE == 0) {
+      const int n1 = A.kron_n1;
+      const size_t nk = S->kept.size();
+      std::vector<std::vector<double>> R1a(nk), R1b(nk);
+      std::vector<int> cq(nk, 0);
+      bool ok = true;
+      for (size_t q = 0; q < nk && ok; ++q) {
+        const int v = S->kept[q];
+        const int64_t mv = Lv.off[q + 1] - Lv.off[q];
+        const int c = isqrt_exact(mv);
+        if (c <= 0 || c > n1) {
+          ok = false;
+          break;
+        }
+        std::vector<double> dense((size_t)A.n * mv, 0.0);
+        const int64_t c0 = A.voff[L - 1][v];
+        for (int64_t i = 0; i < A.n; ++i)
+          for (int64_t k = Rtop.ptr[(int64_t)v * A.n + i]; k < Rtop.ptr[(int64_t)v * A.n + i + 1]; ++k) {
+            const int64_t cc = Rtop.idx[k] - c0;
+            if (cc >= 0 && cc < mv) dense[(size_t)i * mv + cc] = Rtop.val[k];
+          }
+        cq[q] = c;
+        ok = kron_factor([&](int64_t r, int64_t cc) { return dense[(size_t)r * mv + cc]; }, n1, n1, c, c, R1a[q], R1b[q]);
+      }
+      if (ok) {
+        // per D row j: P_j = A_j R1a_v, Q_j = B_j R1b_v  (n1 x c_v); identity operators have A_j = B_j = I
+        std::vector<std::vector<double>> Pj(S->nK), Qj(S->nK);
+        std::vector<const double *> Qdev(S->nK, nullptr);
+        std::vector<int> qof(S->nK, -1);
+        auto mul = [&](const std::vector<double> *F, const std::vector<double> &Rm, int c) {
+          if (!F) return Rm;
+          std::vector<double> out((size_t)n1 * c, 0.0);
+          for (int e = 0; e < n1; ++e)
+            for (int g = 0; g < n1; ++g) {
+              const double f = (*F)[(size_t)e * n1 + g];
+              if (f != 0.0)
+                for (int i = 0; i < c; ++i) out[(size_t)e * c + i] += f * Rm[(size_t)g * c + i];
+            }
+          return out;
+        };
+        for (int a = 0; a < S->nK; ++a) {
+          const int j = S->Krow[a], v = A.D_var[j], o = A.D_op[j];
+          for (size_t q = 0; q < nk; ++q)
+            if (S->kept[q] == v) qof[a] = (int)q;
+          if (qof[a] < 0) continue;
+          Pj[a] = mul(o >= 0 ? &A.kronA[o] : nullptr, R1a[qof[a]], cq[qof[a]]);
+          Qj[a] = mul(o >= 0 ? &A.kronB[o] : nullptr, R1b[qof[a]], cq[qof[a]]);
+          Qdev[a] = pool.upload<double>(Qj[a].data(), Qj[a].size(), s);
+        }
+        size_t wmax = 0;
+        for (size_t qa = 0; qa < nk && ok; ++qa)
+          for (size_t qb = 0; qb < nk && ok; ++qb) {
+            System::KronPair kp;
+            kp.c1a = kp.c2a = cq[qa];
+            kp.c1b = kp.c2b = cq[qb];
+            kp.offa = Lv.off[qa];
+            kp.offb = Lv.off[qb];
+            std::vector<std::pair<int, int>> combos;
+            for (int ja = 0; ja < S->nK; ++ja)
+              for (int kb = 0; kb < S->nK; ++kb)
+                if (qof[ja] == (int)qa && qof[kb] == (int)qb) combos.push_back({ja, kb});
+            if (combos.empty()) continue;
+            if ((int)combos.size() > kKronMaxCombos) {
+              ok = false;
+              break;
+            }
+            kp.ncombo = (int)combos.size();
+            const int64_t Mr = (int64_t)kp.c1a * kp.c1b, K = (int64_t)kp.ncombo * n1;
+            std::vector<double> AA((size_t)Mr * K);
+            for (int c = 0; c < kp.ncombo; ++c) {
+              const int ja = combos[c].first, kb = combos[c].second;
+              const int lo = std::min(ja, kb), hi = std::max(ja, kb);
+              kp.hidx[c] = lo * S->nK - (lo * (lo - 1)) / 2 + (hi - lo);
+              kp.Qj[c] = Qdev[ja];
+              kp.Qk[c] = Qdev[kb];
+              for (int i = 0; i < kp.c1a; ++i)
+                for (int l = 0; l < kp.c1b; ++l)
+                  for (int e = 0; e < n1; ++e)
+                    AA[((size_t)i * kp.c1b + l) * K + (size_t)c * n1 + e] = Pj[ja][(size_t)e * kp.c1a + i] * Pj[kb][(size_t)e * kp.c1b + l];
+            }
+            kp.AA = pool.upload<double>(AA.data(), AA.size(), s);
+            wmax = std::max(wmax, (size_t)kp.c2a * kp.c2b * (size_t)K);
+            S->kp.push_back(kp);
+          }
+        if (ok && !S->kp.empty()) {
+          S->Wcat = pool.alloc<double>(wmax);
+          S->kron = true;
+          const size_t smem = sizeof(double) * ((size_t)n1 + 2 * (size_t)n1 * n1);
+          CK(cudaFuncSetAttribute(k_kron_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        } else {
+          S->kp.clear();
+        }
+      }
+      if (h->cfg.verbose > 0) fprintf(stderr, "[mgbx] build_system(dense, level %d): sum-factorised (Kronecker) assembly %s\n", ltop, S->kron ? "on" : "not applicable");
+    }
     S->pc_r = pool.alloc<double>(m);
     S->pc_z = pool.alloc<double>(m);
     S->pc_p = pool.alloc<double>(m);
@@ -1471,6 +1634,32 @@ void Engine::assemble_dense(Amg &A, System &S, const NodeParams &P) {
   const int64_t m = top.m;
   const int n = (int)A.n, nK = S.nK;
   zero(top.A.val, m * m);
+  if (S.kron) {
+    // sum-factorised: per block of kept variables one small contraction over the fast index (k_kron_w), ONE DMMA GEMM over
+    // (operator pair, slow index) against the constant factor table, and the index permutation into the system matrix
+    const int n1 = A.kron_n1;
+    for (const System::KronPair &kp : S.kp) {
+      KronWArgs W;
+      memset(&W, 0, sizeof(W));
+      W.n1 = n1;
+      W.c2a = kp.c2a;
+      W.c2b = kp.c2b;
+      W.ncombo = kp.ncombo;
+      W.K = kp.ncombo * n1;
+      for (int c = 0; c < kp.ncombo; ++c) {
+        W.c[c].Qj = kp.Qj[c];
+        W.c[c].Qk = kp.Qk[c];
+        W.c[c].h = A.Hn + (int64_t)kp.hidx[c] * A.n;
+      }
+      const size_t smem = sizeof(double) * ((size_t)n1 + (size_t)n1 * kp.c2a + (size_t)n1 * kp.c2b);
+      LAUNCH(KC_DENSE, k_kron_w<<<kp.ncombo * n1, 256, smem, s>>>(W, S.Wcat));
+      const int Mr = kp.c1a * kp.c1b, Nc = kp.c2a * kp.c2b;
+      dgemm_nt(Mr, Nc, W.K, kp.AA, W.K, S.Wcat, W.K, nullptr, S.Hd, Nc, false);
+      LAUNCH(KC_DENSE, k_kron_scatter<<<nblk((int64_t)Mr * Nc), 256, 0, s>>>(kp.c1a, kp.c2a, kp.c1b, kp.c2b, S.Hd, top.A.val, m, kp.offa, kp.offb));
+    }
+    setup_hierarchy(A, S, 0);
+    return;
+  }
   for (size_t qa = 0; qa < S.kept.size(); ++qa)
     for (size_t qb = 0; qb < S.kept.size(); ++qb) {
       const int va = S.kept[qa], vb = S.kept[qb];
@@ -2102,6 +2291,13 @@ int Engine::solve_compact(System &S, int ktop, const double *b, double *x) {
     LAUNCH(KC_VEC, k_axpby<<<nblk(Lv.m), 256, 0, s>>>(Lv.m, 1.0, x, 1.0, Lv.x2, x));
     return 0;
   }
+  // Loud, not slow: an un-condensable slack above the dense fallback size would grind through thousands of failing PCG solves
+  // (kappa -> sqrt(kappa) ~50 times per barrier step) before mgb_core gives up.  The reference's direct solve has no such
+  // regime; refuse it up front unless the caller opts in (cfg.uncondensed_pcg).
+  if (S.uncondensed_slack && !h->cfg.uncondensed_pcg && Lv.m > kDenseMaxUnknowns)
+    throw UnsupportedError("Newton system with a slack variable that cannot be eliminated node-locally (e.g. a slack in :broken_P1) and " +
+                           std::to_string((long long)Lv.m) + " unknowns: above the dense direct solver's size (8192) only the V-cycle PCG is available, "
+                           "which is not reliable for these systems (set cfg.uncondensed_pcg = 1 to try anyway)");
   const int it = pcg(S, ktop, b, x);
   // PCG first, direct second: a solve that broke down or stayed inexact is redone by the dense Cholesky when the system is
   // small enough to hold as a dense matrix (the un-condensable families, the last steps of a parabolic ramp)
@@ -2539,6 +2735,21 @@ void create_amg(mgbx_handle *h, const mgbx_amg &in, Amg &A) {
   }
   const size_t ppN = (size_t)in.p * in.p * in.N;
   for (int o = 0; o < in.nops; ++o) A.ops[o] = pool.upload<double>(in.op_data[o], ppN, s);
+  // dense (spectral) discretisation on a tensor grid: are all operators Kronecker products kron(A1, B1) of n1 x n1 factors
+  // (src/spectral2d.jl:28-35)?  Then the Hessian assembly is sum-factorised (build_system, dense_kernels.cuh).
+  A.kron_n1 = 0;
+  if (in.N == 1 && in.p > 64 && in.nops > 0) {
+    const int n1 = isqrt_exact(in.n);
+    bool ok = n1 > 1;
+    A.kronA.assign(in.nops, {});
+    A.kronB.assign(in.nops, {});
+    for (int o = 0; o < in.nops && ok; ++o) {
+      const double *D = in.op_data[o];   // column-major n x n
+      const int64_t nn = in.n;
+      ok = kron_factor([&](int64_t r, int64_t c) { return D[r + c * nn]; }, n1, n1, n1, n1, A.kronA[o], A.kronB[o]);
+    }
+    if (ok) A.kron_n1 = n1;
+  }
   A.w = pool.upload<double>(in.w, in.n, s);
   A.voff.resize(in.L);
   A.m.resize(in.L);
@@ -2645,6 +2856,10 @@ int guarded(mgbx_handle *h, const std::function<int()> &fn) {
     if (h) h->err = e.what();
     g_last_error = e.what();
     return MGBX_ERR_ARG;
+  } catch (const UnsupportedError &e) {
+    if (h) h->err = e.what();
+    g_last_error = e.what();
+    return MGBX_ERR_UNSUPPORTED;
   } catch (const std::invalid_argument &e) {
     if (h) h->err = e.what();
     g_last_error = e.what();
@@ -2695,6 +2910,8 @@ void mgbx_default_config(mgbx_config *c) {
   c->elem_bulk = 1;
   c->shard_solve = 1;
   c->shard_min_rows = 100000;
+  c->spectral_kron = 1;
+  c->uncondensed_pcg = 0;
 }
 
 void mgbx_default_step_opts(mgbx_step_opts *o, int64_t n) {

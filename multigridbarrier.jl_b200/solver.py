@@ -280,6 +280,7 @@ def parabolic_solve(mg, p=1.0, h=0.2, t0=0.0, t1=1.0, ts=None, f1=None, g=None, 
         ts = np.arange(t0, t1 + 0.5 * h, h)
     x = geom.xflat()
     n = x.shape[0]
+    default_f1, default_g = f1 is None, g is None      # the defaults are evaluated vectorised (no per-node Python call)
     if f1 is None:
         f1 = lambda t, xx: 0.5
     if g is None:
@@ -294,8 +295,17 @@ def parabolic_solve(mg, p=1.0, h=0.2, t0=0.0, t1=1.0, ts=None, f1=None, g=None, 
         idx2 = tuple(range(1, dim + 1)) + (dim + 2,)
         Q = intersect(mg, convex_Euclidian_power(mg, idx=idx1, p_grid=np.full(n, 2.0)),
                       convex_Euclidian_power(mg, idx=idx2, p_grid=np.full(n, float(p))))
-    f1_grid = np.array([[f1(ts[j], x[i]) for j in range(len(ts))] for i in range(n)])
-    U = [np.array([g(ts[k], x[i]) for i in range(n)], dtype=float) for k in range(len(ts))]
+    if default_f1:
+        f1_grid = np.full((n, len(ts)), 0.5)
+    else:
+        f1_grid = np.array([[f1(ts[j], x[i]) for j in range(len(ts))] for i in range(n)])
+    if default_g:
+        g0 = x[:, 0] * x[:, 0] if dim > 1 else x[:, 0].astype(float)
+        for d in range(1, dim):
+            g0 = g0 + x[:, d] * x[:, d]
+        U = [np.stack([g0, np.zeros(n), np.zeros(n)], axis=1) for _ in range(len(ts))]
+    else:
+        U = [np.array([g(ts[k], x[i]) for i in range(n)], dtype=float) for k in range(len(ts))]
     M = prepare_amg(mg, state_variables, D)
     handle = None
     step_stats = []

@@ -452,16 +452,19 @@ def test_element_kernel_variants_agree(name):
 
 
 # ------------------------------------------------------------------------------------------ spectral (dense) path
-@pytest.mark.parametrize("name,geom", [("spectral2d_n9", lambda: G.spectral2d(n=9)), ("spectral2d_n16", lambda: G.spectral2d(n=16)),
-                                       ("spectral1d_n96", lambda: G.spectral1d(n=96))])
-def test_spectral_dense_path_matches_oracle(name, geom):
-    """Spectral discretisations with more than 64 nodes take the dense path: per-node Hessian samples, then
-    H = sum D_j' diag(h) D_k and R'HR as FP64 DMMA GEMMs into a full matrix, dense Cholesky solve."""
+@pytest.mark.parametrize("name,geom,cfg", [("spectral2d_n9", lambda: G.spectral2d(n=9), {}), ("spectral2d_n16", lambda: G.spectral2d(n=16), {}),
+                                           ("spectral2d_n16_unstructured", lambda: G.spectral2d(n=16), {"spectral_kron": 0}),
+                                           ("spectral1d_n96", lambda: G.spectral1d(n=96), {})])
+def test_spectral_dense_path_matches_oracle(name, geom, cfg):
+    """Spectral discretisations with more than 64 nodes take the dense path: per-node Hessian samples, then R'HR as FP64 DMMA
+    GEMMs into a full matrix, dense Cholesky solve.  spectral2d (operators and prolongations are Kronecker products,
+    src/spectral2d.jl:22-35) assembles sum-factorised by default; cfg.spectral_kron = 0 and spectral1d take the unstructured
+    products H = sum D_j' diag(h) D_k, R'(H R)."""
     prob = P.assemble(H.amg(geom()), p=1.0)
     M = prob.M[0]
     t = 0.7
     rng = np.random.default_rng(2)
-    h = native.Handle(prob, barrier_weights=O.barrier_weights(M.w))
+    h = native.Handle(prob, barrier_weights=O.barrier_weights(M.w), **cfg)
     try:
         B = O.Barrier(prob.Q, O.barrier_weights(M.w))
         ops = O.operators(M)
@@ -478,7 +481,7 @@ def test_spectral_dense_path_matches_oracle(name, geom):
             assert np.linalg.norm(H_o @ x_d - g_o) <= 1e-7 * np.linalg.norm(g_o)
     finally:
         h.close()
-    sd = solver.mgb_solve(prob)
+    sd = solver.mgb_solve(prob, config=cfg)
     so = O.mgb_solve(prob)
     assert rel(sd["z"], so["z"]) < 1e-6
     assert sd["SOL_main"]["its"].shape == so["SOL_main"]["its"].shape

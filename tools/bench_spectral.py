@@ -20,10 +20,15 @@ def dgemm_peak(n=4096, reps=5):
 
 peak = dgemm_peak()
 print(json.dumps({"cublas_dgemm_tflops_4096": peak}), flush=True)
-for n1 in [int(a) for a in sys.argv[1:]] or [16, 24, 32]:
+cfg = {}
+for a in sys.argv[1:]:
+    if "=" in a:                       # mgbx_config override, e.g. spectral_kron=0
+        k, v = a.split("=")
+        cfg[k] = float(v) if ("." in v or "e" in v.lower()) else int(v)
+for n1 in [int(a) for a in sys.argv[1:] if "=" not in a] or [16, 24, 32]:
     prob = P.assemble(H.amg(G.spectral2d(n=n1)), p=1.0)
     M = prob.M[0]
-    h = native.Handle(prob, barrier_weights=solver.barrier_weights(M.w))
+    h = native.Handle(prob, barrier_weights=solver.barrier_weights(M.w), **cfg)
     sol = solver.mgb_solve(prob, handle=h)                       # warm-up (plans, module load)
     h.set_grids(None, prob.g)
     h.set_profile(1); h.kernel_stats(reset=True)
@@ -35,7 +40,7 @@ for n1 in [int(a) for a in sys.argv[1:]] or [16, 24, 32]:
     h.set_profile(0); h.close()
     its = int(sol["SOL_main"]["its"].sum())
     g = ks["dgemm_dmma"]
-    print(json.dumps({"workload": "spectral2d(n=%d), p=1" % n1, "nodes": M.geometry.n, "fine_unknowns": M.R_fine[-1].shape[1],
+    print(json.dumps({"workload": "spectral2d(n=%d), p=1" % n1, "config": cfg, "objective": float(sol["SOL_main"]["c_dot_Dz"][-1]), "nodes": M.geometry.n, "fine_unknowns": M.R_fine[-1].shape[1],
                       "newton_steps": its, "solve_s": dt, "dof_newton_steps_per_s": M.geometry.n * its / dt,
                       "dgemm_launches": g[0], "dgemm_ms": g[1], "dgemm_tflops": fl / (g[1] * 1e-3) / 1e12 if g[1] else None,
                       "dgemm_frac_of_cublas": (fl / (g[1] * 1e-3) / 1e12 / peak) if g[1] else None,
