@@ -151,7 +151,7 @@ typedef struct {
   double cheb_ratio;         /* default 8 (sweep in profiles/r01z_smoother_sweep.jsonl) */
   int32_t precond_fp32;      /* 1: the V-cycle (preconditioner) reads FP32 copies of the level matrices (8 instead of 12 bytes per
                                 non-zero); the PCG operator, vectors and all reductions stay FP64.  0 off, 2 (default) automatic: only when
-                                the top matrix has >= 8 M non-zeros (V-cycle HBM-bound) */
+                                the level matrices together have >= 10 M non-zeros (they no longer fit the L2: V-cycle HBM-bound) */
   int32_t pcg_lanes;         /* lanes per matrix row in the persistent kernel's level mat-vecs.  0 (default): per level, the width
                                 in {1, 4, 32} with the shortest dependent-load chain (passes over the rows x loads per pass) when rows average
                                 <= 16 entries, else by average row length;
@@ -185,6 +185,8 @@ typedef struct {
                                 ranks inside the persistent solve kernel (peer stores over NVLink into CUDA-IPC-mapped exchange arenas,
                                 cross-GPU flag barrier, csrc/pcg2.hpp); 0: every rank runs the whole solve (replicated) */
   int32_t shard_min_rows;    /* default 100000 */
+  int32_t shard_min_nnz;     /* default 4000000: a level is sharded over N ranks only if nnz (1 - 1/N) >= this (a phase over it must
+                                be long enough to pay for the cross-GPU barrier) */
   int32_t spectral_kron;     /* 1 (default): dense (spectral) discretisations whose operators and prolongations are Kronecker products
                                 (spectral2d: :dx = kron(DX, I), R = kron(R1, R1), src/spectral2d.jl:22-35) assemble R'HR sum-factorised
                                 (one small DMMA GEMM per block of variables instead of full n x n x n products); 0: unstructured GEMMs */

@@ -1045,7 +1045,10 @@ struct Engine {
   // is far larger than the L2 cache, i.e. when the V-cycle is HBM-bound (measured -12% per PCG iteration at 26 M non-zeros,
   // neutral at 2 M)
   bool precond_fp32(const System &S) const {
-    return h->cfg.precond_fp32 == 1 || (h->cfg.precond_fp32 == 2 && !S.lev.empty() && S.lev[0].A.nnz >= 8000000);
+    if (h->cfg.precond_fp32 != 2) return h->cfg.precond_fp32 == 1;
+    int64_t tot = 0;                       // automatic: the level matrices together (12 B per entry) no longer fit the 126 MB L2
+    for (const SysLevel &Lv : S.lev) tot += Lv.A.nnz;
+    return tot >= 10000000;
   }
   // power iterations per level and assembly for lambda_max(D^-1 A): cfg.lambda_power, or automatic (-1): 6 when the top
   // matrix has long rows (3-D stencils: the Gershgorin bound overestimates 1.3-2.5x there and misplaces the Chebyshev
@@ -1931,7 +1934,10 @@ SellBuild Engine::make_sell(const DevCsr &A, int64_t nthreads) {
   // levels of C2, four lanes on the 32 k-row level)
   int lpr = 1;
   const double avg = A.rows ? (double)A.nnz / (double)A.rows : 0.0;
-  while (lpr < 8 && A.rows * (int64_t)lpr * 2 <= nthreads && avg / lpr >= 2.0) lpr *= 2;
+  // up to a whole warp per row: the near-dense coarse Galerkin levels of 3-D hierarchies (fem3d 64^3: 544 rows of ~500 entries)
+  // otherwise leave 8 lanes walking 60+ dependent rounds each -- 141 us per PCG iteration on a 544-row level
+  // (profiles/r02h_pcg2_phase_profile_fem3d_64cubed.txt)
+  while (lpr < 32 && A.rows * (int64_t)lpr * 2 <= nthreads && avg / lpr >= 2.0) lpr *= 2;
   const int rps = 32 / lpr;
   const int nsl = (int)((A.rows + rps - 1) / rps);
   B.M.rows = (int)A.rows;
@@ -2062,9 +2068,14 @@ System::Pcg2Dev &Engine::pcg2_plan(System &S, int ktop) {
   if (getenv("MGBX_PCG_PROF")) P.prof = h->pool.zeros<unsigned long long>(1 + 2 * (size_t)kPcg2ProfCap, s);
   if (dist() && h->cfg.shard_solve && P.nlev >= 2) {
     // multi-GPU: the leading levels with at least shard_min_rows unknowns are row-sharded over the ranks (pcg2.hpp)
+    // A cross-GPU barrier costs several microseconds more than the local grid barrier, so a level is sharded only when a phase
+    // over it is long enough to pay for that: T (1 - 1/N) > B with T ~ 12 B nnz / 3 TB/s and B ~ 10 us (measured on 2 GPUs:
+    // profiles/r02f_*), i.e. nnz (1 - 1/N) >= shard_min_nnz (default 4 M).  C2's 2-D levels (1.8 M non-zeros) stay replicated.
     int nshard = 0;
+    const std::vector<int> act = active_levels(S, ktop);
     for (int q = 0; q < P.nbig && q < P.nlev - 1; ++q) {
-      if (P.lev[q].m < h->cfg.shard_min_rows) break;
+      const double nnzq = (double)S.lev[act[q]].A.nnz * (1.0 - 1.0 / (double)h->nranks);
+      if (P.lev[q].m < h->cfg.shard_min_rows || nnzq < (double)h->cfg.shard_min_nnz) break;
       nshard = q + 1;
     }
     if (nshard > 0) pcg2_setup_dist(D, nshard);
@@ -2910,6 +2921,7 @@ void mgbx_default_config(mgbx_config *c) {
   c->elem_bulk = 1;
   c->shard_solve = 1;
   c->shard_min_rows = 100000;
+  c->shard_min_nnz = 4000000;
   c->spectral_kron = 1;
   c->uncondensed_pcg = 0;
 }
