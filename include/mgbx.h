@@ -193,6 +193,11 @@ typedef struct {
   int32_t uncondensed_pcg;   /* 0 (default): a fine-level Newton system that keeps a slack variable which cannot be eliminated node-locally
                                 (a slack in :broken_P1, test/test_pure_p2.jl) and has more unknowns than the dense direct solver takes
                                 (8192) is refused with MGBX_ERR_UNSUPPORTED; 1: run the V-cycle PCG on it anyway (slow to fail) */
+  int32_t analytic_schur;    /* 1 (default): the node-local Schur complement of a slack that enters ONE Euclidean-power cone is formed in
+                                closed form, (2/rho) I + (4/rho^2)(B/(A+B)) q q' with H_ss = A + B, instead of H_qq - H_qs H_sq / H_ss:
+                                the subtraction cancels to O(1/t) relative and leaves no correct digit along q at t ~ 1e8 (the reduced
+                                matrix turns indefinite, the PCG stalls).  0: numerical subtraction (the round-1 behaviour; the
+                                specialised p-Laplace kernel always uses the closed form) */
 } mgbx_config;
 
 /* options of one mgb_step (src/mgb.jl:16-30; defaults src/mgb.jl:360-363) */

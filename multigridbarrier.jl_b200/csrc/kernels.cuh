@@ -217,9 +217,13 @@ struct NodeParams {
   double *Hn;                        // n x nK(nK+1)/2, packed (a<=b): a*nK - a(a-1)/2 + (b-a)
   double *hEEinv;                    // n x nE(nE+1)/2
   double *hKE;                       // n x (nK*nE): entry (a, ev) at column a*nE + ev
+  unsigned schur_pieces, schur_elim; // pieces condensed analytically by node_eval / the eliminated variables they cover (bit masks)
   // SLACK output
   double *slack;                     // n
 };
+
+// the analytic condensation only applies when something is eliminated
+__device__ __forceinline__ unsigned nE_mask_guard(const NodeParams &P) { return P.nE > 0 ? P.schur_pieces : 0u; }
 
 __device__ __forceinline__ void node_Dz(const NodeParams &P, int64_t i, double *y) {
   const int64_t e = i / P.p;
@@ -308,7 +312,7 @@ __global__ void __launch_bounds__(kRedThreads) k_node(NodeParams P) {
       double F2[NDT * NDT];
       const double sc = P.bw ? bwi : P.inv_n;
       if (active) {
-        node_eval(P.cd, P.n, i, y, 2, F1, F2);
+        node_eval(P.cd, P.n, i, y, 2, F1, F2, nE_mask_guard(P));
         for (int k = 0; k < nD * nD; ++k) F2[k] *= sc;
       } else {
         for (int k = 0; k < nD * nD; ++k) F2[k] = 0.0;
@@ -344,6 +348,7 @@ __global__ void __launch_bounds__(kRedThreads) k_node(NodeParams P) {
           for (int b = a; b < nK; ++b, ++q) {
             double s = F2[P.Krow[a] * nD + P.Krow[b]];
             for (int ev = 0; ev < nE; ++ev) {
+              if ((P.schur_elim >> ev) & 1u) continue;   // already condensed analytically inside node_eval
               double wv = 0.0;
               for (int ew = 0; ew < nE; ++ew) wv += hEE[ev * nE + ew] * hKE[b * nE + ew];
               s -= hKE[a * nE + ev] * wv;
@@ -813,7 +818,7 @@ __global__ void __launch_bounds__(256) k_elem(ElemFused Q) {
       } else {
         double F2[NDT * NDT];
         if (active) {
-          node_eval(P.cd, P.n, i, y, 2, F1, F2);
+          node_eval(P.cd, P.n, i, y, 2, F1, F2, nE_mask_guard(P));
           for (int k = 0; k < nD * nD; ++k) F2[k] *= sc;
         } else {
           for (int k = 0; k < nD * nD; ++k) F2[k] = 0.0;
@@ -848,6 +853,7 @@ __global__ void __launch_bounds__(256) k_elem(ElemFused Q) {
             for (int b = a; b < nK; ++b, ++qq) {
               double s = F2[P.Krow[a] * nD + P.Krow[b]];
               for (int ev = 0; ev < nE; ++ev) {
+                if ((P.schur_elim >> ev) & 1u) continue;   // already condensed analytically inside node_eval
                 double wv = 0.0;
                 for (int ew = 0; ew < nE; ++ew) wv += hEE[ev * nE + ew] * hKE[b * nE + ew];
                 s -= hKE[a * nE + ev] * wv;
@@ -1187,8 +1193,14 @@ __global__ void __launch_bounds__(256, 3) k_elem_plap(PlapParams P) {
           const double coef = -2.0 * al * sam1 * inv_r2;
           const double sam2 = in ? sam1 / s : safe_pow(s, al - 2.0);
           const double s2am2 = in ? sam1 * sam1 : safe_pow(s, 2.0 * al - 2.0);
-          const double hss = sc * (-al * (al - 1.0) * sam2 * inv_r + al * al * s2am2 * inv_r2 + P.mu / (s * s));
+          // H_ss = A + B with A = (al s^(al-1) / r)^2 (the square of the coupling) and B the rest.  The node-local Schur
+          // complement of the slack is  H_qq - H_qs H_sq / H_ss = (2/r) I + (4/r^2) (B / (A + B)) q q':  formed this way, not by
+          // subtracting two terms of size 4 q q'/r^2 ~ t^2 whose difference is O(t) across q and O(1) along q -- at t ~ 1e8 the
+          // subtraction leaves NO correct digit along q (absolute error eps t^2 ~ 1) and the reduced matrix turns indefinite.
+          const double hA = al * al * s2am2 * inv_r2, hB = -al * (al - 1.0) * sam2 * inv_r + P.mu / (s * s);
+          const double hss = sc * (hA + hB);
           const double ihs = COND ? 1.0 / hss : 0.0;
+          const double schur = hB / (hA + hB);
           double hqs[DIM];
 #pragma unroll
           for (int a = 0; a < DIM; ++a) hqs[a] = sc * coef * q[a];
@@ -1207,8 +1219,8 @@ __global__ void __launch_bounds__(256, 3) k_elem_plap(PlapParams P) {
           for (int a = 0; a < DIM; ++a)
 #pragma unroll
             for (int bb = a; bb < DIM; ++bb, ++k) {
-              const double hab = sc * (4.0 * q[a] * q[bb] * inv_r2 + (a == bb ? 2.0 * inv_r : 0.0));
-              ex[k * TM + tid] = COND ? hab - hqs[a] * hqs[bb] * ihs : hab;
+              const double qq4 = 4.0 * q[a] * q[bb] * inv_r2, dg = (a == bb ? 2.0 * inv_r : 0.0);
+              ex[k * TM + tid] = COND ? sc * (qq4 * schur + dg) : sc * (qq4 + dg);
             }
         } else {
           if (COND) {

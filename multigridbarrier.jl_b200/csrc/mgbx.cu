@@ -1063,6 +1063,7 @@ struct Engine {
     return S.dense || Lv.m <= h->cfg.dense_direct_max;   // dense (spectral) systems have no hierarchy: always direct
   }
   void assemble(Amg &A, System &S, int J, double t, const double *zbase, const double *x);
+  void schur_masks(const Amg &A, const System &S, unsigned &pieces, unsigned &elim) const;
   void assemble_dense(Amg &A, System &S, const NodeParams &P);
   void dgemm_nt(int M, int N, int K, const double *Am, int64_t lda, const double *Bm, int64_t ldb, const double *sc, double *C, int64_t ldc, bool acc, double alpha = 1.0);
   void setup_hierarchy(Amg &A, System &S, int ktop);
@@ -1561,6 +1562,34 @@ System &Engine::system_for(Amg &A, int J) {
   return *A.sys_coarse;
 }
 
+// Which Euclidean-power pieces can be condensed analytically (node_barrier.cuh piece_eval): identity A, not under the phase-I
+// wrapper, the piece's slack row belongs to a node-locally eliminated variable that has no other D row and that no other piece
+// (nor another input of this piece) touches, and none of its q rows is eliminated.  Then H_EE is diagonal in that variable and its
+// Schur complement is the piece's own.
+void Engine::schur_masks(const Amg &A, const System &S, unsigned &pieces, unsigned &elim) const {
+  pieces = elim = 0u;
+  if (!h->cfg.analytic_schur || S.nE == 0 || A.cd.feas) return;
+  const ConvexDev &cd = A.cd;
+  for (int k = 0; k < cd.npieces && k < 32; ++k) {
+    const PieceDev &pc = cd.pc[k];
+    if (pc.kind != MGBX_PIECE_EP || pc.A != nullptr || pc.nc < 2 || pc.ni != pc.nc) continue;
+    const int nq = pc.nc - 1, js = pc.idx[nq];
+    if (js < 0 || js >= A.nD) continue;
+    const int ev = S.Erow[js];
+    if (ev < 0) continue;
+    bool ok = true;
+    for (int r = 0; r < nq; ++r) ok = ok && pc.idx[r] != js && S.Erow[pc.idx[r]] < 0;
+    for (int j = 0; j < A.nD; ++j) ok = ok && (j == js || S.Erow[j] != ev);          // the variable's only row
+    for (int k2 = 0; k2 < cd.npieces; ++k2)
+      if (k2 != k)
+        for (int c = 0; c < cd.pc[k2].ni; ++c) ok = ok && cd.pc[k2].idx[c] != js;     // no other piece reads it
+    if (ok) {
+      pieces |= 1u << k;
+      elim |= 1u << ev;
+    }
+  }
+}
+
 // Evaluate the node Hessians at zbase + R_J x and fill the system matrices from the top level down to
 // level index ktop (= L-1-J), then the preconditioner hierarchy below it.
 void Engine::assemble(Amg &A, System &S, int J, double t, const double *zbase, const double *x) {
@@ -1576,6 +1605,7 @@ void Engine::assemble(Amg &A, System &S, int J, double t, const double *zbase, c
   P.Hn = A.Hn;
   P.hEEinv = A.hEEinv;
   P.hKE = A.hKE;
+  schur_masks(A, S, P.schur_pieces, P.schur_elim);
   if (S.dense) {
     assemble_dense(A, S, P);
     stage_end(STAGE_F2, st);
@@ -2924,6 +2954,7 @@ void mgbx_default_config(mgbx_config *c) {
   c->shard_min_nnz = 4000000;
   c->spectral_kron = 1;
   c->uncondensed_pcg = 0;
+  c->analytic_schur = 1;
 }
 
 void mgbx_default_step_opts(mgbx_step_opts *o, int64_t n) {

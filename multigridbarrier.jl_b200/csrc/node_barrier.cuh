@@ -48,8 +48,13 @@ MGBX_HD double safe_pow(double s, double a) { return exp(a * Log(s)); }
 // The Hessian of the piece in its own coordinates z = A y[idx] + b is never stored: entry (r, s) is formed on
 // the fly from a handful of scalars (EP: 4 z_r z_s / rho^2 + 2 delta_rs / rho, the coupling column and the
 // slack corner; LINEAR: diag(1/z^2)), so the common identity-A case touches no local array beyond z and g.
+// schur: this piece's slack row is eliminated node-locally by the caller and nothing else touches that row -- the q-q block is then
+// returned ALREADY CONDENSED, (2/rho) I + (4/rho^2) (B / (A + B)) z z' with H_ss = A + B, A = (al s^(al-1) / rho)^2 (the square of
+// the coupling): algebraically H_qq - H_qs H_sq / H_ss, but without subtracting two terms of size ~t^2 whose difference is O(1)
+// along z (the subtraction leaves no correct digit there at t ~ 1e8).  The coupling column and H_ss are still returned for the
+// right-hand-side condensation and the back-substitution; the caller must skip this slack in its numerical Schur loop.
 MGBX_HD double piece_eval(const PieceDev &pc, int64_t n, int64_t i, const double *y, int ny, int order,
-                          bool cob, double slack, int slackpos, double *F1, double *F2) {
+                          bool cob, double slack, int slackpos, double *F1, double *F2, bool schur = false) {
   const int ni = pc.ni, nc = pc.nc;
   double z[MGBX_MAX_NC];
   double gz[MGBX_MAX_NC];
@@ -68,7 +73,7 @@ MGBX_HD double piece_eval(const PieceDev &pc, int64_t n, int64_t i, const double
   double f0;
   const bool ep = (pc.kind == MGBX_PIECE_EP);
   const int nq = nc - 1;
-  double inv_r = 0.0, inv_r2 = 0.0, coef = 0.0, hss = 0.0;
+  double inv_r = 0.0, inv_r2 = 0.0, coef = 0.0, hss = 0.0, qqs = 1.0;
   if (ep) {
     if (cob) z[nq] += slack;
     const double s = z[nq];
@@ -94,7 +99,9 @@ MGBX_HD double piece_eval(const PieceDev &pc, int64_t n, int64_t i, const double
         coef = -2.0 * al * sam1 * inv_r2;
         const double sam2 = in ? sam1 / s : safe_pow(s, al - 2.0);
         const double s2am2 = in ? sam1 * sam1 : safe_pow(s, 2.0 * al - 2.0);
-        hss = -al * (al - 1.0) * sam2 * inv_r + al * al * s2am2 * inv_r2 + mu / (s * s);
+        const double hA = al * al * s2am2 * inv_r2, hB = -al * (al - 1.0) * sam2 * inv_r + mu / (s * s);
+        hss = hA + hB;
+        if (schur) qqs = hB / hss;
       }
     }
   } else {
@@ -108,7 +115,7 @@ MGBX_HD double piece_eval(const PieceDev &pc, int64_t n, int64_t i, const double
   // Hessian entry (r, s) in piece coordinates
   auto hz = [&](int r, int s2) -> double {
     if (ep) {
-      if (r < nq && s2 < nq) return 4.0 * z[r] * z[s2] * inv_r2 + (r == s2 ? 2.0 * inv_r : 0.0);
+      if (r < nq && s2 < nq) return 4.0 * z[r] * z[s2] * inv_r2 * qqs + (r == s2 ? 2.0 * inv_r : 0.0);
       if (r == nq && s2 == nq) return hss;
       return coef * z[r < s2 ? r : s2];
     }
@@ -167,8 +174,9 @@ MGBX_HD double piece_eval(const PieceDev &pc, int64_t n, int64_t i, const double
 }
 
 // Sum of the selected pieces (+ the phase-I wrapper).  F1 / F2 are overwritten.
+// schur_mask: bit k set = piece k is condensed analytically (see piece_eval)
 MGBX_HD double node_eval(const ConvexDev &cd, int64_t n, int64_t i, const double *y, int order, double *F1,
-                         double *F2) {
+                         double *F2, unsigned schur_mask = 0u) {
   const int ny = cd.NF;
   if (order >= 1)
     for (int k = 0; k < ny; ++k) F1[k] = 0.0;
@@ -180,7 +188,7 @@ MGBX_HD double node_eval(const ConvexDev &cd, int64_t n, int64_t i, const double
   const double u = cob ? y[slackpos] : 0.0;
   for (int k = 0; k < cd.npieces; ++k) {
     if (cd.select && cd.select[i + (int64_t)k * n] == 0.0) continue;
-    F0 += piece_eval(cd.pc[k], n, i, y, ny, order, cob, u, slackpos, F1, F2);
+    F0 += piece_eval(cd.pc[k], n, i, y, ny, order, cob, u, slackpos, F1, F2, ((schur_mask >> k) & 1u) != 0u);
   }
   if (cob) {
     const double bb = cd.fb, RR = cd.fR;

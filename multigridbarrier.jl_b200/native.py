@@ -61,7 +61,7 @@ class Config(C.Structure):
                 ("fused", C.c_int32), ("smoother", C.c_int32), ("cheb_ratio", C.c_double),
                 ("precond_fp32", C.c_int32), ("pcg_lanes", C.c_int32), ("lambda_power", C.c_int32),
                 ("pcg_fail_rtol", C.c_double), ("pcg_fail_etol", C.c_double), ("pcg_stall_window", C.c_int32), ("direct_fallback", C.c_int32), ("elem_bulk", C.c_int32), ("shard_solve", C.c_int32),
-                ("shard_min_rows", C.c_int32), ("shard_min_nnz", C.c_int32), ("spectral_kron", C.c_int32), ("uncondensed_pcg", C.c_int32)]
+                ("shard_min_rows", C.c_int32), ("shard_min_nnz", C.c_int32), ("spectral_kron", C.c_int32), ("uncondensed_pcg", C.c_int32), ("analytic_schur", C.c_int32)]
 
 
 class StepOpts(C.Structure):

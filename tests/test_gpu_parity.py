@@ -359,7 +359,10 @@ def test_second_generation_persistent_kernel_matches_first(smoother, fp32):
         g = rng.normal(size=m)
         out = []
         for persistent in (1, 2):
-            h = native.Handle(prob, dense_direct_max=0, coarse_max=40, persistent=persistent, smoother=smoother, precond_fp32=fp32, pcg_rtol=1e-11, **kw)
+            # lambda_power = 0: both generations use the Gershgorin bound (the automatic power iteration of 3-D hierarchies is a
+            # host-launched loop in generation 1 and one cooperative launch in generation 2: same estimate, different rounding)
+            h = native.Handle(prob, dense_direct_max=0, coarse_max=40, persistent=persistent, smoother=smoother, precond_fp32=fp32, pcg_rtol=1e-11,
+                              lambda_power=0, **kw)
             try:
                 x, its = h.solve_newton_system(0, J, 2.0, s, g)
                 Hm = h.hessian(0, J, 2.0, s)
@@ -501,7 +504,7 @@ def test_bench_size_properties(big_problem):
     J = len(M.R_fine) - 1
     m = M.R_fine[J].shape[1]
     rng = np.random.default_rng(11)
-    h = native.Handle(prob)
+    h = native.Handle(prob, pcg_rtol=1e-10)      # the residual gate below is 1e-8 (the shipped default tolerance is 1e-7)
     try:
         s = 1e-3 * rng.normal(size=m)
         d = rng.normal(size=m)

@@ -120,3 +120,62 @@ def test_feasibility_wrapper(shim, kind):
     close(F0, o0)
     close(F1, o1)
     close(F2, o2)
+
+
+def test_analytic_schur_complement_of_the_cone_slack_keeps_its_digits(shim):
+    """Node-local condensation of the slack of ONE Euclidean-power cone late in the t-ramp (rho = s^alpha - |q|^2 ~ 1e-8): the
+    closed form (2/rho) I + (4/rho^2)(B/(A+B)) q q' that piece_eval returns for a `schur` piece against H_qq - H_qs H_sq / H_ss in
+    50-digit arithmetic -- and the same difference formed in double precision, which has no correct digit along q."""
+    import mpmath as mp
+    mp.mp.dps = 50
+    shim.hostcheck_node_eval_schur.argtypes = [C.POINTER(native.Convex), C.c_int64, C.c_int, native.c_f64p, native.c_f64p, native.c_f64p,
+                                               native.c_f64p, C.c_uint, C.c_int]
+    rng = np.random.default_rng(3)
+    n = 6
+    for p, al in ((1.0, 2.0), (1.5, 4.0 / 3.0)):
+        mu = 0.0 if p == 1.0 else 1.0
+        s = 0.5 + rng.random(n)
+        d = rng.normal(size=(n, 2))
+        d /= np.linalg.norm(d, axis=1)[:, None]
+        rho = np.array([1e-3, 1e-5, 1e-6, 1e-7, 1e-8, 3e-9])
+        qn = np.sqrt(s ** al - rho)
+        Y = np.column_stack([d * qn[:, None], s])                         # inputs (q1, q2, s)
+        Q = ep(n, (0, 1, 2), np.full(n, p), rng)
+        keep = native._Keep()
+        Qc = native._pack_convex(keep, Q, n)
+        Yc = np.ascontiguousarray(Y.T)
+        out = {}
+        for mask in (0, 1):
+            F0, F1, F2 = np.empty(n), np.empty((3, n)), np.empty((9, n))
+            shim.hostcheck_node_eval_schur(C.byref(Qc), n, 3, native._ptr(Yc), native._ptr(F0), native._ptr(F1), native._ptr(F2), mask, 1)
+            out[mask] = F2.T.reshape(n, 3, 3)
+        for i in range(n):
+            q = [mp.mpf(float(Y[i, 0])), mp.mpf(float(Y[i, 1]))]
+            si = mp.mpf(float(Y[i, 2]))
+            a = mp.mpf(2) / mp.mpf(p)
+            r = si ** a - q[0] ** 2 - q[1] ** 2
+            hss = -a * (a - 1) * si ** (a - 2) / r + a * a * si ** (2 * a - 2) / r ** 2 + mp.mpf(mu) / si ** 2
+            hqs = [-2 * a * si ** (a - 1) * qq / r ** 2 for qq in q]
+            S = [[4 * q[x] * q[y] / r ** 2 + (2 / r if x == y else 0) - hqs[x] * hqs[y] / hss for y in range(2)] for x in range(2)]
+            scale = float(2 / r)
+            H0, H1 = out[0][i], out[1][i]
+            # coupling column and slack corner are the same in both modes (needed for the back-substitution)
+            assert np.array_equal(H0[2, :], H1[2, :]) and np.array_equal(H0[:, 2], H1[:, 2])
+            naive = H0[:2, :2] - np.outer(H0[:2, 2], H0[2, :2]) / H0[2, 2]
+            err_an = max(abs(float(S[x][y]) - H1[x, y]) for x in range(2) for y in range(2)) / scale
+            err_nv = max(abs(float(S[x][y]) - naive[x, y]) for x in range(2) for y in range(2)) / scale
+            # component along q (the small eigenvalue of the condensed block): true value, analytic, naive
+            u = np.array([float(q[0]), float(q[1])])
+            u /= np.linalg.norm(u)
+            lam = float(sum(S[x][y] * mp.mpf(u[x]) * mp.mpf(u[y]) for x in range(2) for y in range(2)))
+            lam_an, lam_nv = float(u @ H1[:2, :2] @ u), float(u @ naive @ u)
+            # rho itself is a difference of the inputs (as in the reference): its rounding, eps s^alpha / rho, is the floor for
+            # both forms.  Across q both forms reach it; ALONG q the closed form stays at that floor RELATIVE TO THE O(1) ENTRY
+            # while the subtraction carries an absolute error ~ eps (2/rho)^2 -- no digit left once rho <= 1e-8.
+            floor = 32 * np.finfo(float).eps * float(si ** a / r)
+            assert err_an < floor + 1e-14, (p, float(r), err_an, floor)
+            assert abs(lam_an - lam) <= (floor + 1e-13) * abs(lam), (p, float(r), lam, lam_an)
+            print("p=%g rho=%.0e  lambda_along_q: exact %.6g analytic %.6g (rel err %.1e)  subtraction %.6g (rel err %.1e)"
+                  % (p, float(r), lam, lam_an, abs(lam_an - lam) / abs(lam), lam_nv, abs(lam_nv - lam) / abs(lam)))
+            if p == 1.0 and float(r) <= 1e-7:     # alpha = 2 (p = 1: total variation, fem3d p = 1): the entry along q is O(1)
+                assert abs(lam_nv - lam) > 0.05 * abs(lam) and abs(lam_an - lam) < 1e-6 * abs(lam), (float(r), lam, lam_an, lam_nv, err_nv)
