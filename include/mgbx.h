@@ -19,7 +19,7 @@
  *   mgbx_get_z_unfinalized  <- SOL.z_unfinalized                      src/mgb.jl:76-80
  *   mgbx_destroy       <- mgb_cleanup                                 src/mgb.jl:840
  *   mgbx_barrier_eval, mgbx_hessian_pattern, mgbx_hessian_values, mgbx_solve_newton_system,
- *   mgbx_plan_pattern, mgbx_recover_transfer, mgbx_shard_row_range  <- fine-grained parity hooks for barrier(Q).f0/f1/f2 (src/convex.jl:155-202),
+ *   mgbx_plan_pattern, mgbx_recover_transfer, mgbx_kron_factor, mgbx_shard_row_range  <- fine-grained parity hooks for barrier(Q).f0/f1/f2 (src/convex.jl:155-202),
  *                         _make_block_assembly_plan (src/BlockMatrices.jl:322-491) and solve (src/utils.jl:142-145)
  *
  * Conventions
@@ -321,6 +321,12 @@ int mgbx_plan_pattern(const mgbx_csr *R, int64_t N, int32_t p, int32_t nu, int32
  * mgbx_amg.T == NULL.  val / rowptr / colind may be NULL to query nnz (rowptr holds R_next->cols + 1 entries). */
 int mgbx_recover_transfer(const mgbx_csr *R_next, const mgbx_csr *R_cur, int64_t *nnz, int64_t *rowptr, int64_t *colind,
                           double *val);
+
+/* host-only (no GPU needed): is the dense (r1 r2) x (c1 c2) matrix M a Kronecker product kron(A, B) of an r1 x c1 and an r2 x c2 factor
+ * (row-major outputs; the scale is fixed by taking B as the block through M's largest entry)?  This is the test mgbx_create applies to
+ * the dense operators and prolongations of a spectral discretisation (:dx = kron(DX, I), R = kron(R1, R1), src/spectral2d.jl:22-35)
+ * before it assembles R'HR sum-factorised (cfg.spectral_kron).  *is_kron = 0: A and B are left untouched. */
+int mgbx_kron_factor(const double *M, int32_t r1, int32_t r2, int32_t c1, int32_t c2, int32_t col_major, double *A, double *B, int32_t *is_kron);
 
 /* host-only (no GPU needed): rows [row_begin, row_end) of a V-cycle level that `rank` owns in the row-sharded multi-GPU solve
  * (cfg.shard_solve; csrc/pcg2.hpp pcg2_rank_rows -- the same arithmetic the persistent kernel's plan uses): the level's sliced-ELL

@@ -3551,6 +3551,21 @@ int mgbx_recover_transfer(const mgbx_csr *R_next, const mgbx_csr *R_cur, int64_t
   });
 }
 
+int mgbx_kron_factor(const double *M, int32_t r1, int32_t r2, int32_t c1, int32_t c2, int32_t col_major, double *A, double *B, int32_t *is_kron) {
+  if (!M || !A || !B || !is_kron || r1 < 1 || r2 < 1 || c1 < 1 || c2 < 1) return MGBX_ERR_ARG;
+  return guarded(nullptr, [&]() -> int {
+    const int64_t rows = (int64_t)r1 * r2, cols = (int64_t)c1 * c2;
+    std::vector<double> a, b;
+    const bool ok = kron_factor([&](int64_t r, int64_t c) { return col_major ? M[r + c * rows] : M[r * cols + c]; }, r1, r2, c1, c2, a, b);
+    *is_kron = ok ? 1 : 0;
+    if (ok) {
+      std::copy(a.begin(), a.end(), A);
+      std::copy(b.begin(), b.end(), B);
+    }
+    return MGBX_OK;
+  });
+}
+
 int mgbx_shard_row_range(int64_t rows, int32_t lanes_per_row, int32_t ctas_per_rank, int32_t nranks, int32_t rank, int64_t *row_begin,
                          int64_t *row_end) {
   if (!row_begin || !row_end || rows < 0 || ctas_per_rank < 1 || nranks < 1 || rank < 0 || rank >= nranks) return MGBX_ERR_ARG;

@@ -99,7 +99,7 @@ EXPORTS = [
     "mgbx_phase1_init", "mgbx_attach_feasibility", "mgbx_set_feasibility_box", "mgbx_reset_feasibility_state", "mgbx_handoff",
     "mgbx_matched_t", "mgbx_get_z", "mgbx_get_z_unfinalized", "mgbx_set_z", "mgbx_set_grids", "mgbx_level_size",
     "mgbx_barrier_eval", "mgbx_hessian_pattern", "mgbx_hessian_values", "mgbx_solve_newton_system",
-    "mgbx_plan_pattern", "mgbx_recover_transfer", "mgbx_shard_row_range", "mgbx_launch_count", "mgbx_memory_report", "mgbx_kernel_stats", "mgbx_set_profile", "mgbx_solver_info",
+    "mgbx_plan_pattern", "mgbx_recover_transfer", "mgbx_kron_factor", "mgbx_shard_row_range", "mgbx_launch_count", "mgbx_memory_report", "mgbx_kernel_stats", "mgbx_set_profile", "mgbx_solver_info",
 ]
 
 _lib = None
@@ -154,6 +154,7 @@ def lib():
     L.mgbx_solve_newton_system.argtypes = [H, C.c_int, C.c_int, C.c_double, c_f64p, c_f64p, c_f64p, c_i32p]
     L.mgbx_plan_pattern.argtypes = [C.POINTER(Csr), C.c_int64, C.c_int32, C.c_int32, C.c_int32, c_i32p,
                                     c_i64p, c_i64p, c_i64p]
+    L.mgbx_kron_factor.argtypes = [c_f64p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_f64p, c_f64p, C.POINTER(C.c_int32)]
     L.mgbx_shard_row_range.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_i64p, c_i64p]
     L.mgbx_recover_transfer.argtypes = [C.POINTER(Csr), C.POINTER(Csr), c_i64p, c_i64p, c_i64p, c_f64p]
     L.mgbx_memory_report.argtypes = [H, C.c_char_p, C.c_int64, c_i64p]
@@ -500,6 +501,19 @@ def plan_pattern(R, N, p, nu, D_var):
     if rc != OK:
         raise MgbxError(rc, (lib().mgbx_last_error(None) or b"").decode())
     return ptr, ind
+
+
+def kron_factor(M, r1, r2, c1, c2):
+    """Host-only: (A, B) with M == kron(A, B) (A r1 x c1, B r2 x c2) or None -- the structure test behind the sum-factorised spectral
+    assembly (csrc/mgbx.cu kron_factor)."""
+    M = np.ascontiguousarray(M, dtype=np.float64)
+    assert M.shape == (r1 * r2, c1 * c2)
+    A, B = np.zeros((r1, c1)), np.zeros((r2, c2))
+    ok = C.c_int32(0)
+    rc = lib().mgbx_kron_factor(_ptr(M), r1, r2, c1, c2, 0, _ptr(A), _ptr(B), C.byref(ok))
+    if rc != OK:
+        raise MgbxError(rc, (lib().mgbx_last_error(None) or b"").decode())
+    return (A, B) if ok.value else None
 
 
 def shard_row_range(rows, lanes_per_row, ctas_per_rank, nranks, rank):

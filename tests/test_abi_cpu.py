@@ -123,3 +123,70 @@ def test_ctypes_layouts_match_the_c_header(tmp_path):
         assert int(out[cname]) == C.sizeof(ct), cname
         for fname, _ in ct._fields_:
             assert int(out["%s.%s" % (cname, fname)]) == getattr(ct, fname).offset, (cname, fname)
+
+
+def test_kronecker_structure_of_the_spectral2d_operators_and_prolongations():
+    """mgbx_kron_factor (host-only): the test mgbx_create applies before assembling R'HR sum-factorised.  spectral2d's operators are
+    kron(DX, I), kron(I, DX), kron(I, I) and its prolongations kron(R1, R1) (src/spectral2d.jl:22-35): every one must be recognised
+    and reproduced to 1e-12; spectral1d's dense matrices and a perturbed product must be rejected; and the sum-factorised formula for
+    one block of R'HR must equal the unstructured product (NumPy emulation of dense_kernels.cuh k_kron_w + GEMM + k_kron_scatter)."""
+    from mgbx import geometry as G, hierarchy as H
+    n1 = 7
+    g = G.spectral2d(n=n1)
+    mg = H.amg(g)
+    facs = {}
+    for name in ("id", "dx", "dy"):
+        D = np.asarray(g.operators[name][0])
+        out = native.kron_factor(D, n1, n1, n1, n1)
+        assert out is not None, name
+        assert np.abs(np.kron(out[0], out[1]) - D).max() <= 1e-12 * np.abs(D).max()
+        facs[name] = out
+    Rf = {}
+    for X in ("dirichlet", "full"):
+        for R in mg.R[X]:
+            R = np.asarray(R)
+            c = int(round(np.sqrt(R.shape[1])))
+            if c == 0 or c * c != R.shape[1]:
+                continue
+            out = native.kron_factor(R, n1, n1, c, c)
+            assert out is not None, (X, R.shape)
+            assert np.abs(np.kron(out[0], out[1]) - R).max() <= 1e-12 * np.abs(R).max()
+            Rf[X] = (R, out)
+    rng = np.random.default_rng(0)
+    bad = np.kron(rng.normal(size=(3, 2)), rng.normal(size=(4, 5)))
+    assert native.kron_factor(bad, 3, 4, 2, 5) is not None
+    bad[5, 7] += 1e-6
+    assert native.kron_factor(bad, 3, 4, 2, 5) is None
+    g1 = G.spectral1d(n=16)
+    assert native.kron_factor(np.asarray(g1.operators["dx"][0]), 4, 4, 4, 4) is None
+    assert native.kron_factor(np.zeros((4, 4)), 2, 2, 2, 2) is None
+    # one block of R'HR: sum over (j, k) in {id, dx, dy}^2 of (D_j R)' diag(h_jk) (D_k R), unstructured vs sum-factorised
+    R, (Ra, Rb) = Rf["dirichlet"]
+    c = Ra.shape[1]
+    ops = ["id", "dx", "dy"]
+    h = {(j, k): rng.normal(size=n1 * n1) for j in range(3) for k in range(j, 3)}
+    ref = np.zeros((c * c, c * c))
+    for j in range(3):
+        for k in range(3):
+            hv = h[(min(j, k), max(j, k))]
+            Dj, Dk = np.asarray(g.operators[ops[j]][0]), np.asarray(g.operators[ops[k]][0])
+            ref += (Dj @ R).T @ (hv[:, None] * (Dk @ R))
+    P = [facs[o][0] @ Ra for o in ops]          # n1 x c  (slow index)
+    Q = [facs[o][1] @ Rb for o in ops]          # n1 x c  (fast index)
+    # scale ambiguity of the factor pairs cancels in P (x) Q only if both come from the same factorisation: check that first
+    for o, (A, B) in facs.items():
+        assert np.abs(np.kron(A @ Ra, B @ Rb) - np.asarray(g.operators[o][0]) @ R).max() <= 1e-11
+    K = 9 * n1
+    AA = np.zeros((c * c, K))
+    W = np.zeros((c * c, K))
+    col = 0
+    for j in range(3):
+        for k in range(3):
+            hv = h[(min(j, k), max(j, k))].reshape(n1, n1)          # node q = e * n1 + f
+            for e in range(n1):
+                AA[:, col * n1 + e] = np.outer(P[j][e], P[k][e]).reshape(-1)                      # [(i, l)]
+                W[:, col * n1 + e] = (Q[j].T @ (hv[e][:, None] * Q[k])).reshape(-1)              # [(i', l')]
+            col += 1
+    Cm = AA @ W.T                                                    # [(i, l), (i', l')]
+    out = Cm.reshape(c, c, c, c).transpose(0, 2, 1, 3).reshape(c * c, c * c)   # -> [(i, i'), (l, l')]
+    assert np.abs(out - ref).max() <= 1e-10 * np.abs(ref).max()
