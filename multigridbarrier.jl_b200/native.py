@@ -191,6 +191,9 @@ class _Keep:
         a = np.asarray(a, dtype=np.float64)
         if a.ndim == 1:
             return self.f64(a)
+        if a.flags.f_contiguous:      # already in the reference's own (Julia: column-major) layout -- no copy
+            self.bufs.append(a)
+            return _ptr(a)
         # cache-blocked transpose: about twice as fast as ascontiguousarray(a.T) on the 1.5 M-row grids of the bench
         n, k = a.shape
         b = np.empty((k, n), dtype=np.float64)
@@ -221,9 +224,15 @@ def _pack_amg(keep: _Keep, M, recover_transfers=False) -> Amg:
     geom = M.geometry
     n, N, p = geom.n, geom.N, geom.V
     names, D_var, D_op = [], [], []
+    # per geometry, computed once: which operators are the identity, and the operator blocks in the boundary's layout -- the
+    # reference's BlockDiag.data is p x p x N column-major already (src/BlockMatrices.jl:17-44), so its shim passes it as it is
+    cache = geom.__dict__.setdefault("_mgbx_abi_cache", {"ident": {}, "ops": {}})
     for (var, op) in M.D:
-        blocks = geom.operators[op]
-        ident = bool(np.array_equal(blocks, np.broadcast_to(np.eye(p), blocks.shape)))
+        if op not in cache["ident"]:
+            blocks = geom.operators[op]
+            eye = np.eye(p)
+            cache["ident"][op] = bool(np.array_equal(blocks[0], eye) and np.array_equal(blocks, np.broadcast_to(eye, blocks.shape)))
+        ident = cache["ident"][op]
         if ident:
             oid = -1
         else:
@@ -235,7 +244,9 @@ def _pack_amg(keep: _Keep, M, recover_transfers=False) -> Amg:
     ops = (c_f64p * max(1, len(names)))()
     for k, nm in enumerate(names):
         # numpy ops[e, r, c]  ->  BlockDiag.data[r, c, e] column-major == memory order [e][c][r]
-        ops[k] = keep.f64(np.ascontiguousarray(geom.operators[nm].transpose(0, 2, 1)))
+        if nm not in cache["ops"]:
+            cache["ops"][nm] = np.ascontiguousarray(geom.operators[nm].transpose(0, 2, 1), dtype=np.float64)
+        ops[k] = keep.f64(cache["ops"][nm])
     keep.bufs.append(ops)
     L = len(M.R_fine)
     # only R_fine[L-1] crosses the boundary with data: the library composes the coarser ones from T (mgbx.h)

@@ -98,7 +98,7 @@ def convex_Euclidian_power(mg: MultiGrid, idx=None, A=None, b=None, p=None,
                 raise ValueError("a default A with idx = Colon() cannot determine the constraint "
                                  "dimension; pass an explicit idx, or a matrix-valued A.")
             nz = len(idx)
-            A_grid = np.tile(np.eye(nz).reshape(-1, order="F"), (n, 1))
+            A_grid = np.asfortranarray(np.tile(np.eye(nz).reshape(-1, order="F"), (n, 1)))   # column-major like the reference's grids
         else:
             A_grid = map_rows(lambda xi: np.asarray(A(xi), float).reshape(-1, order="F"), x)
     nz = len(idx) if idx is not None else int(round(np.sqrt(A_grid.shape[1])))
@@ -106,7 +106,7 @@ def convex_Euclidian_power(mg: MultiGrid, idx=None, A=None, b=None, p=None,
         raise ValueError("A_grid has %d columns per node; expected nz^2 = %d" % (A_grid.shape[1], nz * nz))
     if b_grid is None:
         if b is None:
-            b_grid = np.zeros((n, nz))
+            b_grid = np.zeros((n, nz), order="F")
         else:
             def bf(xi):
                 bx = b(xi)
@@ -268,4 +268,5 @@ def assemble(mg: MultiGrid, dim=None, state_variables=None, D=None, x=None, p=1.
     if M is None:
         M = prepare_amg(mg, state_variables, D)
     Q.validate(M[0].nD)
-    return MGBProblem(M, np.asarray(f_grid, float), np.asarray(g_grid, float), Q, geom)
+    # grids are kept column-major, the layout the reference's (Julia) arrays have and the C ABI takes -- no conversion at the boundary
+    return MGBProblem(M, np.asfortranarray(f_grid, dtype=float), np.asfortranarray(g_grid, dtype=float), Q, geom)
