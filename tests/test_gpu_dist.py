@@ -1,5 +1,5 @@
 """Multi-GPU parity (needs >= 2 GPUs on the box; skipped otherwise): the element-partitioned solve over 2 ranks
-(NCCL all-reduces inside libmgbx) against the single-GPU solve of the same problem -- z 1e-6 rel L2, objective 1e-8,
+(NCCL all-reduces inside libmgbx; with FORCE_SHARD also the row-sharded persistent solve kernel) against the single-GPU solve of the same problem -- z 1e-6 rel L2, objective 1e-8,
 same t-schedule, Newton counts +-1 (tools/dist_check.py asserts exactly that and prints DIST OK)."""
 import os
 import subprocess
@@ -19,12 +19,19 @@ def _ngpu():
         return 0
 
 
-@pytest.mark.parametrize("case,port", [("p1L6", 29541), ("q1c8", 29542)])
-def test_two_rank_solve_matches_single_gpu(case, port):
+FORCE_SHARD = ["shard_min_rows=100", "shard_min_nnz=0", "dense_direct_max=64", "coarse_max=64"]
+
+
+@pytest.mark.parametrize("case,port,extra", [("p1L6", 29541, []), ("q1c8", 29542, []),
+                                             ("p1L6", 29543, FORCE_SHARD), ("q1c8", 29544, FORCE_SHARD)])
+def test_two_rank_solve_matches_single_gpu(case, port, extra):
+    """extra = FORCE_SHARD: the V-cycle levels are row-sharded over the two ranks inside the persistent kernel even on these small
+    problems (peer stores into the CUDA-IPC exchange arenas, cross-GPU barrier); by default levels this small stay replicated.
+    Recorded runs: profiles/r02f_dist_check_2gpu.txt (2 GPUs), profiles/r02i_dist_check_4gpu_forced_sharding.txt (4 GPUs)."""
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", str(port), os.path.join(ROOT, "tools", "dist_check.py"), case]
+           "--master-port", str(port), os.path.join(ROOT, "tools", "dist_check.py"), case] + extra
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "DIST OK" in r.stdout
