@@ -186,3 +186,70 @@ def test_barrier_weights_follow_the_reference_rules():
         solver.barrier_weights(w, np.array([], dtype=int))
     with pytest.raises(ValueError):
         solver.barrier_weights(w, np.array([True, False]))
+
+
+def test_fixture_schedule_gate_accepts_only_the_documented_deviations():
+    """tests/test_gpu_fixtures.py::compare_schedules is the gate the GPU runs are held to against the oracle fixtures.  It must pass
+    identical and +-1 schedules, the two documented deviations (a fork explained by the kappa-growth threshold; a kappa refinement in
+    the LAST barrier step), and reject everything else -- checked here on synthetic schedules, no GPU needed."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("gpu_fixtures_gate", os.path.join(os.path.dirname(__file__), "test_gpu_fixtures.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    gate = mod.compare_schedules
+    ts = np.array([0.1, 1.0, 10.0, 100.0, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8])
+    its = np.zeros((3, len(ts)), dtype=np.int64)
+    its[2] = [12, 7, 6, 6, 6, 5, 5, 5, 5, 7]          # fine level; last step includes a finalize pass of 2
+    its[0, 0], its[1, 0] = 8, 8
+    fin = 2
+    assert gate(ts, its, fin, ts, its, fin)["schedule"] == "identical"
+    a = its.copy()
+    a[2, 3] += 1
+    assert gate(ts, a, fin, ts, its, fin)["schedule"] == "identical"                      # +-1 on a barrier step
+    a[2, 3] += 1
+    with pytest.raises(AssertionError):
+        gate(ts, a, fin, ts, its, fin)                                                        # +2 is not
+    a = its.copy()
+    a[2, -1] += 5                                                                             # finalize pass longer: excluded ...
+    assert gate(ts, a, fin + 5, ts, its, fin)["schedule"] == "identical"
+    with pytest.raises(AssertionError):
+        gate(ts, a, fin + 20, ts, its, fin)                                                   # ... but held to its halving tail
+    # a crawl of 1 361 iterations may differ by 0.5 %
+    c = its.copy()
+    c[1, 0] = 1361
+    d = c.copy()
+    d[1, 0] = 1359
+    assert gate(ts, d, fin, ts, c, fin)["schedule"] == "identical"
+    d[1, 0] = 1340
+    with pytest.raises(AssertionError):
+        gate(ts, d, fin, ts, c, fin)
+    # (1) fork explained by the kappa threshold: 4 vs 5 Newton iterations at step 5 -> the next t differs
+    o = its.copy()
+    o[2, 5] = 4
+    to = np.array([0.1, 1.0, 10.0, 100.0, 1e3, 1e4, 1e5 * 3.1622776601683795, 1e6 * 3.1622776601683795, 1e7 * 3.1622776601683795, 1e8 * 3.1622776601683795])
+    g = its.copy()
+    g[2, 5] = 5
+    assert gate(ts, g, fin, to, o, fin)["schedule"].startswith("forked at step 5")
+    g[2, 5] = 6                                                                               # 4 vs 6: not explained
+    with pytest.raises(AssertionError):
+        gate(ts, g, fin, to, o, fin)
+    g[2, 5] = 5
+    g[2, 2] += 2                                                                              # an earlier step off by 2: rejected even with the fork
+    with pytest.raises(AssertionError):
+        gate(ts, g, fin, to, o, fin)
+    # (2) the last barrier step: one side refined kappa (more than max_newton iterations on a level, different final t)
+    r = its.copy()
+    r[2, -1] = 9 + 6 + fin
+    tr = ts.copy()
+    tr[-1] = 7e7                                                                              # kappa halved once more in the last step
+    out = gate(tr, r, fin, ts, its, fin)
+    assert out["schedule"].startswith("identical up to the last barrier step")
+    tr2 = ts.copy()
+    tr2[-1] = 1.5e8                                                                           # different final t WITHOUT a refinement: rejected
+    with pytest.raises(AssertionError):
+        gate(tr2, its, fin, ts, its, fin)
+    tr3 = tr.copy()
+    tr3[-1] = 5e7                                                                             # final t below 1/tol: rejected
+    with pytest.raises(AssertionError):
+        gate(tr3, r, fin, ts, its, fin)
