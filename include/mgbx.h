@@ -322,6 +322,18 @@ int mgbx_plan_pattern(const mgbx_csr *R, int64_t N, int32_t p, int32_t nu, int32
 int mgbx_recover_transfer(const mgbx_csr *R_next, const mgbx_csr *R_cur, int64_t *nnz, int64_t *rowptr, int64_t *colind,
                           double *val);
 
+/* host-only (no GPU needed): classical Ruge-Stueben hierarchy of a sparse symmetric matrix K -- the prolongations P_0 (finest) ...
+ * P_{levels-1} the reference obtains from the un-vendored AlgebraicMultigrid.jl, `ruge_stuben(K; max_coarse=2).levels[i].P`
+ * (src/amg_prolongators.jl:16-18): classical strength (theta, default 0.25), first-pass RS C/F splitting, direct interpolation,
+ * Galerkin P'KP, at most max_levels levels (10), coarsening stops at max_coarse unknowns.  csrc/host_amg.hpp; bitwise equal to the
+ * Python host mirror's hierarchy.ruge_stuben (tests/test_abi_cpu.py).  mgbx_rs_get with NULL arrays queries the sizes. */
+typedef struct mgbx_rs_hierarchy mgbx_rs_hierarchy;
+int mgbx_rs_create(const mgbx_csr *K, int32_t max_coarse, int32_t max_levels, double theta, mgbx_rs_hierarchy **out);
+int32_t mgbx_rs_levels(const mgbx_rs_hierarchy *H);
+int mgbx_rs_get(const mgbx_rs_hierarchy *H, int32_t level, int64_t *rows, int64_t *cols, int64_t *nnz, int64_t *rowptr, int64_t *colind,
+                double *val);
+void mgbx_rs_destroy(mgbx_rs_hierarchy *H);
+
 /* host-only (no GPU needed): is the dense (r1 r2) x (c1 c2) matrix M a Kronecker product kron(A, B) of an r1 x c1 and an r2 x c2 factor
  * (row-major outputs; the scale is fixed by taking B as the block through M's largest entry)?  This is the test mgbx_create applies to
  * the dense operators and prolongations of a spectral discretisation (:dx = kron(DX, I), R = kron(R1, R1), src/spectral2d.jl:22-35)

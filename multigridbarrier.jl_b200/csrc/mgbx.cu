@@ -30,6 +30,7 @@
 #include "setup_kernels.cuh"
 #include "dense_kernels.cuh"
 #include "pcg2.hpp"
+#include "host_amg.hpp"
 
 using namespace mgbx;
 
@@ -3550,6 +3551,46 @@ int mgbx_recover_transfer(const mgbx_csr *R_next, const mgbx_csr *R_cur, int64_t
     return MGBX_OK;
   });
 }
+
+// ---- classical Ruge-Stueben hierarchy on the host (csrc/host_amg.hpp)
+struct mgbx_rs_hierarchy {
+  std::vector<mgbx::AmgCsr> P;
+};
+
+int mgbx_rs_create(const mgbx_csr *K, int32_t max_coarse, int32_t max_levels, double theta, mgbx_rs_hierarchy **out) {
+  if (!K || !out || !K->rowptr || K->rows != K->cols || K->rows < 0 || max_levels < 1 || max_coarse < 0) return MGBX_ERR_ARG;
+  return guarded(nullptr, [&]() -> int {
+    AmgCsr A;
+    A.rows = K->rows;
+    A.cols = K->cols;
+    A.ptr.assign(K->rowptr, K->rowptr + K->rows + 1);
+    const int64_t nz = A.ptr.back();
+    A.idx.assign(K->colind, K->colind + nz);
+    A.val.assign(K->val, K->val + nz);
+    for (int64_t k = 0; k < nz; ++k)
+      if (A.idx[k] < 0 || A.idx[k] >= A.cols) throw ArgError("mgbx_rs_create: column index out of range");
+    auto H = std::make_unique<mgbx_rs_hierarchy>();
+    H->P = amg_ruge_stuben(std::move(A), max_coarse, max_levels, theta);
+    *out = H.release();
+    return MGBX_OK;
+  });
+}
+
+int32_t mgbx_rs_levels(const mgbx_rs_hierarchy *H) { return H ? (int32_t)H->P.size() : -1; }
+
+int mgbx_rs_get(const mgbx_rs_hierarchy *H, int32_t level, int64_t *rows, int64_t *cols, int64_t *nnz, int64_t *rowptr, int64_t *colind, double *val) {
+  if (!H || level < 0 || level >= (int32_t)H->P.size() || !rows || !cols || !nnz) return MGBX_ERR_ARG;
+  const mgbx::AmgCsr &P = H->P[(size_t)level];
+  *rows = P.rows;
+  *cols = P.cols;
+  *nnz = (int64_t)P.idx.size();
+  if (rowptr) std::copy(P.ptr.begin(), P.ptr.end(), rowptr);
+  if (colind) std::copy(P.idx.begin(), P.idx.end(), colind);
+  if (val) std::copy(P.val.begin(), P.val.end(), val);
+  return MGBX_OK;
+}
+
+void mgbx_rs_destroy(mgbx_rs_hierarchy *H) { delete H; }
 
 int mgbx_kron_factor(const double *M, int32_t r1, int32_t r2, int32_t c1, int32_t c2, int32_t col_major, double *A, double *B, int32_t *is_kron) {
   if (!M || !A || !B || !is_kron || r1 < 1 || r2 < 1 || c1 < 1 || c2 < 1) return MGBX_ERR_ARG;

@@ -36,7 +36,7 @@ except Exception:                       # pragma: no cover
     numba = None
     _njit = lambda f: f
 
-__all__ = ["MultiGrid", "AMG", "amg", "prepare_amg", "ruge_stuben", "amg_ruge_stuben"]
+__all__ = ["MultiGrid", "AMG", "amg", "prepare_amg", "ruge_stuben", "amg_ruge_stuben", "amg_ruge_stuben_native"]
 
 
 # --------------------------------------------------------------------------
@@ -240,6 +240,17 @@ def amg_ruge_stuben(**kw):
     """Prolongator factory (amg_prolongators.jl:16-18)."""
     kw.setdefault("max_coarse", 2)
     return lambda K: ruge_stuben(K, **kw)
+
+
+def amg_ruge_stuben_native(**kw):
+    """The same factory on the C++ implementation inside libmgbx (csrc/host_amg.hpp, mgbx_rs_*): bitwise the same prolongations
+    (tests/test_abi_cpu.py), without numba."""
+    kw.setdefault("max_coarse", 2)
+
+    def f(K):
+        from . import native
+        return native.ruge_stuben(K, **kw)
+    return f
 
 
 # --------------------------------------------------------------------------

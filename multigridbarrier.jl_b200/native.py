@@ -99,7 +99,8 @@ EXPORTS = [
     "mgbx_phase1_init", "mgbx_attach_feasibility", "mgbx_set_feasibility_box", "mgbx_reset_feasibility_state", "mgbx_handoff",
     "mgbx_matched_t", "mgbx_get_z", "mgbx_get_z_unfinalized", "mgbx_set_z", "mgbx_set_grids", "mgbx_level_size",
     "mgbx_barrier_eval", "mgbx_hessian_pattern", "mgbx_hessian_values", "mgbx_solve_newton_system",
-    "mgbx_plan_pattern", "mgbx_recover_transfer", "mgbx_kron_factor", "mgbx_shard_row_range", "mgbx_launch_count", "mgbx_memory_report", "mgbx_kernel_stats", "mgbx_set_profile", "mgbx_solver_info",
+    "mgbx_plan_pattern", "mgbx_recover_transfer", "mgbx_kron_factor", "mgbx_shard_row_range",
+    "mgbx_rs_create", "mgbx_rs_levels", "mgbx_rs_get", "mgbx_rs_destroy", "mgbx_launch_count", "mgbx_memory_report", "mgbx_kernel_stats", "mgbx_set_profile", "mgbx_solver_info",
 ]
 
 _lib = None
@@ -154,6 +155,12 @@ def lib():
     L.mgbx_solve_newton_system.argtypes = [H, C.c_int, C.c_int, C.c_double, c_f64p, c_f64p, c_f64p, c_i32p]
     L.mgbx_plan_pattern.argtypes = [C.POINTER(Csr), C.c_int64, C.c_int32, C.c_int32, C.c_int32, c_i32p,
                                     c_i64p, c_i64p, c_i64p]
+    L.mgbx_rs_create.argtypes = [C.POINTER(Csr), C.c_int32, C.c_int32, C.c_double, C.POINTER(C.c_void_p)]
+    L.mgbx_rs_levels.argtypes = [C.c_void_p]
+    L.mgbx_rs_levels.restype = C.c_int32
+    L.mgbx_rs_get.argtypes = [C.c_void_p, C.c_int32, c_i64p, c_i64p, c_i64p, c_i64p, c_i64p, c_f64p]
+    L.mgbx_rs_destroy.argtypes = [C.c_void_p]
+    L.mgbx_rs_destroy.restype = None
     L.mgbx_kron_factor.argtypes = [c_f64p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_f64p, c_f64p, C.POINTER(C.c_int32)]
     L.mgbx_shard_row_range.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_i64p, c_i64p]
     L.mgbx_recover_transfer.argtypes = [C.POINTER(Csr), C.POINTER(Csr), c_i64p, c_i64p, c_i64p, c_f64p]
@@ -512,6 +519,30 @@ def plan_pattern(R, N, p, nu, D_var):
     if rc != OK:
         raise MgbxError(rc, (lib().mgbx_last_error(None) or b"").decode())
     return ptr, ind
+
+
+def ruge_stuben(K, max_coarse=2, max_levels=10, theta=0.25):
+    """Host-only: prolongations finest -> coarsest of the classical Ruge-Stueben hierarchy of K (csrc/host_amg.hpp) -- the C++ twin of
+    hierarchy.ruge_stuben, bitwise equal to it (src/amg_prolongators.jl:16-18 is the reference's call site)."""
+    keep = _Keep()
+    Kc = keep.csr(sp.csr_matrix(K, dtype=np.float64))
+    h = C.c_void_p()
+    rc = lib().mgbx_rs_create(C.byref(Kc), int(max_coarse), int(max_levels), float(theta), C.byref(h))
+    if rc != OK:
+        raise MgbxError(rc, (lib().mgbx_last_error(None) or b"").decode())
+    try:
+        Ps = []
+        for l in range(lib().mgbx_rs_levels(h)):
+            rows, cols, nnz = C.c_int64(), C.c_int64(), C.c_int64()
+            lib().mgbx_rs_get(h, l, C.byref(rows), C.byref(cols), C.byref(nnz), None, None, None)
+            ptr, ind, val = np.empty(rows.value + 1, np.int64), np.empty(nnz.value, np.int64), np.empty(nnz.value)
+            rc = lib().mgbx_rs_get(h, l, C.byref(rows), C.byref(cols), C.byref(nnz), _ptr(ptr, c_i64p), _ptr(ind, c_i64p), _ptr(val))
+            if rc != OK:
+                raise MgbxError(rc, "mgbx_rs_get")
+            Ps.append(sp.csr_matrix((val, ind, ptr), shape=(rows.value, cols.value)))
+        return Ps
+    finally:
+        lib().mgbx_rs_destroy(h)
 
 
 def kron_factor(M, r1, r2, c1, c2):

@@ -190,3 +190,41 @@ def test_kronecker_structure_of_the_spectral2d_operators_and_prolongations():
     Cm = AA @ W.T                                                    # [(i, l), (i', l')]
     out = Cm.reshape(c, c, c, c).transpose(0, 2, 1, 3).reshape(c * c, c * c)   # -> [(i, i'), (l, l')]
     assert np.abs(out - ref).max() <= 1e-10 * np.abs(ref).max()
+
+
+def test_cpp_ruge_stuben_is_bitwise_the_host_mirror():
+    """mgbx_rs_* (csrc/host_amg.hpp): the classical Ruge-Stueben hierarchy in C++ against hierarchy.ruge_stuben (numba) -- the same
+    number of levels and bitwise the same prolongations (pattern and values) on 2-D P1 / P2, 3-D Q1 / Q2 stiffness matrices and on a
+    random SPD matrix with positive off-diagonals; then whole amg() hierarchies built on either implementation are identical."""
+    import scipy.sparse as sp
+    from mgbx import geometry as G, hierarchy as H
+
+    def same(Pa, Pb):
+        assert len(Pa) == len(Pb), (len(Pa), len(Pb))
+        for a, b in zip(Pa, Pb):
+            a, b = sp.csr_matrix(a), sp.csr_matrix(b)
+            a.sort_indices()
+            b.sort_indices()
+            assert a.shape == b.shape
+            assert np.array_equal(a.indptr, b.indptr) and np.array_equal(a.indices, b.indices)
+            assert np.array_equal(a.data, b.data)
+
+    captured = []
+    for g in (G.subdivide(G.fem2d_P1(), 5), G.subdivide(G.fem2d_P2(), 3), G.structured_box(3, 7, k=1), G.subdivide(G.fem3d(k=2), 3),
+              G.structured_triangles(11)):
+        H.amg(g, prolongator=lambda K: (captured.append(sp.csr_matrix(K)), H.ruge_stuben(K, max_coarse=2))[1])
+    assert len(captured) >= 8
+    for K in captured:
+        same(native.ruge_stuben(K, max_coarse=2), H.ruge_stuben(K, max_coarse=2))
+    rng = np.random.default_rng(4)
+    R = sp.random(300, 300, density=0.02, random_state=5, format="csr")
+    K = (R + R.T + sp.identity(300) * 3.0).tocsr()
+    K.data[::7] *= -1.0
+    K = (K + K.T).tocsr()
+    same(native.ruge_stuben(K, max_coarse=10, theta=0.5), H.ruge_stuben(K, max_coarse=10, theta=0.5))
+    # whole hierarchies
+    g = G.structured_box(3, 6, k=1)
+    ma, mb = H.amg(g), H.amg(g, prolongator=H.amg_ruge_stuben_native())
+    for X in ma.R:
+        same(ma.R[X], mb.R[X])
+        same(ma.T[X], mb.T[X])
